@@ -1,0 +1,162 @@
+/*
+ * rxm.h -- C ABI of the B200 batch matcher ("rxm" = regex/MFA matcher).
+ *
+ * This is the drop-in boundary for ONE path of Danya-Is/re2-modification: the
+ * per-string automaton simulation that `./diploma -match` runs once per input
+ * token.  Everything before it (parse, bnf, reverse, automaton construction)
+ * stays the reference's own C++ on the CPU; a flattening stage
+ * (re2-modification_b200/csrc/rxm_flatten.hpp) turns the object graph that
+ * Regexp::compile returns into the plain-old-data `rxm_tables` below, and the
+ * entry points here replace, for whole batches,
+ *
+ *     bool MFA::match(string str)               automata.h:69,  mfa.cpp:215-236
+ *     bool Automata::match(const string& str)   automata.h:42,  automata.cpp:177-210
+ *
+ * as called from the `-match` loop, matchers/match.cpp:22-31.  The reference has
+ * no FFI of its own; a maintainer binds these functions
+ * from match.cpp directly -- see INTEGRATION.md.
+ *
+ * Rules of the boundary
+ *   - plain C: pointers and sizes only, no C++/torch types; never throws;
+ *   - every function returns an `int` status (RXM_OK == 0) except rxm_strerror;
+ *   - there is NO CPU fallback: without a usable CUDA device every compute
+ *     entry point returns RXM_ERR_NO_DEVICE / RXM_ERR_CUDA;
+ *   - result bits are bit-exact with the reference for the same
+ *     (expression, flags, string); see DESIGN.md for the canonical tie-break.
+ */
+#ifndef RXM_H
+#define RXM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RXM_ABI_VERSION 1u
+
+/* ---- status codes ------------------------------------------------------- */
+enum {
+    RXM_OK = 0,
+    RXM_ERR_INVALID = 1,      /* NULL / malformed argument or table            */
+    RXM_ERR_UNSUPPORTED = 2,  /* automaton outside device limits (NOT a fallback) */
+    RXM_ERR_NO_DEVICE = 3,    /* no CUDA device / bad ordinal                  */
+    RXM_ERR_CUDA = 4,         /* a CUDA runtime call failed; see rxm_last_cuda_error */
+    RXM_ERR_NOMEM = 5,        /* host or device allocation failed              */
+    RXM_ERR_PARSE = 6,        /* rxm_tables_parse: bad text                    */
+    RXM_ERR_OVERFLOW = 7      /* a string exceeded a kernel limit (reported, never guessed) */
+};
+
+/* ---- automaton tables (host, plain old data) ----------------------------- */
+enum { RXM_KIND_NFA = 0, RXM_KIND_MFA = 1 };
+
+/* Edge kinds.  `by` is the label string of Edge / MemoryEdge (edge.h:15,34-49). */
+enum {
+    RXM_EDGE_EPS = 0,   /* by == "" (or "ε" after MFA::makeDOTFile, mfa.cpp:40-42) */
+    RXM_EDGE_LIT = 1,   /* by is one byte, compared as text with the input byte
+                           (automata.cpp:111, mfa.cpp:171); edge_sym = that byte.
+                           In an MFA the bytes '1'..'9' ALSO name a memory cell
+                           (mfa.cpp:148,176) -- the kernels apply both meanings
+                           in the reference's order.                              */
+    RXM_EDGE_ANY = 2,   /* by == "."  : matches every input byte                  */
+    RXM_EDGE_NEVER = 3  /* any other label (e.g. `string(&rune)` garbage,
+                           bt_thomson.cpp:11): can never fire; kept for edge order */
+};
+
+#define RXM_MAX_CELLS 9u      /* README.md:22: cells are named 1..9              */
+#define RXM_MAX_STATES 4096u  /* table format limit (kernels have their own)     */
+
+/*
+ * Structure-of-arrays transition table in CSR form.  States are numbered by the
+ * ADDRESS RANK of the reference's Node* / MemoryNode* objects (that is the
+ * iteration order of std::set<Node*> / std::set<MemoryState>, automata.h:12-13,
+ * automata.cpp:122, mfa.cpp:206); a state's edges keep std::list order
+ * (node.h:13,29).  Only states reachable from `start` (plus `finish`) appear.
+ */
+typedef struct rxm_tables {
+    uint32_t abi_version;  /* RXM_ABI_VERSION */
+    uint32_t kind;         /* RXM_KIND_NFA | RXM_KIND_MFA  (is_mfa of Regexp::compile) */
+    uint32_t reversed;     /* Automata::is_reversed / MFA::is_reversed (automata.h:24,55) */
+    uint32_t n_states;
+    uint32_t n_edges;
+    uint32_t start;
+    uint32_t finish;
+    uint32_t n_cells;      /* highest memory-cell id used by any edge, 0..9        */
+    const uint32_t *edge_begin; /* [n_states + 1]  CSR row starts                 */
+    const uint8_t *edge_kind;   /* [n_edges]  RXM_EDGE_*                          */
+    const uint8_t *edge_sym;    /* [n_edges]  literal byte for RXM_EDGE_LIT, else 0 */
+    const uint16_t *edge_to;    /* [n_edges]  target state                        */
+    const uint16_t *edge_open;  /* [n_edges]  bit (k-1) set: memoryActions["k"] == open  (edge.h:29-32) */
+    const uint16_t *edge_close; /* [n_edges]  bit (k-1) set: memoryActions["k"] == close */
+} rxm_tables;
+
+/* Text form of a table (one automaton), used for fixtures and for handing a
+ * table from the flattening stage to another process.  rxm_tables_parse
+ * allocates ONE block owned by the caller: release with rxm_tables_release.  */
+int rxm_tables_format(const rxm_tables *t, char *buf, size_t buf_size, size_t *needed);
+int rxm_tables_parse(const char *text, size_t len, rxm_tables **out);
+void rxm_tables_release(rxm_tables *t);
+int rxm_tables_validate(const rxm_tables *t);
+
+/* ---- device side ---------------------------------------------------------- */
+typedef struct rxm_matcher *rxm_handle;
+
+/* Which kernel family the host planner picked for a table. */
+enum {
+    RXM_ENGINE_K1_DFA = 1,     /* memory-free automaton, determinised with the reference's exact step */
+    RXM_ENGINE_K1_BITSET = 2,  /* memory-free automaton, bit-parallel active-set kernel             */
+    RXM_ENGINE_K2_THREAD = 3,  /* MFA, one thread per string                                        */
+    RXM_ENGINE_K3_WARP = 4     /* MFA, one warp per string (long strings / large automata)          */
+};
+
+typedef struct rxm_plan_info {
+    uint32_t engine;        /* RXM_ENGINE_*                                        */
+    uint32_t dfa_states;    /* K1_DFA: reachable active sets (incl. dead state)    */
+    uint32_t dfa_classes;   /* K1_DFA: byte classes                                */
+    uint32_t exact_step_differs; /* memory-free: #(set,letter) pairs where the reference's
+                                    `visited` step (automata.cpp:104-107) differs from the
+                                    textbook step -- informational                   */
+    uint32_t n_states;
+    uint32_t n_edges;
+    uint32_t n_cells;
+    uint32_t reversed;
+    uint32_t sm_count;
+    uint32_t reserved[7];
+} rxm_plan_info;
+
+/* Copies `host_tables` (caller keeps ownership), plans, uploads to `device`. */
+int rxm_tables_upload(const rxm_tables *host_tables, int device, rxm_handle *out);
+int rxm_plan_query(rxm_handle h, rxm_plan_info *info);
+int rxm_free(rxm_handle h);
+
+/*
+ * Match strings i = 0..n-1, string i = chars[offsets[i] .. offsets[i+1]).
+ * Writes out_bits[i] = 0 or 1 (one BYTE per string, like the `0`/`1` lines of
+ * match.cpp:29).  `chars`, `offsets`, `out_bits` may each be a device pointer
+ * (on the handle's device) or a host pointer (pageable or pinned); host
+ * buffers are staged through the handle's device workspace inside the call.
+ * `stream` is a cudaStream_t (NULL = default stream).  With device pointers the
+ * call is asynchronous on `stream`; with any host pointer it returns after the
+ * results are in `out_bits`.  Calls on one handle must be serialised by the
+ * caller; different handles may be used concurrently.
+ */
+int rxm_match_batch(rxm_handle h, const uint8_t *chars, const uint64_t *offsets, uint64_t n,
+                    uint8_t *out_bits, void *stream);
+
+/* Number of kernels of this library launched through `h` so far. */
+int rxm_launch_count(rxm_handle h, uint64_t *launches);
+
+/* Strings whose simulation hit a kernel limit in the LAST rxm_match_batch on
+ * `h` (frontier recursion depth).  Their out_bits are 0 and the call returns
+ * RXM_ERR_OVERFLOW when the count is non-zero and the buffers were host
+ * buffers; with device buffers query this after synchronising the stream.     */
+int rxm_overflow_count(rxm_handle h, uint64_t *count);
+
+const char *rxm_strerror(int status);
+const char *rxm_last_cuda_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RXM_H */

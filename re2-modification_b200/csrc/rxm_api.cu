@@ -1,0 +1,269 @@
+// C-ABI launch layer (include/rxm.h) + kernel launches.  sm_100a only.
+//
+// No CPU fallback lives here: if the CUDA runtime cannot provide the requested
+// device every compute entry point returns an error status.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/rxm.h"
+#include "rxm_host_tables.hpp"
+#include "rxm_kernels.cuh"
+#include "rxm_mfa_dispatch.hpp"
+#include "rxm_plan.hpp"
+
+namespace {
+
+thread_local char g_cuda_err[512] = "";
+
+int cuda_fail(cudaError_t e, const char *what) {
+    std::snprintf(g_cuda_err, sizeof g_cuda_err, "%s: %s", what, cudaGetErrorString(e));
+    return RXM_ERR_CUDA;
+}
+#define CU(call)                                        \
+    do {                                                \
+        cudaError_t e_ = (call);                        \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+    } while (0)
+
+template <class T>
+int upload_vec(const std::vector<T> &v, T **dptr) {
+    *dptr = nullptr;
+    if (v.empty()) return RXM_OK;
+    CU(cudaMalloc(reinterpret_cast<void **>(dptr), v.size() * sizeof(T)));
+    CU(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return RXM_OK;
+}
+
+}  // namespace
+
+struct rxm_matcher {
+    int device = 0;
+    int sm_count = 0;
+    rxm::HostTables tables;
+    rxm_plan_info info{};
+
+    // K1: determinised automaton
+    rxm::DfaPlan dfa;
+    rxm::K1Tables k1{};
+    uint8_t *d_k1_table = nullptr;   // direct: [256][SP] u8 ; classed: see rxm_kernels.cuh
+    uint8_t *d_k1_accept = nullptr;
+
+    // K2: MFA tables
+    uint16_t *d_edge_begin = nullptr;
+    uint64_t *d_edges = nullptr;
+
+    // staging workspace for host buffers
+    uint8_t *d_chars = nullptr;
+    size_t cap_chars = 0;
+    uint64_t *d_offsets = nullptr;
+    uint8_t *d_bits = nullptr;
+    size_t cap_n = 0;
+
+    unsigned long long *d_overflow = nullptr;  // strings that hit a kernel limit
+    uint64_t launches = 0;
+    uint64_t last_overflow = 0;
+};
+
+static bool is_device_ptr(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+extern "C" const char *rxm_last_cuda_error(void) { return g_cuda_err; }
+
+extern "C" int rxm_tables_upload(const rxm_tables *host_tables, int device, rxm_handle *out) {
+    if (!out) return RXM_ERR_INVALID;
+    *out = nullptr;
+    int st = rxm_tables_validate(host_tables);
+    if (st != RXM_OK) return st;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cuda_fail(e, "cudaGetDeviceCount");
+        cudaGetLastError();
+        return RXM_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= ndev) return RXM_ERR_NO_DEVICE;
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+
+    rxm_matcher *m = new (std::nothrow) rxm_matcher();
+    if (!m) return RXM_ERR_NOMEM;
+    m->device = device;
+    m->sm_count = prop.multiProcessorCount;
+    m->tables.assign(*host_tables);
+    const rxm_tables t = m->tables.view();
+    m->info.n_states = t.n_states;
+    m->info.n_edges = t.n_edges;
+    m->info.n_cells = t.n_cells;
+    m->info.reversed = t.reversed;
+    m->info.sm_count = uint32_t(m->sm_count);
+    std::string err;
+
+    auto fail = [&](int code) {
+        if (!err.empty()) std::snprintf(g_cuda_err, sizeof g_cuda_err, "%s", err.c_str());
+        rxm_free(m);
+        return code;
+    };
+
+    if (t.kind == RXM_KIND_NFA) {
+        st = rxm::plan_dfa(t, m->dfa, &err);
+        if (st != RXM_OK) return fail(st);
+        std::vector<uint8_t> table, accept;
+        st = rxm::k1_build_tables(m->dfa, m->k1, table, accept, &err);
+        if (st != RXM_OK) return fail(st);
+        if ((st = upload_vec(table, &m->d_k1_table)) != RXM_OK) return fail(st);
+        if ((st = upload_vec(accept, &m->d_k1_accept)) != RXM_OK) return fail(st);
+        m->info.engine = RXM_ENGINE_K1_DFA;
+        m->info.dfa_states = m->dfa.n_states;
+        m->info.dfa_classes = m->dfa.n_classes;
+        m->info.exact_step_differs = m->dfa.exact_step_differs;
+    } else {
+        st = rxm::check_mfa(t, &err);
+        if (st != RXM_OK) return fail(st);
+        if (t.n_states > RXM_MFA_MAX_STATES) {
+            err = "MFA with more than " + std::to_string(RXM_MFA_MAX_STATES) + " states";
+            return fail(RXM_ERR_UNSUPPORTED);
+        }
+        std::vector<uint16_t> eb(t.n_states + 1);
+        for (uint32_t q = 0; q <= t.n_states; q++) eb[q] = uint16_t(t.edge_begin[q]);
+        std::vector<uint64_t> er(t.n_edges);
+        for (uint32_t i = 0; i < t.n_edges; i++)
+            er[i] = rxm::pack_edge(t.edge_kind[i], t.edge_sym[i], t.edge_to[i], t.edge_open[i],
+                                   t.edge_close[i]);
+        if (t.n_edges > 8000) {
+            err = "MFA with more than 8000 edges";
+            return fail(RXM_ERR_UNSUPPORTED);
+        }
+        if ((st = upload_vec(eb, &m->d_edge_begin)) != RXM_OK) return fail(st);
+        if ((st = upload_vec(er, &m->d_edges)) != RXM_OK) return fail(st);
+        m->info.engine = RXM_ENGINE_K2_THREAD;
+    }
+    if (cudaMalloc(reinterpret_cast<void **>(&m->d_overflow), sizeof(unsigned long long)) != cudaSuccess)
+        return fail(cuda_fail(cudaGetLastError(), "cudaMalloc overflow counter"));
+    CU(cudaMemset(m->d_overflow, 0, sizeof(unsigned long long)));
+    *out = m;
+    return RXM_OK;
+}
+
+extern "C" int rxm_plan_query(rxm_handle h, rxm_plan_info *info) {
+    if (!h || !info) return RXM_ERR_INVALID;
+    *info = h->info;
+    return RXM_OK;
+}
+
+extern "C" int rxm_free(rxm_handle h) {
+    if (!h) return RXM_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_k1_table);
+    cudaFree(h->d_k1_accept);
+    cudaFree(h->d_edge_begin);
+    cudaFree(h->d_edges);
+    cudaFree(h->d_chars);
+    cudaFree(h->d_offsets);
+    cudaFree(h->d_bits);
+    cudaFree(h->d_overflow);
+    delete h;
+    return RXM_OK;
+}
+
+extern "C" int rxm_launch_count(rxm_handle h, uint64_t *launches) {
+    if (!h || !launches) return RXM_ERR_INVALID;
+    *launches = h->launches;
+    return RXM_OK;
+}
+
+extern "C" int rxm_overflow_count(rxm_handle h, uint64_t *count) {
+    if (!h || !count) return RXM_ERR_INVALID;
+    unsigned long long v = 0;
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpy(&v, h->d_overflow, sizeof v, cudaMemcpyDeviceToHost));
+    h->last_overflow = v;
+    *count = v;
+    return RXM_OK;
+}
+
+static int launch_on_device(rxm_matcher *m, const uint8_t *d_chars, const uint64_t *d_offsets,
+                            uint64_t n, uint8_t *d_out, cudaStream_t stream) {
+    CU(cudaMemsetAsync(m->d_overflow, 0, sizeof(unsigned long long), stream));
+    if (n == 0) return RXM_OK;
+    int launched = 0;
+    int st;
+    if (m->info.engine == RXM_ENGINE_K1_DFA) {
+        st = rxm::k1_launch(m->k1, m->d_k1_table, m->d_k1_accept, d_chars, d_offsets, n, d_out,
+                            m->sm_count, stream, &launched);
+    } else {
+        rxm::MfaView v{m->d_edge_begin, m->d_edges, m->tables.n_states(), m->tables.start,
+                       m->tables.finish, m->tables.reversed};
+        st = rxm::k2_launch(v, m->tables.n_cells, m->tables.n_edges(), d_chars, d_offsets, n, d_out,
+                            m->d_overflow, m->sm_count, stream, &launched);
+    }
+    m->launches += uint64_t(launched);
+    if (st != RXM_OK) return st;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    return RXM_OK;
+}
+
+extern "C" int rxm_match_batch(rxm_handle h, const uint8_t *chars, const uint64_t *offsets,
+                               uint64_t n, uint8_t *out_bits, void *stream_) {
+    if (!h || !offsets || (n && !out_bits)) return RXM_ERR_INVALID;
+    rxm_matcher *m = h;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CU(cudaSetDevice(m->device));
+
+    const bool dev_off = is_device_ptr(offsets);
+    const bool dev_out = is_device_ptr(out_bits);
+    const bool dev_chars = chars ? is_device_ptr(chars) : dev_off;
+    if (dev_off && dev_out && dev_chars)
+        return launch_on_device(m, chars, offsets, n, out_bits, stream);
+    if (dev_off || dev_out || (chars && dev_chars)) return RXM_ERR_INVALID;  // all host or all device
+
+    // host buffers: stage through the handle's workspace
+    const uint64_t total = offsets[n];
+    if (offsets[0] != 0 && !chars) return RXM_ERR_INVALID;
+    for (uint64_t i = 0; i < n; i++)
+        if (offsets[i] > offsets[i + 1]) return RXM_ERR_INVALID;
+    if (total && !chars) return RXM_ERR_INVALID;
+    if (total + 64 > m->cap_chars) {
+        cudaFree(m->d_chars);
+        m->d_chars = nullptr;
+        m->cap_chars = 0;
+        const size_t want = size_t(total + 64 + (total >> 3));
+        CU(cudaMalloc(reinterpret_cast<void **>(&m->d_chars), want));
+        m->cap_chars = want;
+    }
+    if (n + 1 > m->cap_n) {
+        cudaFree(m->d_offsets);
+        cudaFree(m->d_bits);
+        m->d_offsets = nullptr;
+        m->d_bits = nullptr;
+        m->cap_n = 0;
+        const size_t want = size_t(n + 1 + (n >> 3));
+        CU(cudaMalloc(reinterpret_cast<void **>(&m->d_offsets), want * sizeof(uint64_t)));
+        CU(cudaMalloc(reinterpret_cast<void **>(&m->d_bits), want));
+        m->cap_n = want;
+    }
+    if (total) CU(cudaMemcpyAsync(m->d_chars, chars, total, cudaMemcpyHostToDevice, stream));
+    CU(cudaMemcpyAsync(m->d_offsets, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+    int st = launch_on_device(m, m->d_chars, m->d_offsets, n, m->d_bits, stream);
+    if (st != RXM_OK) return st;
+    unsigned long long ovf = 0;
+    if (n) CU(cudaMemcpyAsync(out_bits, m->d_bits, n, cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpyAsync(&ovf, m->d_overflow, sizeof ovf, cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    m->last_overflow = ovf;
+    return ovf ? RXM_ERR_OVERFLOW : RXM_OK;
+}

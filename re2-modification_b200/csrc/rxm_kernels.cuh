@@ -1,0 +1,47 @@
+// Kernel-side declarations shared by rxm_api.cu and rxm_kernels.cu.
+#ifndef RXM_KERNELS_CUH
+#define RXM_KERNELS_CUH
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/rxm.h"
+#include "rxm_mfa_core.cuh"
+#include "rxm_plan.hpp"
+
+namespace rxm {
+
+// ---- K1: determinised memory-free automaton ------------------------------------------
+enum : uint32_t {
+    K1_DIRECT = 0,   // T[byte][SP] u8, SP = 2^log2sp >= n_states, one shared-memory lookup per byte
+    K1_CLASSED = 1   // cmap[256] u8 then trans[class][n_states] u16: two lookups per byte
+};
+
+struct K1Tables {
+    uint32_t mode;
+    uint32_t log2sp;       // K1_DIRECT
+    uint32_t n_states;
+    uint32_t n_classes;
+    uint32_t start;
+    uint32_t reversed;
+    uint32_t table_bytes;  // bytes of the device table blob (copied to shared memory)
+    uint32_t accept_bytes;
+};
+
+int k1_build_tables(const DfaPlan &p, K1Tables &kt, std::vector<uint8_t> &table,
+                    std::vector<uint8_t> &accept, std::string *err);
+
+int k1_launch(const K1Tables &kt, const uint8_t *d_table, const uint8_t *d_accept,
+              const uint8_t *d_chars, const uint64_t *d_offsets, uint64_t n, uint8_t *d_out,
+              int sm_count, cudaStream_t stream, int *launched);
+
+// ---- K2: MFA, one thread per string ------------------------------------------------------
+int k2_launch(const MfaView &dev_view, uint32_t n_cells, uint32_t n_edges, const uint8_t *d_chars,
+              const uint64_t *d_offsets, uint64_t n, uint8_t *d_out, unsigned long long *d_overflow,
+              int sm_count, cudaStream_t stream, int *launched);
+
+}  // namespace rxm
+#endif

@@ -1,0 +1,64 @@
+// TEST INFRASTRUCTURE.  Compiles the kernels' shared simulation core
+// (re2-modification_b200/csrc/rxm_mfa_core.cuh) for the HOST so that its logic
+// can be compared with the oracle in the CPU test tier, before GPU time is
+// spent.  It is built into tests/hostsim/libhostsim.so and loaded only by
+// tests; librxm.so does not contain or call it.
+#include <cstdint>
+#include <vector>
+
+#include "../../include/rxm.h"
+#include "../../re2-modification_b200/csrc/rxm_mfa_core.cuh"
+#include "../../re2-modification_b200/csrc/rxm_mfa_dispatch.hpp"
+#include "../../re2-modification_b200/csrc/rxm_plan.hpp"
+
+template <int NC, int CAP, int DMAX>
+static void run_batch(const rxm::MfaView &v, const uint8_t *chars, const uint64_t *off, uint64_t n,
+                      uint8_t *out) {
+    auto *sim = new rxm::MfaSim<NC, CAP, DMAX>();
+    for (uint64_t i = 0; i < n; i++) {
+        rxm::Reader rd{chars + off[i], uint32_t(off[i + 1] - off[i]), v.reversed};
+        out[i] = uint8_t(sim->run(v, rd));
+    }
+    delete sim;
+}
+
+extern "C" int hostsim_mfa_batch(const rxm_tables *t, const uint8_t *chars, const uint64_t *off,
+                                 uint64_t n, uint8_t *out) {
+    std::vector<uint16_t> eb(t->n_states + 1);
+    for (uint32_t q = 0; q <= t->n_states; q++) eb[q] = uint16_t(t->edge_begin[q]);
+    std::vector<uint64_t> er(t->n_edges);
+    for (uint32_t e = 0; e < t->n_edges; e++)
+        er[e] = rxm::pack_edge(t->edge_kind[e], t->edge_sym[e], t->edge_to[e], t->edge_open[e],
+                               t->edge_close[e]);
+    rxm::MfaView v{eb.data(), er.data(), t->n_states, t->start, t->finish, t->reversed};
+    bool rxm_dispatch_ok = true;
+#define CALL(NC, CAP, DMAX) run_batch<NC, CAP, DMAX>(v, chars, off, n, out)
+    RXM_MFA_DISPATCH(t->n_cells, t->n_states, CALL);
+#undef CALL
+    return rxm_dispatch_ok ? 0 : 2;
+}
+
+// DFA built by the planner, stepped on the host (checks plan_dfa against the oracle).
+extern "C" int hostsim_dfa_batch(const rxm_tables *t, const uint8_t *chars, const uint64_t *off,
+                                 uint64_t n, uint8_t *out, uint32_t *info3) {
+    rxm::DfaPlan p;
+    std::string err;
+    int st = rxm::plan_dfa(*t, p, &err);
+    if (st != RXM_OK) return st;
+    if (info3) {
+        info3[0] = p.n_states;
+        info3[1] = p.n_classes;
+        info3[2] = p.exact_step_differs;
+    }
+    for (uint64_t i = 0; i < n; i++) {
+        const uint8_t *s = chars + off[i];
+        const uint64_t len = off[i + 1] - off[i];
+        uint32_t q = p.start;
+        for (uint64_t j = 0; j < len && q; j++) {
+            const uint8_t b = p.reversed ? s[len - 1 - j] : s[j];
+            q = p.trans[size_t(p.byte_class[b]) * p.n_states + q];
+        }
+        out[i] = p.accept[q];
+    }
+    return 0;
+}
