@@ -1,0 +1,484 @@
+#!/usr/bin/env python3
+"""Headline benchmark of the batch matcher (BASELINE.json metric / configs[1]).
+
+One "step" = one pass of the hot path (rxm_match_batch, include/rxm.h) over one
+batch of synthetic strings.  Default workload at any N: per GPU, 1 000 000 random
+{a,b} strings of 64-4096 chars against the config-2 expression
+(a|bb)*aaba(a|bb*aa)* -- the "alive" set of SURVEY.md 8d (random walks on the
+automaton, last letter flipped for half of them), because i.i.d. uniform strings
+die within a few letters and would time the early exit, not the scan.  The
+uniform set is timed too and reported under "uniform_iid".
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--strings S] [--workload config2|config3]
+  python bench.py --impl reference ...      the reference's own CPU code on host cores
+
+Under torchrun each rank drives its own GPU on its own shard (strings are
+independent: no data-path collective); times are max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib.util
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "re2-modification_b200")
+CASES = os.path.join(ROOT, "tests", "golden", "cases")
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+WORKLOADS = {
+    # name: (table fixture, expression, flags, description)
+    "config2": ("nfa_config2", "(a|bb)*aaba(a|bb*aa)*", [],
+                "config2: (a|bb)*aaba(a|bb*aa)* on random {a,b} strings of 64-4096 chars "
+                "(alive random-walk set, last letter flipped for 50%)"),
+    "config3": ("ex05_fwd", "{a*}:1c{&1}:2c(&1|&2)*", [],
+                "config3: example 5 {a*}:1c{&1}:2c(&1|&2)* on x c x c x^m strings of 64-4096 chars, "
+                "50% corrupted in the last block"),
+}
+
+
+def _load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def make_workload(W, name, table_text, n, seed, device, uniform=False):
+    if name == "config2":
+        if uniform:
+            return W.uniform_strings(n, 64, 4096, b"ab", seed, device)
+        return W.alive_strings(table_text, n, 64, 4096, seed, device)
+    if name == "config3":
+        return W.example5_strings(n, 64, 4096, seed, device)
+    raise SystemExit(f"unknown workload {name}")
+
+
+# --------------------------------------------------------------------------------------
+# reference CPU implementation (oracle/_ref, or the C port when it is absent)
+# --------------------------------------------------------------------------------------
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference_parallel(binary, regex, flags, chars, offsets, procs):
+    """`procs` processes of the reference's -match code, each on a contiguous shard.
+    Returns (wall seconds of the slowest match loop, bits)."""
+    n = len(offsets) - 1
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "in.rxmb")
+        with open(path, "wb") as f:
+            f.write(b"RXMBATCH")
+            f.write(np.uint64(n).tobytes())
+            f.write(np.uint64(len(chars)).tobytes())
+            f.write(np.ascontiguousarray(offsets, dtype=np.uint64).tobytes())
+            f.write(np.ascontiguousarray(chars, dtype=np.uint8).tobytes())
+        per = (n + procs - 1) // procs
+        jobs = []
+        for p in range(procs):
+            lo, hi = min(n, p * per), min(n, (p + 1) * per)
+            if lo >= hi:
+                continue
+            wd = os.path.join(td, f"w{p}")
+            os.makedirs(wd)
+            out = os.path.join(wd, "out.bits")
+            cmd = [binary, "-match", *flags, "-regex", regex, "-batch", path, out,
+                   "-range", str(lo), str(hi)]
+            jobs.append((lo, hi, out, subprocess.Popen(cmd, cwd=wd, stdout=subprocess.DEVNULL,
+                                                       stderr=subprocess.PIPE)))
+        bits = np.zeros(n, dtype=np.uint8)
+        slowest = 0.0
+        for lo, hi, out, pr in jobs:
+            _, err = pr.communicate()
+            if pr.returncode != 0:
+                raise RuntimeError(f"reference process failed: {err.decode()[-300:]}")
+            for line in err.decode().splitlines():
+                if line.startswith("ORACLE_TIME"):
+                    slowest = max(slowest, float(line.split()[1]))
+            bits[lo:hi] = np.fromfile(out, dtype=np.uint8)
+        return slowest, bits
+
+
+def run_port(tables, chars, offsets):
+    """The C restatement (oracle/librxm_oracle.so), one thread."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers as H
+    t0 = time.perf_counter()
+    bits = H.oracle_bits(tables, chars, offsets)
+    return time.perf_counter() - t0, bits
+
+
+def cpu_sample(W, wl, table_text, per_core, cores, seed):
+    import torch
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    chars, offsets = make_workload(W, wl, table_text, per_core * cores, seed, dev)
+    return chars.cpu().numpy(), offsets.cpu().numpy().astype(np.uint64)
+
+
+def reference_binary():
+    for b in ("diploma_ref_O2", "diploma_ref"):
+        p = os.path.join(REF_DIR, b)
+        if os.path.exists(p):
+            return p, b
+    return None, None
+
+
+def cpu_baseline(W, rxm, wl, tables, regex, flags):
+    """Reference -match code on the host cores, on a bounded sample of the workload."""
+    cores = host_cores()
+    res = {}
+    binary, bname = reference_binary()
+    if binary:
+        per_core = 1500 if wl == "config2" else 60
+        chars, offsets = cpu_sample(W, wl, tables.text, per_core, cores, 4242)
+        n = len(offsets) - 1
+        t_all, _ = run_reference_parallel(binary, regex, flags, chars, offsets, cores)
+        one = slice(0, per_core + 1)
+        o1 = offsets[one]
+        t_one, _ = run_reference_parallel(binary, regex, flags, chars[:int(o1[-1])], o1, 1)
+        res = {
+            "value": n / t_all, "unit": "strings/s", "cores": cores, "kind": "reference",
+            "build": bname + " (unmodified reference sources, -O2; upstream CMake sets no -O flag)",
+            "sample": f"{n} strings ({int(offsets[-1])} bytes) of the same workload, "
+                      f"{cores} processes x {per_core} strings, string-parallel",
+            "input_mb_s": float(offsets[-1]) / t_all / 1e6,
+            "single_thread": {"value": per_core / t_one, "unit": "strings/s", "cores": 1,
+                              "sample": f"{per_core} strings"},
+        }
+        o0 = os.path.join(REF_DIR, "diploma_ref")
+        if os.path.exists(o0) and bname != "diploma_ref":
+            k = max(1, per_core // 8)
+            ok = offsets[:k + 1]
+            t0, _ = run_reference_parallel(o0, regex, flags, chars[:int(ok[-1])], ok, 1)
+            res["single_thread_O0_upstream_flags"] = {"value": k / t0, "unit": "strings/s",
+                                                       "cores": 1, "sample": f"{k} strings"}
+    else:
+        per = 20000 if wl == "config2" else 2000
+        chars, offsets = cpu_sample(W, wl, tables.text, per, 1, 4242)
+        t, _ = run_port(tables, chars, offsets)
+        res = {"value": per / t, "unit": "strings/s", "cores": 1, "kind": "port",
+               "sample": f"{per} strings ({int(offsets[-1])} bytes) of the same workload, "
+                         "C restatement oracle/rxm_oracle.c, one thread",
+               "input_mb_s": float(offsets[-1]) / t / 1e6}
+    return res
+
+
+def reference_arm(args, W, rxm):
+    """--impl reference: the reference's CPU implementation, all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    wl = args.workload
+    case, regex, flags, desc = WORKLOADS[wl]
+    tables = rxm.Tables.load(os.path.join(CASES, case + ".rxt"))
+    cores = host_cores()
+    binary, bname = reference_binary()
+    per_core = 1500 if wl == "config2" else 60
+    chars, offsets = cpu_sample(W, wl, tables.text, per_core, cores if binary else 1, 4242)
+    n = len(offsets) - 1
+    times = []
+    for step in range(args.warmup + args.steps):
+        if binary:
+            t, _ = run_reference_parallel(binary, regex, flags, chars, offsets, cores)
+        else:
+            t, _ = run_port(tables, chars, offsets)
+        if step >= args.warmup:
+            times.append(t)
+    total = sum(times)
+    value = n * len(times) / total
+    line = {
+        "impl": "reference", "metric": "strings_per_sec", "value": value, "unit": "strings/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": desc, "strings_per_step": n, "bytes_per_step": int(offsets[-1])},
+        "input_gb_s": float(offsets[-1]) * len(times) / total / 1e9,
+        "cpu_baseline": {"value": value, "unit": "strings/s",
+                         "cores": cores if binary else 1,
+                         "kind": "reference" if binary else "port",
+                         "build": (bname + " (-O2 build of the unmodified reference sources)") if binary
+                                  else "oracle/rxm_oracle.c",
+                         "sample": f"{n} strings per step, string-parallel over "
+                                   f"{cores if binary else 1} processes"},
+        "e2e": {"value": value, "unit": "strings/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_id):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(gpu_id)],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path).read().splitlines():
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+                power.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        # samples under load = the upper half by SM clock (idle samples bracket the region)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--strings", type=int, default=1_000_000, help="strings per GPU")
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rxm = _load("rxm", os.path.join(PKG, "rxm.py"))
+    W = _load("workloads", os.path.join(PKG, "workloads.py"))
+    if args.impl == "reference":
+        return reference_arm(args, W, rxm)
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    wl = args.workload
+    case, regex, flags, desc = WORKLOADS[wl]
+    tables = rxm.Tables.load(os.path.join(CASES, case + ".rxt"))
+    n = args.strings
+    chars, offsets = make_workload(W, wl, tables.text, n, 1000 + rank, dev)
+    total_bytes = int(offsets[-1])
+    out = torch.empty(n, dtype=torch.uint8, device=dev)
+    m = rxm.Matcher(tables, local_rank)
+    plan = m.plan()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_device():
+        m.match_ptrs(chars.data_ptr(), offsets.data_ptr(), n, out.data_ptr(), stream)
+
+    # ---- kernel-resident timing (inputs already in HBM) ---------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    props = torch.cuda.get_device_properties(local_rank)
+    gpu_id = getattr(props, "uuid", None)
+    gpu_id = f"GPU-{gpu_id}" if gpu_id and not str(gpu_id).startswith("GPU-") else (gpu_id or local_rank)
+    sampler = ClockSampler(gpu_id)
+    launches0 = m.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    # the timed region is padded so nvidia-smi (100 ms period) sees it
+    t_pad = time.perf_counter()
+    while time.perf_counter() - t_pad < 0.5:
+        step_device()
+        torch.cuda.synchronize()
+    launches0 = m.launch_count()
+    ev[0].record()
+    for k in range(args.steps):
+        step_device()
+        ev[k + 1].record()
+    barrier()
+    launches = m.launch_count() - launches0
+    while time.perf_counter() - t_pad < 1.2:
+        step_device()
+        torch.cuda.synchronize()
+    clocks = sampler.stop()
+    step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    total_ms = max_over_ranks(ev[0].elapsed_time(ev[args.steps]))
+    ms_per_step = total_ms / args.steps
+    n_all = sum_over_ranks(float(n))
+    bytes_all = sum_over_ranks(float(total_bytes))
+    value = n_all / (ms_per_step / 1e3)
+    if m.overflow_count():
+        raise SystemExit("bench.py: strings hit a kernel limit")
+
+    # ---- parity spot check against the oracle (outside every timed region) ---------------
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers as H
+    k_chk = min(n, 3000)
+    off_h = offsets[:k_chk + 1].cpu().numpy().astype(np.uint64)
+    chars_h = chars[:int(off_h[-1])].cpu().numpy()
+    want = H.oracle_bits(tables, chars_h, off_h)
+    got = out[:k_chk].cpu().numpy()
+    if not np.array_equal(got, want):
+        raise SystemExit(f"bench.py: {int((got != want).sum())} of {k_chk} bits differ from the oracle")
+    match_frac = float(out.float().mean().item())
+
+    # ---- end to end through the C ABI with HOST buffers -----------------------------------
+    h_chars = torch.empty(total_bytes, dtype=torch.uint8, pin_memory=True)
+    h_chars.copy_(chars)
+    h_off = torch.empty(n + 1, dtype=torch.int64, pin_memory=True)
+    h_off.copy_(offsets)
+    h_out = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    torch.cuda.synchronize()
+
+    def step_host():
+        m.match_ptrs(h_chars.data_ptr(), h_off.data_ptr(), n, h_out.data_ptr(), stream)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    if not torch.equal(h_out, out.cpu()):
+        raise SystemExit("bench.py: host-buffer path and device-pointer path disagree")
+    e2e_value = n_all * e2e_steps / e2e_s
+
+    # ---- uniform i.i.d. variant of config 2 (early exit) -----------------------------------
+    extra = {}
+    if wl == "config2":
+        del h_chars
+        u_chars, u_off = make_workload(W, wl, tables.text, n, 2000 + rank, dev, uniform=True)
+        for _ in range(3):
+            m.match_ptrs(u_chars.data_ptr(), u_off.data_ptr(), n, out.data_ptr(), stream)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            m.match_ptrs(u_chars.data_ptr(), u_off.data_ptr(), n, out.data_ptr(), stream)
+        e1.record()
+        barrier()
+        u_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        extra["uniform_iid"] = {
+            "note": "i.i.d. uniform {a,b} strings: the active set dies within a few letters "
+                    "(automata.cpp:186-188), so this times the early exit, not a scan",
+            "ms_per_step": u_ms, "strings_per_sec": n_all / (u_ms / 1e3),
+            "nominal_input_gb_s": sum_over_ranks(float(int(u_off[-1]))) / (u_ms / 1e3) / 1e9,
+            "match_fraction": float(out.float().mean().item()),
+        }
+        del u_chars, u_off
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak = float(json.load(open(peaks_path))["hbm_gbs"])
+            peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        else:
+            peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+        algo_bytes = total_bytes + 9 * n  # per launch on this rank: len + 8 B offset + 1 B result
+        k_ms = statistics.mean(step_ms)
+        achieved = algo_bytes / (k_ms / 1e3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", f"traffic_{wl}.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        line = {
+            "metric": "strings_per_sec", "value": value, "unit": "strings/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": desc, "strings_per_gpu": n, "bytes_per_gpu": total_bytes,
+                       "mean_len": total_bytes / n, "match_fraction": match_frac,
+                       "engine": rxm.ENGINE_NAMES.get(plan.engine, str(plan.engine)),
+                       "l2": "inputs (%.2f GB per GPU) are larger than the 126 MB L2" % (total_bytes / 1e9),
+                       "sharding": "by string index, one rank per GPU, no data-path collective"},
+            "input_gb_s": bytes_all / (ms_per_step / 1e3) / 1e9,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel_ms": k_ms,
+                         "algorithmic_bytes_per_launch": algo_bytes},
+            "e2e": {"value": e2e_value, "unit": "strings/s",
+                    "h2d_bytes_per_step": total_bytes + 8 * (n + 1), "d2h_bytes_per_step": n + 8,
+                    "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+                    "input_gb_s": bytes_all * e2e_steps / e2e_s / 1e9},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "parity_checked": k_chk,
+        }
+        line.update(extra)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(W, rxm, wl, tables, regex, flags)
+        print(json.dumps(line), flush=True)
+    m.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

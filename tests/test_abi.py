@@ -1,0 +1,66 @@
+"""CPU tier: the C-ABI library loads, exports every symbol include/rxm.h declares,
+and its host-only entry points (table text, validation) work.  No compute calls."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import helpers as H
+from cases import CASE_NAMES, load_case
+
+rxm = H.rxm
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(H.ROOT, "include", "rxm.h")).read()
+    declared = set(re.findall(r"\b(rxm_[a-z_]+)\s*\(", header))
+    declared -= {"rxm_handle"}
+    assert declared == set(rxm.ABI_SYMBOLS), declared ^ set(rxm.ABI_SYMBOLS)
+    L = C.CDLL(rxm.LIB_PATH)
+    for name in declared:
+        assert getattr(L, name) is not None
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_table_text_roundtrip(name):
+    t, _, _ = load_case(name)
+    text = t.format()
+    assert text == t.text
+    t2 = rxm.Tables(text)
+    assert t2.c.n_states == t.c.n_states and t2.c.n_edges == t.c.n_edges
+    assert rxm.lib().rxm_tables_validate(t2.ptr) == rxm.RXM_OK
+
+
+@pytest.mark.parametrize("bad", [
+    "", "rxm-tables 2\n", "rxm-tables 1\nkind dfa\n",
+    "rxm-tables 1\nkind nfa\nreversed 0\nstates 2\nstart 0\nfinish 5\ncells 0\nedges 0\nend\n",
+    "rxm-tables 1\nkind nfa\nreversed 0\nstates 2\nstart 0\nfinish 1\ncells 0\nedges 1\n0 L a 7\nend\n",
+    "rxm-tables 1\nkind nfa\nreversed 0\nstates 2\nstart 0\nfinish 1\ncells 0\nedges 1\n0 L a 1 o1\nend\n",
+    "rxm-tables 1\nkind mfa\nreversed 0\nstates 2\nstart 0\nfinish 1\ncells 1\nedges 1\n0 L a 1 o1 c1\nend\n",
+    "rxm-tables 1\nkind nfa\nreversed 0\nstates 2\nstart 0\nfinish 1\ncells 0\nedges 2\n0 L a 1\nend\n",
+])
+def test_table_parse_rejects_malformed(bad):
+    with pytest.raises(rxm.RxmError) as e:
+        rxm.Tables(bad)
+    assert e.value.status == rxm.RXM_ERR_PARSE
+
+
+def test_strerror_and_null_arguments():
+    assert rxm.strerror(rxm.RXM_OK) == "ok"
+    assert "fallback" in rxm.strerror(rxm.RXM_ERR_UNSUPPORTED)
+    L = rxm.lib()
+    assert L.rxm_tables_validate(None) == rxm.RXM_ERR_INVALID
+    assert L.rxm_match_batch(None, None, None, 0, None, None) == rxm.RXM_ERR_INVALID
+    assert L.rxm_free(None) == rxm.RXM_OK
+
+
+def test_no_device_is_an_error_not_a_fallback():
+    """Without a CUDA device the product path must fail loudly."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    t, _, _ = load_case("nfa_config2")
+    with pytest.raises(rxm.RxmError) as e:
+        rxm.Matcher(t, 0)
+    assert e.value.status in (rxm.RXM_ERR_NO_DEVICE, rxm.RXM_ERR_CUDA)
