@@ -65,6 +65,11 @@ struct rxm_matcher {
     uint8_t *d_bits = nullptr;
     size_t cap_n = 0;
 
+    // K1 bucket-pass workspace
+    rxm::K1Rec *d_recs = nullptr;
+    size_t cap_recs = 0;
+    uint32_t *d_hist = nullptr;          // [K1_BUCKETS] + task counter
+
     unsigned long long *d_overflow = nullptr;  // strings that hit a kernel limit
     uint64_t launches = 0;
     uint64_t last_overflow = 0;
@@ -175,6 +180,8 @@ extern "C" int rxm_free(rxm_handle h) {
     cudaFree(h->d_offsets);
     cudaFree(h->d_bits);
     cudaFree(h->d_overflow);
+    cudaFree(h->d_recs);
+    cudaFree(h->d_hist);
     delete h;
     return RXM_OK;
 }
@@ -202,8 +209,19 @@ static int launch_on_device(rxm_matcher *m, const uint8_t *d_chars, const uint64
     int launched = 0;
     int st;
     if (m->info.engine == RXM_ENGINE_K1_DFA) {
-        st = rxm::k1_launch(m->k1, m->d_k1_table, m->d_k1_accept, d_chars, d_offsets, n, d_out,
-                            m->sm_count, stream, &launched);
+        if (n > 0xfffffff0ull) return RXM_ERR_UNSUPPORTED;  // record index is 32 bits
+        if (n > m->cap_recs) {
+            cudaFree(m->d_recs);
+            m->d_recs = nullptr;
+            m->cap_recs = 0;
+            const size_t want = size_t(n + (n >> 3) + 32);
+            CU(cudaMalloc(reinterpret_cast<void **>(&m->d_recs), want * sizeof(rxm::K1Rec)));
+            m->cap_recs = want;
+        }
+        if (!m->d_hist) CU(cudaMalloc(reinterpret_cast<void **>(&m->d_hist), (rxm::K1_BUCKETS + 32) * sizeof(uint32_t)));
+        rxm::K1Launch a{m->d_k1_table, m->d_k1_accept, d_chars, d_offsets, n, d_out, m->d_recs, m->d_hist,
+                        m->d_hist + rxm::K1_BUCKETS, m->d_overflow, m->sm_count, stream};
+        st = rxm::k1_launch(m->k1, a, &launched);
     } else {
         rxm::MfaView v{m->d_edge_begin, m->d_edges, m->tables.n_states(), m->tables.start,
                        m->tables.finish, m->tables.reversed};

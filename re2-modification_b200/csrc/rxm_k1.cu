@@ -1,0 +1,462 @@
+// K1 -- determinised memory-free automaton, sm_100a.
+// Replaces Automata::match (automata.cpp:177-210) for whole batches.
+//
+// Data path (DESIGN.md "K1"):
+//   1. bucket pass   -- three tiny kernels build 16-byte records {start, len, index}
+//                       ordered by DESCENDING length bucket (counting sort on a
+//                       3 %-granular log scale).  Strings are not moved.
+//   2. scan kernel   -- persistent warps pull 32 consecutive records (== 32 strings
+//                       of nearly equal length) from an atomic task counter (longest
+//                       first).  The warp streams the 32 strings in lock-step:
+//                       quarter-/eighth-warps copy 16-byte pieces of each lane's next
+//                       CH-byte chunk with cp.async.cg straight into a padded,
+//                       bank-conflict-free shared-memory ring (no register staging,
+//                       L1 bypassed, every global request a full aligned sector run);
+//                       each lane then walks ITS string with one shared-memory table
+//                       lookup per byte, state in a register.
+//   Each lane's chunk grid is anchored at its string's 16-byte-aligned start, so only
+//   the first and the last one or two 16-byte vectors of a string take the predicated
+//   path; everything between runs the unpredicated 16-step body.
+#include "rxm_kernels.cuh"
+
+#include <cstdlib>
+
+namespace rxm {
+
+int k1_build_tables(const DfaPlan &p, K1Tables &kt, std::vector<uint8_t> &table,
+                    std::vector<uint8_t> &accept, std::string *err) {
+    kt = K1Tables();
+    kt.n_states = p.n_states;
+    kt.n_classes = p.n_classes;
+    kt.start = p.start;
+    kt.reversed = p.reversed;
+    accept.assign(p.accept.begin(), p.accept.end());
+    while (accept.size() % 16) accept.push_back(0);
+    kt.accept_bytes = uint32_t(accept.size());
+    if (p.n_states <= 256) {
+        uint32_t l = 4;
+        while ((1u << l) < p.n_states) l++;
+        kt.mode = K1_DIRECT;
+        kt.log2sp = l;
+        const uint32_t sp = 1u << l;
+        table.assign(size_t(256) * sp, 0);
+        for (uint32_t b = 0; b < 256; b++)
+            for (uint32_t s = 0; s < p.n_states; s++)
+                table[size_t(b) * sp + s] = uint8_t(p.trans[size_t(p.byte_class[b]) * p.n_states + s]);
+    } else {
+        kt.mode = K1_CLASSED;
+        const size_t bytes = 256 + 2 * size_t(p.n_classes) * p.n_states;
+        if (bytes + kt.accept_bytes > 160 * 1024) {
+            if (err) *err = "determinised automaton does not fit shared memory";
+            return RXM_ERR_UNSUPPORTED;
+        }
+        table.assign((bytes + 15) & ~size_t(15), 0);
+        for (uint32_t b = 0; b < 256; b++) table[b] = p.byte_class[b];
+        uint16_t *tr = reinterpret_cast<uint16_t *>(table.data() + 256);
+        for (size_t i = 0; i < p.trans.size(); i++) tr[i] = p.trans[i];
+    }
+    kt.table_bytes = uint32_t(table.size());
+    return RXM_OK;
+}
+
+namespace {
+
+// ---- bucket pass ---------------------------------------------------------------------
+// Monotone length -> bucket map with <= 1/32 relative width: exact below 64, then five
+// mantissa bits per octave.
+__host__ __device__ __forceinline__ uint32_t len_bucket(uint32_t len) {
+    if (len < 64u) return len;
+#if defined(__CUDA_ARCH__)
+    const uint32_t e = 31u - uint32_t(__clz(int(len)));
+#else
+    uint32_t e = 31;
+    while (!((len >> e) & 1u)) e--;
+#endif
+    return 64u + (e - 6u) * 32u + ((len >> (e - 5u)) & 31u);
+}
+
+__global__ void __launch_bounds__(256)
+k1_hist_kernel(const uint64_t *__restrict__ offsets, uint64_t n, uint32_t *__restrict__ hist,
+               unsigned long long *__restrict__ overflow) {
+    __shared__ uint32_t sh[K1_BUCKETS];
+    for (uint32_t i = threadIdx.x; i < K1_BUCKETS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t len = offsets[i + 1] - offsets[i];
+        if (len >= 0x7fffffffull) {
+            atomicAdd(overflow, 1ull);  // reported; such a string gets bit 0
+            atomicAdd(&sh[0], 1u);
+        } else {
+            atomicAdd(&sh[len_bucket(uint32_t(len))], 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < K1_BUCKETS; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+// counts -> first record slot of each bucket, longest bucket first; resets the task counter
+__global__ void __launch_bounds__(1024) k1_cursor_kernel(uint32_t *__restrict__ hist, uint32_t *__restrict__ task_counter) {
+    __shared__ uint32_t part[1024];
+    const uint32_t t = threadIdx.x;
+    const uint32_t b = K1_BUCKETS - 1 - t;  // descending length
+    const uint32_t c = (t < K1_BUCKETS) ? hist[b] : 0;
+    part[t] = c;
+    __syncthreads();
+    for (uint32_t d = 1; d < 1024; d <<= 1) {
+        const uint32_t v = (t >= d) ? part[t - d] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    if (t < K1_BUCKETS) hist[b] = part[t] - c;  // exclusive
+    if (t == 0) *task_counter = 0;
+}
+
+__global__ void __launch_bounds__(256)
+k1_scatter_kernel(const uint64_t *__restrict__ offsets, uint64_t n, uint32_t *__restrict__ cursor,
+                  K1Rec *__restrict__ recs) {
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t b = offsets[i], e = offsets[i + 1];
+        uint64_t len = e - b;
+        if (len >= 0x7fffffffull) len = 0;  // counted and reported by k1_hist_kernel
+        const uint32_t slot = atomicAdd(&cursor[len_bucket(uint32_t(len))], 1u);
+        K1Rec r;
+        r.start = b;
+        r.len = uint32_t(len);
+        r.idx = uint32_t(i);
+        recs[slot] = r;
+    }
+}
+
+// ---- scan kernel -----------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gsrc, bool pred) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t"
+        "@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}\n" ::"r"(smem_dst),
+        "l"(gsrc), "r"(int(pred))
+        : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+template <int L>
+struct DirectStep {  // T[byte][SP] u8, SP = 1 << L
+    uint32_t tbase;  // shared-memory byte address of the table
+    __device__ __forceinline__ uint32_t operator()(uint32_t q, uint32_t byte) const {
+        uint32_t r;
+        const uint32_t a = tbase + (byte << L) + q;
+        asm("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(a));
+        return r;
+    }
+};
+struct ClassedStep {  // cmap[256] u8, then trans[class][n_states] u16
+    uint32_t tbase;
+    uint32_t n_states;
+    __device__ __forceinline__ uint32_t operator()(uint32_t q, uint32_t byte) const {
+        uint32_t c, r;
+        asm("ld.shared.u8 %0, [%1];" : "=r"(c) : "r"(tbase + byte));
+        asm("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(tbase + 256u + 2u * (c * n_states + q)));
+        return r;
+    }
+};
+
+template <bool REV, class Step>
+__device__ __forceinline__ uint32_t step_word(const Step &st, uint32_t q, uint32_t w) {
+    if (!REV) {
+        q = st(q, __byte_perm(w, 0, 0x4440));
+        q = st(q, __byte_perm(w, 0, 0x4441));
+        q = st(q, __byte_perm(w, 0, 0x4442));
+        q = st(q, __byte_perm(w, 0, 0x4443));
+    } else {
+        q = st(q, __byte_perm(w, 0, 0x4443));
+        q = st(q, __byte_perm(w, 0, 0x4442));
+        q = st(q, __byte_perm(w, 0, 0x4441));
+        q = st(q, __byte_perm(w, 0, 0x4440));
+    }
+    return q;
+}
+
+// CH = bytes per lane per stage, STAGES = ring depth.  Lane stride CH+16 keeps the
+// per-lane LDS.128 and the cooperative 16-byte cp.async writes bank-conflict free.
+template <bool REV, class Step, int CH, int STAGES>
+__device__ __forceinline__ void k1_scan_body(const Step st, const uint8_t *__restrict__ chars,
+                                             const K1Rec *__restrict__ recs, uint64_t n,
+                                             uint8_t *__restrict__ out, uint32_t acc_base,
+                                             uint32_t start_state, uint32_t *__restrict__ task_counter,
+                                             uint32_t ring_base /* this warp's ring, smem address */) {
+    constexpr int LS = CH + 16;             // lane stride in the ring
+    constexpr int STAGE_BYTES = 32 * LS;
+    constexpr int VPC = CH / 16;            // vectors per chunk
+    constexpr int LPT = CH / 16;            // lanes cooperating on one target lane's chunk
+    constexpr int TPI = 32 / LPT;           // target lanes served per cp.async instruction
+    constexpr int NI = 32 / TPI;            // cp.async instructions per round (== LPT)
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t part = lane % LPT;       // which 16-byte piece of the chunk this lane copies
+    const uint32_t tsub = lane / LPT;       // which of the TPI targets
+
+    for (;;) {
+        uint32_t task = 0;
+        if (lane == 0) task = atomicAdd(task_counter, 1u);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        const uint64_t first = uint64_t(task) * 32u;
+        if (first >= n) break;
+        K1Rec rec;
+        rec.start = 0;
+        rec.len = 0;
+        rec.idx = 0xffffffffu;
+        if (first + lane < n) rec = recs[first + lane];
+
+        // The lane's "stream": 16-byte vectors covering [p, p+len), anchored at the
+        // aligned vector that holds the first byte read (forward: the string's first
+        // byte; reversed: its last byte).
+        const uint8_t *p = chars + rec.start;
+        const uint32_t len = rec.len;
+        uint32_t h;                // pad bytes in front of the stream (in reading direction)
+        const uint8_t *anchor;     // forward: aligned address of vector 0; reversed: aligned END of vector 0
+        if (!REV) {
+            h = uint32_t(reinterpret_cast<uintptr_t>(p)) & 15u;
+            anchor = p - h;
+        } else {
+            const uint8_t *e = p + len;
+            h = (16u - (uint32_t(reinterpret_cast<uintptr_t>(e)) & 15u)) & 15u;
+            anchor = e + h;
+        }
+        const uint32_t nbytes = len ? h + len : 0u;          // stream length incl. front pad
+        const uint32_t nvec = (nbytes + 15u) >> 4;
+        const uint32_t nrounds_lane = (nvec + VPC - 1) / VPC;
+        const uint32_t nrounds = __reduce_max_sync(0xffffffffu, nrounds_lane);
+
+        // per-instruction source bases / limits of the target lanes this lane copies for
+        const uint8_t *src_base[NI];
+        uint32_t src_lim[NI];   // bytes of the target's stream (rounded up to 16)
+        uint32_t dst_off[NI];
+#pragma unroll
+        for (int g = 0; g < NI; g++) {
+            const uint32_t t = uint32_t(g) * TPI + tsub;
+            const uint64_t a = __shfl_sync(0xffffffffu, uint64_t(reinterpret_cast<uintptr_t>(anchor)), int(t));
+            const uint32_t nv = __shfl_sync(0xffffffffu, nvec, int(t));
+            src_lim[g] = nv * 16u;
+            if (!REV) src_base[g] = reinterpret_cast<const uint8_t *>(uintptr_t(a)) + part * 16u;
+            else src_base[g] = reinterpret_cast<const uint8_t *>(uintptr_t(a)) - (part + 1u) * 16u;
+            dst_off[g] = t * LS + part * 16u;
+        }
+        auto issue_round = [&](uint32_t rr) {
+            const uint32_t sbase = ring_base + (rr % STAGES) * STAGE_BYTES;
+            const uint32_t boff = rr * CH;
+#pragma unroll
+            for (int g = 0; g < NI; g++) {
+                const bool ok = (boff + part * 16u) < src_lim[g];
+                const uint8_t *s = !REV ? src_base[g] + boff : src_base[g] - boff;
+                cp_async16(sbase + dst_off[g], s, ok);
+            }
+            cp_async_commit();
+        };
+
+        uint32_t q = start_state;
+#pragma unroll
+        for (int s = 0; s < STAGES - 1; s++) issue_round(uint32_t(s));  // commits even when empty
+        for (uint32_t r = 0; r < nrounds; r++) {
+            issue_round(r + STAGES - 1);  // predicated off beyond each stream's end
+            cp_async_wait<STAGES - 1>();
+            __syncwarp();
+            const uint32_t my = ring_base + (r % STAGES) * STAGE_BYTES + lane * LS;
+#pragma unroll
+            for (int j = 0; j < VPC; j++) {
+                const uint32_t lo = (r * VPC + uint32_t(j)) * 16u;  // stream offset of this vector
+                const bool inside = lo < nbytes;
+                const bool full = (lo >= h) && (lo + 16u <= nbytes);
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (inside) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                         : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                                         : "r"(my + uint32_t(j) * 16u));
+                if (__all_sync(0xffffffffu, full || !inside)) {
+                    // unpredicated body; lanes whose stream has ended step on zeros and
+                    // discard the result
+                    uint32_t qn = q;
+                    if (!REV) {
+                        qn = step_word<REV>(st, qn, v.x);
+                        qn = step_word<REV>(st, qn, v.y);
+                        qn = step_word<REV>(st, qn, v.z);
+                        qn = step_word<REV>(st, qn, v.w);
+                    } else {
+                        qn = step_word<REV>(st, qn, v.w);
+                        qn = step_word<REV>(st, qn, v.z);
+                        qn = step_word<REV>(st, qn, v.y);
+                        qn = step_word<REV>(st, qn, v.x);
+                    }
+                    q = inside ? qn : q;
+                } else if (inside) {
+                    // boundary vector: byte k of the vector in READING order sits at stream
+                    // offset lo + k; memory byte index is k (forward) or 15 - k (reversed)
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int k = 0; k < 16; k++) {
+                        const uint32_t pos = lo + uint32_t(k);
+                        const int mb = REV ? 15 - k : k;
+                        const uint32_t byte = (w[mb >> 2] >> (8 * (mb & 3))) & 0xffu;
+                        if (pos >= h && pos < nbytes) q = st(q, byte);
+                    }
+                }
+            }
+            __syncwarp();
+            // every live stream's active set is empty (automata.cpp:186-188)
+            if (__all_sync(0xffffffffu, q == 0u || (r + 1u) * CH >= nbytes)) break;
+        }
+        cp_async_wait<0>();
+        __syncwarp();
+        if (rec.idx != 0xffffffffu) {
+            uint32_t a;
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(a) : "r"(acc_base + q));
+            out[rec.idx] = uint8_t(a);
+        }
+    }
+}
+
+constexpr int K1_WARPS = 8;
+
+template <bool REV, int L, int CH, int STAGES>
+__global__ void __launch_bounds__(K1_WARPS * 32)
+k1_dfa_direct_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict__ recs, uint64_t n,
+                     uint8_t *__restrict__ out, const uint8_t *__restrict__ g_table,
+                     const uint8_t *__restrict__ g_accept, uint32_t accept_bytes, uint32_t start,
+                     uint32_t *__restrict__ task_counter) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr uint32_t TB = 256u << L;
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(g_table);
+    uint4 *d4 = reinterpret_cast<uint4 *>(smem);
+    for (uint32_t i = threadIdx.x; i < TB / 16; i += blockDim.x) d4[i] = s4[i];
+    for (uint32_t i = threadIdx.x; i < accept_bytes; i += blockDim.x) smem[TB + i] = g_accept[i];
+    __syncthreads();
+    const uint32_t sbase = uint32_t(__cvta_generic_to_shared(smem));
+    const uint32_t ring0 = (sbase + TB + accept_bytes + 127u) & ~127u;
+    const DirectStep<L> st{sbase};
+    k1_scan_body<REV, DirectStep<L>, CH, STAGES>(st, chars, recs, n, out, sbase + TB, start, task_counter,
+                                                 ring0 + (threadIdx.x >> 5) * (STAGES * 32 * (CH + 16)));
+}
+
+template <bool REV, int CH, int STAGES>
+__global__ void __launch_bounds__(K1_WARPS * 32)
+k1_dfa_classed_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict__ recs, uint64_t n,
+                      uint8_t *__restrict__ out, const uint8_t *__restrict__ g_table, uint32_t table_bytes,
+                      const uint8_t *__restrict__ g_accept, uint32_t accept_bytes, uint32_t n_states,
+                      uint32_t start, uint32_t *__restrict__ task_counter) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(g_table);
+    uint4 *d4 = reinterpret_cast<uint4 *>(smem);
+    for (uint32_t i = threadIdx.x; i < table_bytes / 16; i += blockDim.x) d4[i] = s4[i];
+    for (uint32_t i = threadIdx.x; i < accept_bytes; i += blockDim.x) smem[table_bytes + i] = g_accept[i];
+    __syncthreads();
+    const uint32_t sbase = uint32_t(__cvta_generic_to_shared(smem));
+    const uint32_t ring0 = (sbase + table_bytes + accept_bytes + 127u) & ~127u;
+    const ClassedStep st{sbase, n_states};
+    k1_scan_body<REV, ClassedStep, CH, STAGES>(st, chars, recs, n, out, sbase + table_bytes, start, task_counter,
+                                               ring0 + (threadIdx.x >> 5) * (STAGES * 32 * (CH + 16)));
+}
+
+// ring geometry variants (RXM_K1_VARIANT=0..2 selects one for tuning; default 0)
+struct V0 { static constexpr int CH = 64, STAGES = 2; };
+struct V1 { static constexpr int CH = 64, STAGES = 3; };
+struct V2 { static constexpr int CH = 128, STAGES = 2; };
+
+inline int k1_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("RXM_K1_VARIANT");
+        v = e ? atoi(e) : 0;
+        if (v < 0 || v > 2) v = 0;
+    }
+    return v;
+}
+
+template <class Kern>
+int blocks_per_sm(Kern kern, size_t smem) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, K1_WARPS * 32, smem) != cudaSuccess) return 0;
+    return nb;
+}
+
+template <bool REV, int L, class V>
+int launch_direct_v(const K1Tables &kt, const K1Launch &a) {
+    const size_t smem = (256u << L) + kt.accept_bytes + 128 + size_t(K1_WARPS) * V::STAGES * 32 * (V::CH + 16);
+    auto kern = k1_dfa_direct_kernel<REV, L, V::CH, V::STAGES>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+        return RXM_ERR_CUDA;
+    int nb = blocks_per_sm(kern, smem);
+    if (nb <= 0) return RXM_ERR_CUDA;
+    const uint64_t tasks = (a.n + 31) / 32;
+    uint64_t blocks = uint64_t(a.sm_count) * nb;
+    const uint64_t need = (tasks + K1_WARPS - 1) / K1_WARPS;
+    if (blocks > need) blocks = need;
+    kern<<<unsigned(blocks), K1_WARPS * 32, smem, a.stream>>>(a.d_chars, a.d_recs, a.n, a.d_out, a.d_table,
+                                                             a.d_accept, kt.accept_bytes, kt.start,
+                                                             a.d_task_counter);
+    return RXM_OK;
+}
+
+template <bool REV, int L>
+int launch_direct(const K1Tables &kt, const K1Launch &a) {
+    switch (k1_variant()) {
+        case 1: return launch_direct_v<REV, L, V1>(kt, a);
+        case 2: return launch_direct_v<REV, L, V2>(kt, a);
+        default: return launch_direct_v<REV, L, V0>(kt, a);
+    }
+}
+
+template <bool REV>
+int launch_direct_l(const K1Tables &kt, const K1Launch &a) {
+    switch (kt.log2sp) {
+        case 4: return launch_direct<REV, 4>(kt, a);
+        case 5: return launch_direct<REV, 5>(kt, a);
+        case 6: return launch_direct<REV, 6>(kt, a);
+        case 7: return launch_direct<REV, 7>(kt, a);
+        case 8: return launch_direct<REV, 8>(kt, a);
+        default: return RXM_ERR_INVALID;
+    }
+}
+
+template <bool REV>
+int launch_classed(const K1Tables &kt, const K1Launch &a) {
+    const size_t smem = size_t(kt.table_bytes) + kt.accept_bytes + 128 + size_t(K1_WARPS) * V0::STAGES * 32 * (V0::CH + 16);
+    auto kern = k1_dfa_classed_kernel<REV, V0::CH, V0::STAGES>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+        return RXM_ERR_CUDA;
+    int nb = blocks_per_sm(kern, smem);
+    if (nb <= 0) return RXM_ERR_CUDA;
+    const uint64_t tasks = (a.n + 31) / 32;
+    uint64_t blocks = uint64_t(a.sm_count) * nb;
+    const uint64_t need = (tasks + K1_WARPS - 1) / K1_WARPS;
+    if (blocks > need) blocks = need;
+    kern<<<unsigned(blocks), K1_WARPS * 32, smem, a.stream>>>(a.d_chars, a.d_recs, a.n, a.d_out, a.d_table,
+                                                             kt.table_bytes, a.d_accept, kt.accept_bytes,
+                                                             kt.n_states, kt.start, a.d_task_counter);
+    return RXM_OK;
+}
+
+}  // namespace
+
+int k1_launch(const K1Tables &kt, const K1Launch &a, int *launched) {
+    *launched = 0;
+    // workspace: recs | hist/cursor[K1_BUCKETS] | task counter
+    const int threads = 256;
+    uint64_t blocks = (a.n + threads - 1) / threads;
+    const uint64_t cap = uint64_t(a.sm_count) * 8;
+    if (blocks > cap) blocks = cap;
+    if (cudaMemsetAsync(a.d_hist, 0, K1_BUCKETS * sizeof(uint32_t), a.stream) != cudaSuccess) return RXM_ERR_CUDA;
+    k1_hist_kernel<<<unsigned(blocks), threads, 0, a.stream>>>(a.d_offsets, a.n, a.d_hist, a.d_overflow);
+    k1_cursor_kernel<<<1, 1024, 0, a.stream>>>(a.d_hist, a.d_task_counter);
+    k1_scatter_kernel<<<unsigned(blocks), threads, 0, a.stream>>>(a.d_offsets, a.n, a.d_hist, a.d_recs);
+    *launched = 3;
+    int st;
+    if (kt.mode == K1_DIRECT) st = kt.reversed ? launch_direct_l<true>(kt, a) : launch_direct_l<false>(kt, a);
+    else st = kt.reversed ? launch_classed<true>(kt, a) : launch_classed<false>(kt, a);
+    if (st == RXM_OK) *launched = 4;
+    return st;
+}
+
+}  // namespace rxm

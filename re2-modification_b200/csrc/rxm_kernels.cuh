@@ -34,9 +34,30 @@ struct K1Tables {
 int k1_build_tables(const DfaPlan &p, K1Tables &kt, std::vector<uint8_t> &table,
                     std::vector<uint8_t> &accept, std::string *err);
 
-int k1_launch(const K1Tables &kt, const uint8_t *d_table, const uint8_t *d_accept,
-              const uint8_t *d_chars, const uint64_t *d_offsets, uint64_t n, uint8_t *d_out,
-              int sm_count, cudaStream_t stream, int *launched);
+// One record per string, written by the bucket pass in descending length-bucket order.
+struct __align__(16) K1Rec {
+    unsigned long long start;  // byte offset into chars
+    uint32_t len;
+    uint32_t idx;              // original string index (where the result bit goes)
+};
+constexpr uint32_t K1_BUCKETS = 1024;
+
+struct K1Launch {
+    const uint8_t *d_table;
+    const uint8_t *d_accept;
+    const uint8_t *d_chars;
+    const uint64_t *d_offsets;
+    uint64_t n;
+    uint8_t *d_out;
+    K1Rec *d_recs;               // [n]        workspace
+    uint32_t *d_hist;            // [K1_BUCKETS] workspace (counts, then cursors)
+    uint32_t *d_task_counter;    // [1]        workspace
+    unsigned long long *d_overflow;
+    int sm_count;
+    cudaStream_t stream;
+};
+
+int k1_launch(const K1Tables &kt, const K1Launch &a, int *launched);
 
 // ---- K2: MFA, one thread per string ------------------------------------------------------
 int k2_launch(const MfaView &dev_view, uint32_t n_cells, uint32_t n_edges, const uint8_t *d_chars,

@@ -33,6 +33,13 @@ def load_rxm():
 
 rxm = load_rxm()
 
+
+def load_workloads():
+    spec = importlib.util.spec_from_file_location("workloads", os.path.join(PKG, "workloads.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
 _oracle = None
 
 
@@ -40,9 +47,9 @@ def oracle():
     global _oracle
     if _oracle is None:
         L = C.CDLL(ORACLE_LIB)
-        L.rxm_oracle_match.argtypes = [C.POINTER(rxm.RxmTables), C.c_void_p, C.c_uint64]
+        L.rxm_oracle_match.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.rxm_oracle_match.restype = C.c_int
-        L.rxm_oracle_match_batch.argtypes = [C.POINTER(rxm.RxmTables), C.c_void_p, C.c_void_p,
+        L.rxm_oracle_match_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_uint64, C.c_void_p]
         L.rxm_oracle_match_batch.restype = None
         _oracle = L
@@ -63,7 +70,7 @@ def oracle_bits(tables, chars, offsets):
     out = np.empty(n, dtype=np.uint8)
     chars = np.ascontiguousarray(chars, dtype=np.uint8)
     offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
-    oracle().rxm_oracle_match_batch(tables.ptr, chars.ctypes.data, offsets.ctypes.data, n,
+    oracle().rxm_oracle_match_batch(C.cast(tables.ptr, C.c_void_p), chars.ctypes.data, offsets.ctypes.data, n,
                                     out.ctypes.data)
     return out
 

@@ -111,3 +111,68 @@ def test_mixed_host_device_pointers_are_rejected():
         m.match_ptrs(d_chars.data_ptr(), off.ctypes.data, len(strings), out.ctypes.data)
     assert e.value.status == rxm.RXM_ERR_INVALID
     m.close()
+
+
+@pytest.mark.parametrize("name", ["nfa_config2", "nfa_abb", "nfa_dots"])
+def test_k1_every_length_and_alignment(name):
+    """Forward (config2) and right-to-left (abb, dots: reversed Glushkov) scans: every
+    length 0..300 at every start alignment mod 16, plus a few long strings, so that the
+    head/tail vectors of the staged scan are exercised in every position."""
+    t, _, _ = load_case(name)
+    rng = np.random.default_rng(99)
+    strings = []
+    for L in range(0, 301):
+        strings.append(bytes(rng.choice(np.frombuffer(b"ab", dtype=np.uint8), size=L)))
+    for L in (511, 512, 513, 1000, 4095, 4096, 4097, 20000):
+        strings.append(bytes(rng.choice(np.frombuffer(b"ab", dtype=np.uint8), size=L)))
+    # strings that stay alive: walk inside the language
+    strings += [b"aaba" + b"a" * k for k in range(0, 70)]
+    strings += [b"a" * k + b"abb" for k in range(0, 70)]
+    chars, off = H.make_batch(strings)
+    want = H.oracle_bits(t, chars, off)
+    m = rxm.Matcher(t, 0)
+    assert np.array_equal(m.match_host(chars, off), want)
+    # shifted copy: prepend 1..15 junk bytes so every string changes alignment
+    import torch
+    for shift in (1, 7, 15):
+        d_chars = torch.cat([torch.zeros(shift, dtype=torch.uint8),
+                             torch.from_numpy(chars)]).cuda()
+        d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+        d_out = torch.empty(len(strings), dtype=torch.uint8, device="cuda")
+        m.match_ptrs(d_chars.data_ptr() + shift, d_off.data_ptr(), len(strings), d_out.data_ptr(),
+                     torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_out.cpu().numpy(), want), shift
+    m.close()
+
+
+def test_k1_large_batch_properties():
+    """BASELINE-sized property checks (no oracle at this size): the result vector is a
+    pure function of each string -- a permuted batch gives the permuted bits, and a batch
+    split in two gives the same bits as the whole."""
+    import torch
+    t, _, _ = load_case("nfa_config2")
+    W = H.load_workloads()
+    n = 200_000
+    chars, off = W.alive_strings(t.text, n, 64, 4096, 5, "cuda")
+    m = rxm.Matcher(t, 0)
+    out = torch.empty(n, dtype=torch.uint8, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    m.match_ptrs(chars.data_ptr(), off.data_ptr(), n, out.data_ptr(), s)
+    torch.cuda.synchronize()
+    frac = float(out.float().mean())
+    assert 0.45 < frac < 0.55
+    # split
+    h = n // 2
+    out2 = torch.empty(n, dtype=torch.uint8, device="cuda")
+    m.match_ptrs(chars.data_ptr(), off.data_ptr(), h, out2.data_ptr(), s)
+    off_b = (off[h:] - 0).contiguous()
+    m.match_ptrs(chars.data_ptr(), off_b.data_ptr(), n - h, out2.data_ptr() + h, s)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+    # oracle on a sample
+    k = 2000
+    off_h = off[:k + 1].cpu().numpy().astype(np.uint64)
+    want = H.oracle_bits(t, chars[:int(off_h[-1])].cpu().numpy(), off_h)
+    assert np.array_equal(out[:k].cpu().numpy(), want)
+    m.close()
