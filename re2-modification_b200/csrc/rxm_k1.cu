@@ -31,9 +31,9 @@ int k1_build_tables(const DfaPlan &p, K1Tables &kt, std::vector<uint8_t> &table,
     kt.start = p.start;
     kt.reversed = p.reversed;
     accept.assign(p.accept.begin(), p.accept.end());
-    while (accept.size() % 16) accept.push_back(0);
+    while (accept.size() % 256) accept.push_back(0);
     kt.accept_bytes = uint32_t(accept.size());
-    if (p.n_states <= 256) {
+    if (p.n_states <= 128) {  // direct table (static shared memory, <= 32 KB)
         uint32_t l = 4;
         while ((1u << l) < p.n_states) l++;
         kt.mode = K1_DIRECT;
@@ -62,18 +62,20 @@ int k1_build_tables(const DfaPlan &p, K1Tables &kt, std::vector<uint8_t> &table,
 namespace {
 
 // ---- bucket pass ---------------------------------------------------------------------
-// Monotone length -> bucket map with <= 1/32 relative width: exact below 64, then five
-// mantissa bits per octave.
+// Monotone length -> bucket map with <= 1/64 relative width: exact below 128, then six
+// mantissa bits per octave (max index 128 + 24*64 - 1 < K1_BUCKETS).
 __host__ __device__ __forceinline__ uint32_t len_bucket(uint32_t len) {
-    if (len < 64u) return len;
+    if (len < 128u) return len;
 #if defined(__CUDA_ARCH__)
     const uint32_t e = 31u - uint32_t(__clz(int(len)));
 #else
     uint32_t e = 31;
     while (!((len >> e) & 1u)) e--;
 #endif
-    return 64u + (e - 6u) * 32u + ((len >> (e - 5u)) & 31u);
+    return 128u + (e - 7u) * 64u + ((len >> (e - 6u)) & 63u);
 }
+
+__device__ __forceinline__ uint32_t clamp_len(uint64_t len) { return len >= 0x7fffffffull ? 0u : uint32_t(len); }
 
 __global__ void __launch_bounds__(256)
 k1_hist_kernel(const uint64_t *__restrict__ offsets, uint64_t n, uint32_t *__restrict__ hist,
@@ -84,12 +86,8 @@ k1_hist_kernel(const uint64_t *__restrict__ offsets, uint64_t n, uint32_t *__res
     const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint64_t len = offsets[i + 1] - offsets[i];
-        if (len >= 0x7fffffffull) {
-            atomicAdd(overflow, 1ull);  // reported; such a string gets bit 0
-            atomicAdd(&sh[0], 1u);
-        } else {
-            atomicAdd(&sh[len_bucket(uint32_t(len))], 1u);
-        }
+        if (len >= 0x7fffffffull) atomicAdd(overflow, 1ull);  // reported; such a string gets bit 0
+        atomicAdd(&sh[len_bucket(clamp_len(len))], 1u);
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < K1_BUCKETS; i += blockDim.x)
@@ -98,11 +96,12 @@ k1_hist_kernel(const uint64_t *__restrict__ offsets, uint64_t n, uint32_t *__res
 
 // counts -> first record slot of each bucket, longest bucket first; resets the task counter
 __global__ void __launch_bounds__(1024) k1_cursor_kernel(uint32_t *__restrict__ hist, uint32_t *__restrict__ task_counter) {
+    static_assert(K1_BUCKETS == 2048, "two buckets per thread");
     __shared__ uint32_t part[1024];
     const uint32_t t = threadIdx.x;
-    const uint32_t b = K1_BUCKETS - 1 - t;  // descending length
-    const uint32_t c = (t < K1_BUCKETS) ? hist[b] : 0;
-    part[t] = c;
+    const uint32_t b0 = K1_BUCKETS - 1 - 2 * t, b1 = b0 - 1;  // descending length
+    const uint32_t c0 = hist[b0], c1 = hist[b1];
+    part[t] = c0 + c1;
     __syncthreads();
     for (uint32_t d = 1; d < 1024; d <<= 1) {
         const uint32_t v = (t >= d) ? part[t - d] : 0;
@@ -110,24 +109,45 @@ __global__ void __launch_bounds__(1024) k1_cursor_kernel(uint32_t *__restrict__ 
         part[t] += v;
         __syncthreads();
     }
-    if (t < K1_BUCKETS) hist[b] = part[t] - c;  // exclusive
+    const uint32_t ex = part[t] - (c0 + c1);  // exclusive
+    hist[b0] = ex;
+    hist[b1] = ex + c0;
     if (t == 0) *task_counter = 0;
 }
 
+// Records are placed with ONE global atomic per (tile, bucket): the tile's strings are
+// counted in shared memory, a slot range is reserved per bucket, and the strings then take
+// their slots from the shared-memory copy of the range.
+constexpr int K1_TILE = 8192;
 __global__ void __launch_bounds__(256)
 k1_scatter_kernel(const uint64_t *__restrict__ offsets, uint64_t n, uint32_t *__restrict__ cursor,
                   K1Rec *__restrict__ recs) {
-    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
-    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint64_t b = offsets[i], e = offsets[i + 1];
-        uint64_t len = e - b;
-        if (len >= 0x7fffffffull) len = 0;  // counted and reported by k1_hist_kernel
-        const uint32_t slot = atomicAdd(&cursor[len_bucket(uint32_t(len))], 1u);
-        K1Rec r;
-        r.start = b;
-        r.len = uint32_t(len);
-        r.idx = uint32_t(i);
-        recs[slot] = r;
+    __shared__ uint32_t cnt[K1_BUCKETS];
+    const uint64_t ntiles = (n + K1_TILE - 1) / K1_TILE;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t lo = tile * K1_TILE;
+        const uint64_t hi = (lo + K1_TILE < n) ? lo + K1_TILE : n;
+        for (uint32_t i = threadIdx.x; i < K1_BUCKETS; i += blockDim.x) cnt[i] = 0;
+        __syncthreads();
+        for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x)
+            atomicAdd(&cnt[len_bucket(clamp_len(offsets[i + 1] - offsets[i]))], 1u);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < K1_BUCKETS; i += blockDim.x) {
+            const uint32_t c = cnt[i];
+            if (c) cnt[i] = atomicAdd(&cursor[i], c);  // now the first slot of this tile's range
+        }
+        __syncthreads();
+        for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+            const uint64_t b = offsets[i];
+            const uint32_t len = clamp_len(offsets[i + 1] - b);
+            const uint32_t slot = atomicAdd(&cnt[len_bucket(len)], 1u);
+            K1Rec r;
+            r.start = b;
+            r.len = len;
+            r.idx = uint32_t(i);
+            recs[slot] = r;
+        }
+        __syncthreads();
     }
 }
 
@@ -145,24 +165,23 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+// q' = T[byte][q] with T[byte][SP] u8 in shared memory.  The index is formed with one
+// integer multiply-add (FMA pipe) so that the ALU pipe only carries the byte extraction.
 template <int L>
-struct DirectStep {  // T[byte][SP] u8, SP = 1 << L
-    uint32_t tbase;  // shared-memory byte address of the table
+struct DirectStep {
+    const uint8_t *T;  // shared-memory table (address space resolved after inlining)
     __device__ __forceinline__ uint32_t operator()(uint32_t q, uint32_t byte) const {
-        uint32_t r;
-        const uint32_t a = tbase + (byte << L) + q;
-        asm("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(a));
-        return r;
+        uint32_t idx;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(idx) : "r"(byte), "n"(1 << L), "r"(q));
+        return T[idx];
     }
 };
 struct ClassedStep {  // cmap[256] u8, then trans[class][n_states] u16
-    uint32_t tbase;
+    const uint8_t *cmap;
+    const uint16_t *trans;
     uint32_t n_states;
     __device__ __forceinline__ uint32_t operator()(uint32_t q, uint32_t byte) const {
-        uint32_t c, r;
-        asm("ld.shared.u8 %0, [%1];" : "=r"(c) : "r"(tbase + byte));
-        asm("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(tbase + 256u + 2u * (c * n_states + q)));
-        return r;
+        return trans[uint32_t(cmap[byte]) * n_states + q];
     }
 };
 
@@ -181,13 +200,34 @@ __device__ __forceinline__ uint32_t step_word(const Step &st, uint32_t q, uint32
     }
     return q;
 }
+template <bool REV, class Step>
+__device__ __forceinline__ uint32_t step_vec(const Step &st, uint32_t q, const uint4 &v) {
+    if (!REV) {
+        q = step_word<REV>(st, q, v.x);
+        q = step_word<REV>(st, q, v.y);
+        q = step_word<REV>(st, q, v.z);
+        q = step_word<REV>(st, q, v.w);
+    } else {
+        q = step_word<REV>(st, q, v.w);
+        q = step_word<REV>(st, q, v.z);
+        q = step_word<REV>(st, q, v.y);
+        q = step_word<REV>(st, q, v.x);
+    }
+    return q;
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
 
 // CH = bytes per lane per stage, STAGES = ring depth.  Lane stride CH+16 keeps the
 // per-lane LDS.128 and the cooperative 16-byte cp.async writes bank-conflict free.
 template <bool REV, class Step, int CH, int STAGES>
 __device__ __forceinline__ void k1_scan_body(const Step st, const uint8_t *__restrict__ chars,
                                              const K1Rec *__restrict__ recs, uint64_t n,
-                                             uint8_t *__restrict__ out, uint32_t acc_base,
+                                             uint8_t *__restrict__ out, const uint8_t *accept,
                                              uint32_t start_state, uint32_t *__restrict__ task_counter,
                                              uint32_t ring_base /* this warp's ring, smem address */) {
     constexpr int LS = CH + 16;             // lane stride in the ring
@@ -199,6 +239,7 @@ __device__ __forceinline__ void k1_scan_body(const Step st, const uint8_t *__res
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t part = lane % LPT;       // which 16-byte piece of the chunk this lane copies
     const uint32_t tsub = lane / LPT;       // which of the TPI targets
+    const uint32_t my_ring = ring_base + lane * LS;
 
     for (;;) {
         uint32_t task = 0;
@@ -214,11 +255,11 @@ __device__ __forceinline__ void k1_scan_body(const Step st, const uint8_t *__res
 
         // The lane's "stream": 16-byte vectors covering [p, p+len), anchored at the
         // aligned vector that holds the first byte read (forward: the string's first
-        // byte; reversed: its last byte).
+        // byte; reversed: its last byte).  h = pad bytes in front of the stream.
         const uint8_t *p = chars + rec.start;
         const uint32_t len = rec.len;
-        uint32_t h;                // pad bytes in front of the stream (in reading direction)
-        const uint8_t *anchor;     // forward: aligned address of vector 0; reversed: aligned END of vector 0
+        uint32_t h;
+        const uint8_t *anchor;  // forward: address of vector 0; reversed: END of vector 0
         if (!REV) {
             h = uint32_t(reinterpret_cast<uintptr_t>(p)) & 15u;
             anchor = p - h;
@@ -227,80 +268,73 @@ __device__ __forceinline__ void k1_scan_body(const Step st, const uint8_t *__res
             h = (16u - (uint32_t(reinterpret_cast<uintptr_t>(e)) & 15u)) & 15u;
             anchor = e + h;
         }
-        const uint32_t nbytes = len ? h + len : 0u;          // stream length incl. front pad
+        const uint32_t nbytes = len ? h + len : 0u;  // stream length incl. front pad
         const uint32_t nvec = (nbytes + 15u) >> 4;
-        const uint32_t nrounds_lane = (nvec + VPC - 1) / VPC;
-        const uint32_t nrounds = __reduce_max_sync(0xffffffffu, nrounds_lane);
+        // vectors [vlo, vhi) are complete (no pad, no tail) in EVERY lane of the warp
+        const uint32_t vlo = __reduce_max_sync(0xffffffffu, h ? 1u : 0u);
+        const uint32_t vhi = __reduce_min_sync(0xffffffffu, nbytes >> 4);
+        const uint32_t nrounds = (__reduce_max_sync(0xffffffffu, nvec) + VPC - 1) / VPC;
 
-        // per-instruction source bases / limits of the target lanes this lane copies for
-        const uint8_t *src_base[NI];
-        uint32_t src_lim[NI];   // bytes of the target's stream (rounded up to 16)
+        // sources / limits of the target lanes this lane copies for (round-invariant)
+        const uint8_t *src[NI];
+        uint32_t src_lim[NI];
         uint32_t dst_off[NI];
 #pragma unroll
         for (int g = 0; g < NI; g++) {
             const uint32_t t = uint32_t(g) * TPI + tsub;
             const uint64_t a = __shfl_sync(0xffffffffu, uint64_t(reinterpret_cast<uintptr_t>(anchor)), int(t));
             const uint32_t nv = __shfl_sync(0xffffffffu, nvec, int(t));
-            src_lim[g] = nv * 16u;
-            if (!REV) src_base[g] = reinterpret_cast<const uint8_t *>(uintptr_t(a)) + part * 16u;
-            else src_base[g] = reinterpret_cast<const uint8_t *>(uintptr_t(a)) - (part + 1u) * 16u;
-            dst_off[g] = t * LS + part * 16u;
+            src_lim[g] = nv * 16u - part * 16u;  // copy while round offset < this
+            if (nv * 16u < part * 16u) src_lim[g] = 0;
+            if (!REV) src[g] = reinterpret_cast<const uint8_t *>(uintptr_t(a)) + part * 16u;
+            else src[g] = reinterpret_cast<const uint8_t *>(uintptr_t(a)) - (part + 1u) * 16u;
+            dst_off[g] = ring_base + t * LS + part * 16u;
         }
-        auto issue_round = [&](uint32_t rr) {
-            const uint32_t sbase = ring_base + (rr % STAGES) * STAGE_BYTES;
-            const uint32_t boff = rr * CH;
+        uint32_t issued = 0;  // rounds issued so far
+        auto issue_round = [&]() {
+            const uint32_t sb = (issued % STAGES) * STAGE_BYTES;
+            const uint32_t boff = issued * CH;
 #pragma unroll
             for (int g = 0; g < NI; g++) {
-                const bool ok = (boff + part * 16u) < src_lim[g];
-                const uint8_t *s = !REV ? src_base[g] + boff : src_base[g] - boff;
-                cp_async16(sbase + dst_off[g], s, ok);
+                cp_async16(dst_off[g] + sb, src[g], boff < src_lim[g]);
+                src[g] = !REV ? src[g] + CH : src[g] - CH;
             }
             cp_async_commit();
+            issued++;
         };
 
         uint32_t q = start_state;
 #pragma unroll
-        for (int s = 0; s < STAGES - 1; s++) issue_round(uint32_t(s));  // commits even when empty
+        for (int s = 0; s < STAGES - 1; s++) issue_round();
         for (uint32_t r = 0; r < nrounds; r++) {
-            issue_round(r + STAGES - 1);  // predicated off beyond each stream's end
+            issue_round();  // predicated off beyond each stream's end; always commits
             cp_async_wait<STAGES - 1>();
             __syncwarp();
-            const uint32_t my = ring_base + (r % STAGES) * STAGE_BYTES + lane * LS;
+            const uint32_t my = my_ring + (r % STAGES) * STAGE_BYTES;
+            const uint32_t v0 = r * VPC;
+            if (v0 >= vlo && v0 + VPC <= vhi) {
+                // interior round: every vector complete in every lane
 #pragma unroll
-            for (int j = 0; j < VPC; j++) {
-                const uint32_t lo = (r * VPC + uint32_t(j)) * 16u;  // stream offset of this vector
-                const bool inside = lo < nbytes;
-                const bool full = (lo >= h) && (lo + 16u <= nbytes);
-                uint4 v = make_uint4(0, 0, 0, 0);
-                if (inside) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                                         : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                                         : "r"(my + uint32_t(j) * 16u));
-                if (__all_sync(0xffffffffu, full || !inside)) {
-                    // unpredicated body; lanes whose stream has ended step on zeros and
-                    // discard the result
-                    uint32_t qn = q;
-                    if (!REV) {
-                        qn = step_word<REV>(st, qn, v.x);
-                        qn = step_word<REV>(st, qn, v.y);
-                        qn = step_word<REV>(st, qn, v.z);
-                        qn = step_word<REV>(st, qn, v.w);
+                for (int j = 0; j < VPC; j++) q = step_vec<REV>(st, q, lds128(my + uint32_t(j) * 16u));
+            } else {
+#pragma unroll 1
+                for (int j = 0; j < VPC; j++) {
+                    const uint32_t lo = (v0 + uint32_t(j)) * 16u;  // stream offset of this vector
+                    if (lo >= nbytes) break;
+                    const uint4 v = lds128(my + uint32_t(j) * 16u);
+                    if (lo >= h && lo + 16u <= nbytes) {
+                        q = step_vec<REV>(st, q, v);
                     } else {
-                        qn = step_word<REV>(st, qn, v.w);
-                        qn = step_word<REV>(st, qn, v.z);
-                        qn = step_word<REV>(st, qn, v.y);
-                        qn = step_word<REV>(st, qn, v.x);
-                    }
-                    q = inside ? qn : q;
-                } else if (inside) {
-                    // boundary vector: byte k of the vector in READING order sits at stream
-                    // offset lo + k; memory byte index is k (forward) or 15 - k (reversed)
-                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                        // boundary vector: byte k in READING order sits at stream offset lo + k;
+                        // its index in memory order is k (forward) or 15 - k (reversed)
+                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                    for (int k = 0; k < 16; k++) {
-                        const uint32_t pos = lo + uint32_t(k);
-                        const int mb = REV ? 15 - k : k;
-                        const uint32_t byte = (w[mb >> 2] >> (8 * (mb & 3))) & 0xffu;
-                        if (pos >= h && pos < nbytes) q = st(q, byte);
+                        for (int k = 0; k < 16; k++) {
+                            const uint32_t pos = lo + uint32_t(k);
+                            const int mb = REV ? 15 - k : k;
+                            const uint32_t byte = (w[mb >> 2] >> (8 * (mb & 3))) & 0xffu;
+                            if (pos >= h && pos < nbytes) q = st(q, byte);
+                        }
                     }
                 }
             }
@@ -310,11 +344,7 @@ __device__ __forceinline__ void k1_scan_body(const Step st, const uint8_t *__res
         }
         cp_async_wait<0>();
         __syncwarp();
-        if (rec.idx != 0xffffffffu) {
-            uint32_t a;
-            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(a) : "r"(acc_base + q));
-            out[rec.idx] = uint8_t(a);
-        }
+        if (rec.idx != 0xffffffffu) out[rec.idx] = accept[q];
     }
 }
 
@@ -324,19 +354,20 @@ template <bool REV, int L, int CH, int STAGES>
 __global__ void __launch_bounds__(K1_WARPS * 32)
 k1_dfa_direct_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict__ recs, uint64_t n,
                      uint8_t *__restrict__ out, const uint8_t *__restrict__ g_table,
-                     const uint8_t *__restrict__ g_accept, uint32_t accept_bytes, uint32_t start,
+                     const uint8_t *__restrict__ g_accept, uint32_t start,
                      uint32_t *__restrict__ task_counter) {
-    extern __shared__ __align__(128) uint8_t smem[];
     constexpr uint32_t TB = 256u << L;
+    __shared__ __align__(16) uint8_t s_table[TB];   // static: its offset folds into the LDS
+    __shared__ __align__(16) uint8_t s_accept[256];
+    extern __shared__ __align__(128) uint8_t ring[];
     const uint4 *s4 = reinterpret_cast<const uint4 *>(g_table);
-    uint4 *d4 = reinterpret_cast<uint4 *>(smem);
+    uint4 *d4 = reinterpret_cast<uint4 *>(s_table);
     for (uint32_t i = threadIdx.x; i < TB / 16; i += blockDim.x) d4[i] = s4[i];
-    for (uint32_t i = threadIdx.x; i < accept_bytes; i += blockDim.x) smem[TB + i] = g_accept[i];
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_accept[i] = g_accept[i];
     __syncthreads();
-    const uint32_t sbase = uint32_t(__cvta_generic_to_shared(smem));
-    const uint32_t ring0 = (sbase + TB + accept_bytes + 127u) & ~127u;
-    const DirectStep<L> st{sbase};
-    k1_scan_body<REV, DirectStep<L>, CH, STAGES>(st, chars, recs, n, out, sbase + TB, start, task_counter,
+    const uint32_t ring0 = uint32_t(__cvta_generic_to_shared(ring));
+    const DirectStep<L> st{s_table};
+    k1_scan_body<REV, DirectStep<L>, CH, STAGES>(st, chars, recs, n, out, s_accept, start, task_counter,
                                                  ring0 + (threadIdx.x >> 5) * (STAGES * 32 * (CH + 16)));
 }
 
@@ -354,8 +385,8 @@ k1_dfa_classed_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict
     __syncthreads();
     const uint32_t sbase = uint32_t(__cvta_generic_to_shared(smem));
     const uint32_t ring0 = (sbase + table_bytes + accept_bytes + 127u) & ~127u;
-    const ClassedStep st{sbase, n_states};
-    k1_scan_body<REV, ClassedStep, CH, STAGES>(st, chars, recs, n, out, sbase + table_bytes, start, task_counter,
+    const ClassedStep st{smem, reinterpret_cast<const uint16_t *>(smem + 256), n_states};
+    k1_scan_body<REV, ClassedStep, CH, STAGES>(st, chars, recs, n, out, smem + table_bytes, start, task_counter,
                                                ring0 + (threadIdx.x >> 5) * (STAGES * 32 * (CH + 16)));
 }
 
@@ -363,13 +394,15 @@ k1_dfa_classed_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict
 struct V0 { static constexpr int CH = 64, STAGES = 2; };
 struct V1 { static constexpr int CH = 64, STAGES = 3; };
 struct V2 { static constexpr int CH = 128, STAGES = 2; };
+struct V3 { static constexpr int CH = 32, STAGES = 2; };
+struct V4 { static constexpr int CH = 32, STAGES = 3; };
 
 inline int k1_variant() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("RXM_K1_VARIANT");
         v = e ? atoi(e) : 0;
-        if (v < 0 || v > 2) v = 0;
+        if (v < 0 || v > 4) v = 0;
     }
     return v;
 }
@@ -383,7 +416,7 @@ int blocks_per_sm(Kern kern, size_t smem) {
 
 template <bool REV, int L, class V>
 int launch_direct_v(const K1Tables &kt, const K1Launch &a) {
-    const size_t smem = (256u << L) + kt.accept_bytes + 128 + size_t(K1_WARPS) * V::STAGES * 32 * (V::CH + 16);
+    const size_t smem = size_t(K1_WARPS) * V::STAGES * 32 * (V::CH + 16);
     auto kern = k1_dfa_direct_kernel<REV, L, V::CH, V::STAGES>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
         return RXM_ERR_CUDA;
@@ -394,8 +427,7 @@ int launch_direct_v(const K1Tables &kt, const K1Launch &a) {
     const uint64_t need = (tasks + K1_WARPS - 1) / K1_WARPS;
     if (blocks > need) blocks = need;
     kern<<<unsigned(blocks), K1_WARPS * 32, smem, a.stream>>>(a.d_chars, a.d_recs, a.n, a.d_out, a.d_table,
-                                                             a.d_accept, kt.accept_bytes, kt.start,
-                                                             a.d_task_counter);
+                                                             a.d_accept, kt.start, a.d_task_counter);
     return RXM_OK;
 }
 
@@ -404,6 +436,8 @@ int launch_direct(const K1Tables &kt, const K1Launch &a) {
     switch (k1_variant()) {
         case 1: return launch_direct_v<REV, L, V1>(kt, a);
         case 2: return launch_direct_v<REV, L, V2>(kt, a);
+        case 3: return launch_direct_v<REV, L, V3>(kt, a);
+        case 4: return launch_direct_v<REV, L, V4>(kt, a);
         default: return launch_direct_v<REV, L, V0>(kt, a);
     }
 }
@@ -415,7 +449,6 @@ int launch_direct_l(const K1Tables &kt, const K1Launch &a) {
         case 5: return launch_direct<REV, 5>(kt, a);
         case 6: return launch_direct<REV, 6>(kt, a);
         case 7: return launch_direct<REV, 7>(kt, a);
-        case 8: return launch_direct<REV, 8>(kt, a);
         default: return RXM_ERR_INVALID;
     }
 }

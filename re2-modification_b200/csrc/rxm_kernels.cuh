@@ -40,7 +40,7 @@ struct __align__(16) K1Rec {
     uint32_t len;
     uint32_t idx;              // original string index (where the result bit goes)
 };
-constexpr uint32_t K1_BUCKETS = 1024;
+constexpr uint32_t K1_BUCKETS = 2048;
 
 struct K1Launch {
     const uint8_t *d_table;
