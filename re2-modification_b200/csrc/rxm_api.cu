@@ -156,9 +156,10 @@ extern "C" int rxm_tables_upload(const rxm_tables *host_tables, int device, rxm_
         if ((st = upload_vec(er, &m->d_edges)) != RXM_OK) return fail(st);
         m->info.engine = RXM_ENGINE_K2_THREAD;
     }
-    if (cudaMalloc(reinterpret_cast<void **>(&m->d_overflow), sizeof(unsigned long long)) != cudaSuccess)
+    // [0] strings that hit a kernel limit, [1] K2/K3 work counter
+    if (cudaMalloc(reinterpret_cast<void **>(&m->d_overflow), 2 * sizeof(unsigned long long)) != cudaSuccess)
         return fail(cuda_fail(cudaGetLastError(), "cudaMalloc overflow counter"));
-    CU(cudaMemset(m->d_overflow, 0, sizeof(unsigned long long)));
+    CU(cudaMemset(m->d_overflow, 0, 2 * sizeof(unsigned long long)));
     *out = m;
     return RXM_OK;
 }
@@ -226,7 +227,7 @@ static int launch_on_device(rxm_matcher *m, const uint8_t *d_chars, const uint64
         rxm::MfaView v{m->d_edge_begin, m->d_edges, m->tables.n_states(), m->tables.start,
                        m->tables.finish, m->tables.reversed};
         st = rxm::k2_launch(v, m->tables.n_cells, m->tables.n_edges(), d_chars, d_offsets, n, d_out,
-                            m->d_overflow, m->sm_count, stream, &launched);
+                            m->d_overflow, m->d_overflow + 1, m->sm_count, stream, &launched);
     }
     m->launches += uint64_t(launched);
     if (st != RXM_OK) return st;

@@ -62,7 +62,8 @@ int k1_launch(const K1Tables &kt, const K1Launch &a, int *launched);
 // ---- K2: MFA, one thread per string ------------------------------------------------------
 int k2_launch(const MfaView &dev_view, uint32_t n_cells, uint32_t n_edges, const uint8_t *d_chars,
               const uint64_t *d_offsets, uint64_t n, uint8_t *d_out, unsigned long long *d_overflow,
-              int sm_count, cudaStream_t stream, int *launched);
+              unsigned long long *d_next /* work counter */, int sm_count, cudaStream_t stream,
+              int *launched);
 
 }  // namespace rxm
 #endif

@@ -141,115 +141,142 @@ RXM_HD void apply_actions(Cfg<NC> &m, uint32_t open_mask, uint32_t close_mask, u
     }
 }
 
+// True if two configurations are the same state of the simulation, creation stamp aside
+// (start/len of absent cells are don't-care).
+template <int NC>
+RXM_HD bool cfg_same(const Cfg<NC> &a, const Cfg<NC> &b) {
+    if (a.first != b.first || a.node != b.node || a.flags != b.flags) return false;
+#pragma unroll
+    for (int k = 0; k < NC; k++)
+        if (fl_exists(a.flags, k) && (a.len[k] != b.len[k] || (a.len[k] && a.start[k] != b.start[k]))) return false;
+    return true;
+}
+
 // One simulation of one string.  CAP = slot capacity (>= number of states that
-// can be live at once; n_states always suffices), DMAX = recursion stack depth.
-// Returns 0/1, or 2 if a limit was hit (the caller reports it; never a guess).
+// can be live at once; n_states always suffices), DMAX = depth of the explicit
+// evaluateState recursion stack.  Returns 0/1, or 2 if a limit was hit (the
+// caller reports it; never a guess).
+//
+// evaluateState's recursion (epsilon edges, absent-cell edges) only ever changes the
+// node, the creation stamp, the flag word and -- for an absent-cell edge -- the
+// start/len of a cell the parent does not have.  So the depth-first walk runs on ONE
+// working configuration held in registers; a level of the stack is just
+// {node, stamp, flags, edge cursor}.  Restoring the parent's flags on return also undoes
+// the child's read() marks, exactly like the reference's per-call copy_memory.
 template <int NC, int CAP, int DMAX>
 struct MfaSim {
     typedef Cfg<NC> cfg_t;
-    struct Frame {
-        cfg_t c;
-        uint32_t e, e_end;
-    };
 
-    cfg_t cur[CAP], nxt[CAP];
-    Frame stack[DMAX];
-    uint32_t ncur, nnxt;
+    cfg_t buf[2][CAP];
+    uint32_t cnt[2];
+    uint32_t st_node[DMAX], st_born[DMAX], st_flags[DMAX], st_e[DMAX];
     uint32_t born;
+    uint32_t nb;  // index of the buffer being filled ("new_states")
+    uint32_t steps_run, steps_skipped;  // statistics
     bool overflow;
 
     RXM_HD void insert(const cfg_t &c) {
-        for (uint32_t j = 0; j < nnxt; j++) {
+        cfg_t *nxt = buf[nb];
+        const uint32_t m = cnt[nb];
+        for (uint32_t j = 0; j < m; j++) {
             if (nxt[j].node == c.node) {
                 if (cfg_less<NC>(c, nxt[j])) nxt[j] = c;
                 return;
             }
         }
-        if (nnxt < CAP) nxt[nnxt++] = c;
-        else overflow = true;
+        if (m < CAP) {
+            nxt[m] = c;
+            cnt[nb] = m + 1;
+        } else {
+            overflow = true;
+        }
+    }
+
+    // entry of evaluateState: mfa.cpp:138-141.  false = this call returns at once
+    RXM_HD bool enter(const MfaView &t, uint32_t n, const cfg_t &w, uint32_t i) {
+        if (w.node == t.finish && w.first == n) {
+            insert(w);
+            return false;
+        }
+        if (t.reversed) {  // is_siffix_long_enough, mfa.cpp:116-133
+            uint32_t need = 0;
+#pragma unroll
+            for (int k = 0; k < NC; k++) {
+                const uint32_t fl = (w.flags >> (3 * k)) & 7u;
+                if ((fl & 1u) && ((fl & 2u) || !(fl & 4u))) need += w.len[k];
+            }
+            if (need > n - i) return false;
+        }
+        return true;
     }
 
     // evaluateState (mfa.cpp:136-200) for configuration `root`, step index i
     RXM_HD void eval(const MfaView &t, const Reader &rd, const cfg_t &root, uint32_t i) {
         const uint32_t n = rd.n;
-        int sp = 0;
-        stack[0].c = root;
-        stack[0].e = 0xffffffffu;  // "not entered yet"
-        stack[0].e_end = 0;
-        while (sp >= 0) {
-            Frame &f = stack[sp];
-            if (f.e == 0xffffffffu) {  // function entry
-                if (f.c.node == t.finish && f.c.first == n) {  // :138-140
-                    insert(f.c);
-                    sp--;
-                    continue;
-                }
-                if (t.reversed) {  // :141, :116-133
-                    uint32_t need = 0;
-#pragma unroll
-                    for (int k = 0; k < NC; k++) {
-                        const uint32_t fl = (f.c.flags >> (3 * k)) & 7u;
-                        if ((fl & 1u) && ((fl & 2u) || !(fl & 4u))) need += f.c.len[k];
-                    }
-                    if (need > n - i) {
-                        sp--;
-                        continue;
-                    }
-                }
-                f.e = t.edge_begin[f.c.node];
-                f.e_end = t.edge_begin[f.c.node + 1];
-            }
-            if (f.e == f.e_end) {
+        cfg_t w = root;
+        if (!enter(t, n, w, i)) return;
+        uint32_t sp = 0;
+        uint32_t e = t.edge_begin[w.node], e_end = t.edge_begin[w.node + 1];
+        for (;;) {
+            if (e == e_end) {  // return from this call
+                if (sp == 0) return;
                 sp--;
+                w.node = st_node[sp];
+                w.born = st_born[sp];
+                w.flags = st_flags[sp];
+                e = st_e[sp];
+                e_end = t.edge_begin[w.node + 1];
                 continue;
             }
-            const uint64_t er = t.edges[f.e++];
+            const uint64_t er = t.edges[e++];
             const uint32_t kind = edge_kind(er), sym = edge_sym(er), to = edge_to(er);
             const bool is_cell = (kind == kEdgeLit) && sym >= '1' && sym <= '9' && int(sym - '1') < NC;
             const int k = is_cell ? int(sym - '1') : 0;
-            if (kind == kEdgeEps) {  // :143-147 (actions ignored)
-                if (sp + 1 >= DMAX) {
+            const bool absent = is_cell && !fl_exists(w.flags, k);
+            if (kind == kEdgeEps || absent) {  // :143-147 / :148-160: recursive call on a copy
+                if (sp == DMAX) {
                     overflow = true;
                     continue;
                 }
-                Frame &g = stack[sp + 1];
-                g.c = f.c;
-                g.c.node = to;
-                g.c.born = ++born;
-                g.e = 0xffffffffu;
+                st_node[sp] = w.node;
+                st_born[sp] = w.born;
+                st_flags[sp] = w.flags;
+                st_e[sp] = e;
                 sp++;
-            } else if (is_cell && !fl_exists(f.c.flags, k)) {  // :148-160 absent cell: epsilon-like
-                if (sp + 1 >= DMAX) {
-                    overflow = true;
-                    continue;
+                w.node = to;
+                w.born = ++born;
+                if (absent) {  // new Variable(), then open() or close() by this edge's action on it
+                    uint32_t fl = 1u;
+                    if ((edge_open(er) >> k) & 1u) fl = 3u;
+                    w.start[k] = w.first;
+                    w.len[k] = 0;
+                    w.flags = (w.flags & ~(7u << (3 * k))) | (fl << (3 * k));
                 }
-                Frame &g = stack[sp + 1];
-                g.c = f.c;
-                g.c.node = to;
-                g.c.born = ++born;
-                uint32_t fl = 1u;  // exists, closed, unread, empty
-                if ((edge_open(er) >> k) & 1u) {
-                    fl = 3u;
-                    g.c.start[k] = f.c.first;
+                if (!enter(t, n, w, i)) {  // callee returned immediately
+                    sp--;
+                    w.node = st_node[sp];
+                    w.born = st_born[sp];
+                    w.flags = st_flags[sp];
+                    continue;  // e, e_end still the parent's
                 }
-                g.c.len[k] = 0;
-                g.c.flags = (g.c.flags & ~(7u << (3 * k))) | (fl << (3 * k));
-                g.e = 0xffffffffu;
-                sp++;
-            } else if (i != n && i == f.c.first) {  // :161
+                e = t.edge_begin[w.node];
+                e_end = t.edge_begin[w.node + 1];
+            } else if (i != n && i == w.first) {  // :161
                 const uint32_t ch = rd.at(i);
                 if (kind == kEdgeAny || (kind == kEdgeLit && sym == ch)) {  // :171-175
-                    cfg_t nx = f.c;  // :167 copy BEFORE any read()
+                    cfg_t nx = w;  // :167 copy BEFORE any read()
                     nx.node = to;
                     nx.born = ++born;
                     apply_actions<NC>(nx, edge_open(er), edge_close(er), i, 1u);
                     nx.first += 1;
                     insert(nx);
                 } else if (is_cell) {  // cell present: :176-193
-                    cfg_t nx = f.c;  // copy taken before read() marks the source
-                    f.c.flags |= (4u << (3 * k));  // Variable::read(): later edges inherit is_read
-                    const uint32_t L = f.c.len[k], vs = f.c.start[k];
+                    const uint32_t before = w.flags;
+                    w.flags |= (4u << (3 * k));  // Variable::read(): later edges inherit is_read
+                    const uint32_t L = w.len[k], vs = w.start[k];
                     if (n - i >= L && rd.span_equal(vs, i, L)) {
+                        cfg_t nx = w;
+                        nx.flags = before;  // the copy was taken before read()
                         nx.node = to;
                         nx.born = ++born;
                         nx.first += L;
@@ -257,9 +284,33 @@ struct MfaSim {
                         insert(nx);
                     }
                 }
-            } else if (i != n && i < f.c.first) {  // :195-197 waiting inside a block
-                insert(f.c);
+            } else if (i != n && i < w.first) {  // :195-197 waiting inside a block
+                insert(w);
             }
+        }
+    }
+
+    // one evaluateStates call (mfa.cpp:203-213): expand buf[nb^1] into buf[nb]
+    RXM_HD void step(const MfaView &t, const Reader &rd, uint32_t i) {
+        cfg_t *cur = buf[nb ^ 1u];
+        const uint32_t ncur = cnt[nb ^ 1u];
+        cnt[nb] = 0;
+        // set order: (first, node) -- at most one configuration per node
+        uint64_t last = 0;
+        bool have_last = false;
+        for (uint32_t r = 0; r < ncur; r++) {
+            uint32_t best = 0;
+            uint64_t bestkey = ~uint64_t(0);
+            for (uint32_t j = 0; j < ncur; j++) {
+                const uint64_t key = (uint64_t(cur[j].first) << 32) | cur[j].node;
+                if (key < bestkey && (!have_last || key > last)) {
+                    bestkey = key;
+                    best = j;
+                }
+            }
+            last = bestkey;
+            have_last = true;
+            eval(t, rd, cur[best], i);
         }
     }
 
@@ -268,45 +319,70 @@ struct MfaSim {
         const uint32_t n = rd.n;
         overflow = false;
         born = 0;
-        ncur = 1;
-        cur[0].first = 0;
-        cur[0].born = 0;
-        cur[0].flags = 0;
-        cur[0].node = t.start;
+        steps_run = steps_skipped = 0;
+        nb = 1;
+        cnt[0] = 1;
+        cnt[1] = 0;
+        cfg_t &c0 = buf[0][0];
+        c0.first = 0;
+        c0.born = 0;
+        c0.flags = 0;
+        c0.node = t.start;
 #pragma unroll
         for (int k = 0; k < NC; k++) {
-            cur[0].start[k] = 0;
-            cur[0].len[k] = 0;
+            c0.start[k] = 0;
+            c0.len[k] = 0;
         }
         for (uint32_t i = 0;; i++) {
-            if (i < n && ncur == 0) break;  // :224-225
-            nnxt = 0;
-            // set order: (first, node) -- at most one configuration per node
-            uint64_t done = 0;  // CAP <= 64 handled by bitmask; larger CAP by flag array below
-            for (uint32_t r = 0; r < ncur; r++) {
-                uint32_t best = 0xffffffffu;
-                uint64_t bestkey = ~uint64_t(0);
-                for (uint32_t j = 0; j < ncur; j++) {
-                    if (CAP <= 64 ? ((done >> j) & 1u) : (cur[j].node & 0x80000000u)) continue;
-                    const uint64_t key = (uint64_t(cur[j].first) << 32) | (cur[j].node & 0x7fffffffu);
-                    if (key < bestkey) {
-                        bestkey = key;
-                        best = j;
-                    }
-                }
-                if (CAP <= 64) done |= uint64_t(1) << best;
-                cfg_t c = cur[best];
-                if (CAP > 64) cur[best].node |= 0x80000000u;
-                eval(t, rd, c, i);
-            }
-            // states = new_states (:212)
-            ncur = nnxt;
-            for (uint32_t j = 0; j < nnxt; j++) cur[j] = nxt[j];
+            if (i < n && cnt[nb ^ 1u] == 0) break;  // :224-225
+            step(t, rd, i);
+            steps_run++;
+            nb ^= 1u;  // states = new_states (:212): buf[nb^1] is now current, buf[nb] the previous set
             if (overflow) return 2;
             if (i == n) break;  // the pass at i == n is the last (:227-228)
+            // ---- fast-forward over idle steps (exact; DESIGN.md "K2: waiting steps") ----
+            // If no configuration was active in the step just run (all were waiting inside a
+            // backreference block, or parked on finish with first == n) and the step reproduced
+            // the set it started from, every following step does the same until the first
+            // configuration becomes active or -- reversed mode -- gets pruned.  Jump to the step
+            // BEFORE that event and run it normally: it hands out the creation stamps in the
+            // same relative order as the step it stands for.
+            const cfg_t *now = buf[nb ^ 1u];
+            const cfg_t *prev = buf[nb];
+            const uint32_t m = cnt[nb ^ 1u];
+            if (m == 0 || m != cnt[nb] || i + 2 >= n) continue;
+            uint32_t ev = n;  // next event step
+            bool idle = true;
+            for (uint32_t j = 0; j < m && idle; j++) {
+                const cfg_t &c = now[j];
+                if (c.first <= i) idle = false;  // was active in this step, or stale
+                if (c.first < ev) ev = c.first;
+                if (t.reversed && !(c.node == t.finish && c.first == n)) {
+                    uint32_t need = 0;
+#pragma unroll
+                    for (int k = 0; k < NC; k++) {
+                        const uint32_t fl = (c.flags >> (3 * k)) & 7u;
+                        if ((fl & 1u) && ((fl & 2u) || !(fl & 4u))) need += c.len[k];
+                    }
+                    const uint32_t ps = n - need + 1;  // first step at which need > n - step (need <= n - i here)
+                    if (ps < ev) ev = ps;
+                }
+                bool found = false;
+                for (uint32_t q = 0; q < m; q++)
+                    if (prev[q].node == c.node) {
+                        found = cfg_same<NC>(prev[q], c);
+                        break;
+                    }
+                if (!found) idle = false;
+            }
+            if (idle && ev > i + 2) {
+                steps_skipped += ev - 2 - i;
+                i = ev - 2;  // loop increment makes the next step ev - 1
+            }
         }
-        for (uint32_t j = 0; j < ncur; j++)
-            if (cur[j].node == t.finish) return 1;  // :230-235
+        const cfg_t *fin = buf[nb ^ 1u];
+        for (uint32_t j = 0; j < cnt[nb ^ 1u]; j++)
+            if (fin[j].node == t.finish) return 1;  // :230-235
         return 0;
     }
 };

@@ -7,7 +7,7 @@
 #ifndef RXM_MFA_DISPATCH_HPP
 #define RXM_MFA_DISPATCH_HPP
 
-#define RXM_MFA_DMAX 12
+#define RXM_MFA_DMAX 8
 #define RXM_MFA_MAX_STATES 128
 
 #define RXM_MFA_DISPATCH_CAP(NCV, cap, CALL)                 \

@@ -11,6 +11,13 @@
 #include "../../re2-modification_b200/csrc/rxm_mfa_dispatch.hpp"
 #include "../../re2-modification_b200/csrc/rxm_plan.hpp"
 
+static uint64_t g_steps_run = 0, g_steps_skipped = 0;
+extern "C" void hostsim_step_stats(uint64_t *run, uint64_t *skipped) {
+    *run = g_steps_run;
+    *skipped = g_steps_skipped;
+    g_steps_run = g_steps_skipped = 0;
+}
+
 template <int NC, int CAP, int DMAX>
 static void run_batch(const rxm::MfaView &v, const uint8_t *chars, const uint64_t *off, uint64_t n,
                       uint8_t *out) {
@@ -18,6 +25,8 @@ static void run_batch(const rxm::MfaView &v, const uint8_t *chars, const uint64_
     for (uint64_t i = 0; i < n; i++) {
         rxm::Reader rd{chars + off[i], uint32_t(off[i + 1] - off[i]), v.reversed};
         out[i] = uint8_t(sim->run(v, rd));
+        g_steps_run += sim->steps_run;
+        g_steps_skipped += sim->steps_skipped;
     }
     delete sim;
 }
