@@ -1,0 +1,55 @@
+"""GPU tier: the `-match` driver whose simulation runs on the device
+(re2-modification_b200/bin/diploma_rxm) against the reference's own driver protocol:
+same stdout (banners + one 0/1 line per token) as oracle/_ref/diploma_ref_bump where that
+binary exists, and the golden bits in any case.  Both binaries are prebuilt (they embed the
+reference front end); nothing here reads /root/reference."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import helpers as H
+from cases import BY_NAME, load_case
+
+pytestmark = pytest.mark.gpu
+DRIVER = os.path.join(H.PKG, "bin", "diploma_rxm")
+
+
+def _run(binary, flags, regex, tokens, cwd):
+    text = regex + "\n" + "\n".join(tokens) + "\nexit\n"
+    r = subprocess.run([binary, "-match", *flags], input=text.encode(), capture_output=True,
+                       cwd=cwd, timeout=300)
+    assert r.returncode == 0, r.stderr.decode()[-400:]
+    return r.stdout.decode()
+
+
+@pytest.mark.skipif(not os.path.exists(DRIVER), reason="diploma_rxm not built")
+@pytest.mark.parametrize("name", ["nfa_config2", "ex01_fwd", "ex02_rev", "ex05_fwd", "ex10_rev"])
+def test_match_driver_stdin_protocol(name):
+    m = BY_NAME[name]
+    _, strings, bits = load_case(name)
+    keep = [i for i, s in enumerate(strings) if s and s != b"exit"]  # `cin >>` cannot carry ""
+    tokens = [strings[i].decode() for i in keep]
+    with tempfile.TemporaryDirectory() as td:
+        out = _run(DRIVER, m["flags"], m["regex"], tokens, td)
+        got = [ln for ln in out.splitlines() if ln in ("0", "1")]
+        assert [int(x) for x in got] == [int(bits[i]) for i in keep]
+        if os.path.exists(H.REF_BUMP):
+            ref = _run(H.REF_BUMP, m["flags"], m["regex"], tokens, td)
+            assert out == ref  # banners included
+
+
+@pytest.mark.skipif(not os.path.exists(DRIVER), reason="diploma_rxm not built")
+def test_match_driver_batch_route():
+    m = BY_NAME["ex05_fwd"]
+    _, strings, bits = load_case("ex05_fwd")
+    chars, off = H.make_batch(strings)
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, "in.rxmb"), os.path.join(td, "out.bits")
+        H.write_batch_file(fin, chars, off)
+        r = subprocess.run([DRIVER, "-match", "-regex", m["regex"], "-batch", fin, fout],
+                           capture_output=True, cwd=td, timeout=300)
+        assert r.returncode == 0, r.stderr.decode()[-400:]
+        assert np.array_equal(np.fromfile(fout, dtype=np.uint8), bits)
