@@ -387,5 +387,246 @@ struct MfaSim {
     }
 };
 
+// =====================================================================================
+// Edge programs (compiled on the host by rxm_plan.cpp: compile_programs)
+// =====================================================================================
+struct ProgItem {
+    uint32_t a;  // bit0 type (0 ENTER, 1 LEAF) | bit1 skip_if_final | bit2 has_leaf (ENTER)
+                 // | bits4-5 edge kind | bits6-13 literal byte | bits16-31 node (ENTER: v, LEAF: target)
+    uint32_t b;  // bits0-8 open mask | bits9-17 close mask | bits18-26 cells created on the path
+    uint32_t c;  // bits0-8 created cells that were opened | bits9-17 cells marked read before this item
+                 // | bits18-21 (cell index + 1) when the LEAF reads a present cell, else 0
+    uint32_t d;  // reserved
+};
+RXM_HD bool pi_is_leaf(const ProgItem &p) { return p.a & 1u; }
+RXM_HD bool pi_skip_final(const ProgItem &p) { return p.a & 2u; }
+RXM_HD bool pi_has_leaf(const ProgItem &p) { return p.a & 4u; }
+RXM_HD uint32_t pi_kind(const ProgItem &p) { return (p.a >> 4) & 3u; }
+RXM_HD uint32_t pi_sym(const ProgItem &p) { return (p.a >> 6) & 0xffu; }
+RXM_HD uint32_t pi_node(const ProgItem &p) { return p.a >> 16; }
+RXM_HD uint32_t pi_open(const ProgItem &p) { return p.b & 0x1ffu; }
+RXM_HD uint32_t pi_close(const ProgItem &p) { return (p.b >> 9) & 0x1ffu; }
+RXM_HD uint32_t pi_created(const ProgItem &p) { return (p.b >> 18) & 0x1ffu; }
+RXM_HD uint32_t pi_created_open(const ProgItem &p) { return p.c & 0x1ffu; }
+RXM_HD uint32_t pi_prior_reads(const ProgItem &p) { return (p.c >> 9) & 0x1ffu; }
+RXM_HD uint32_t pi_read_cell(const ProgItem &p) { return (p.c >> 18) & 0xfu; }
+
+struct ProgView {
+    const ProgItem *items;
+    const uint32_t *begin;  // [node << n_cells | mask]
+    const uint32_t *count;
+    uint32_t n_cells;
+};
+
+RXM_HD uint32_t exists_mask(uint32_t flags) {  // bit k <- flags bit 3k
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 9; k++) m |= ((flags >> (3 * k)) & 1u) << k;
+    return m;
+}
+
+// The working configuration of a program item: the root plus the cells created on the way
+// down (exists, maybe open, empty, anchored at `first`) plus the is_read marks in force.
+template <int NC>
+RXM_HD void prog_working(Cfg<NC> &w, const Cfg<NC> &root, uint32_t created, uint32_t created_open,
+                         uint32_t marks) {
+    w = root;
+#pragma unroll
+    for (int k = 0; k < NC; k++) {
+        if ((created >> k) & 1u) {
+            const uint32_t fl = ((created_open >> k) & 1u) ? 3u : 1u;
+            w.flags = (w.flags & ~(7u << (3 * k))) | (fl << (3 * k));
+            w.start[k] = root.first;
+            w.len[k] = 0;
+        }
+        if ((marks >> k) & 1u) w.flags |= 4u << (3 * k);
+    }
+}
+
+// Sequential interpreter of the edge programs: same results as MfaSim, no recursion.
+template <int NC, int CAP>
+struct ProgSim {
+    typedef Cfg<NC> cfg_t;
+    cfg_t buf[2][CAP];
+    uint32_t cnt[2];
+    uint32_t born;
+    uint32_t nb;
+    uint32_t steps_run, steps_skipped;
+    bool overflow;
+
+    RXM_HD void insert(const cfg_t &c) {
+        cfg_t *nxt = buf[nb];
+        const uint32_t m = cnt[nb];
+        for (uint32_t j = 0; j < m; j++) {
+            if (nxt[j].node == c.node) {
+                if (cfg_less<NC>(c, nxt[j])) nxt[j] = c;
+                return;
+            }
+        }
+        if (m < CAP) {
+            nxt[m] = c;
+            cnt[nb] = m + 1;
+        } else {
+            overflow = true;
+        }
+    }
+
+    RXM_HD void eval(const MfaView &t, const ProgView &pv, const Reader &rd, const cfg_t &root, uint32_t i) {
+        const uint32_t n = rd.n;
+        const bool fin = (root.first == n);
+        if (!(root.node == t.finish && fin) && t.reversed) {  // mfa.cpp:141 (after the :138 test)
+            uint32_t need = 0;
+#pragma unroll
+            for (int k = 0; k < NC; k++) {
+                const uint32_t fl = (root.flags >> (3 * k)) & 7u;
+                if ((fl & 1u) && ((fl & 2u) || !(fl & 4u))) need += root.len[k];
+            }
+            if (need > n - i) return;
+        }
+        const uint32_t key = (root.node << pv.n_cells) | (exists_mask(root.flags) & ((1u << pv.n_cells) - 1u));
+        const uint32_t b = pv.begin[key];
+        if (b == 0xffffffffu) {  // a (node, cells) pair the host analysis did not reach
+            overflow = true;
+            return;
+        }
+        const uint32_t cntp = pv.count[key];
+        const bool active = (i != n && i == root.first);
+        const bool waiting = (i != n && i < root.first);
+        const uint32_t ch = active ? rd.at(i) : 0u;
+        const uint32_t digit_bit = (active && ch >= '1' && ch <= '9') ? (1u << (ch - '1')) : 0u;
+        for (uint32_t x = 0; x < cntp; x++) {
+            const ProgItem it = pv.items[b + x];
+            if (fin && pi_skip_final(it)) continue;  // below a call that returned at mfa.cpp:138-140
+            if (!pi_is_leaf(it)) {
+                const uint32_t v = pi_node(it);
+                const bool at_finish = (v == t.finish && fin);
+                if (at_finish || (waiting && pi_has_leaf(it))) {  // :138-140 / :195-197
+                    cfg_t w;
+                    prog_working<NC>(w, root, pi_created(it), pi_created_open(it), 0u);
+                    w.node = v;
+                    if (x != 0) w.born = born + x + 1u;
+                    insert(w);
+                }
+                continue;
+            }
+            if (!active) continue;
+            const uint32_t kind = pi_kind(it), sym = pi_sym(it);
+            const uint32_t rc = pi_read_cell(it);
+            if (kind == kEdgeAny || (kind == kEdgeLit && sym == ch)) {  // :171-175
+                cfg_t nx;
+                prog_working<NC>(nx, root, pi_created(it), pi_created_open(it), pi_prior_reads(it) & ~digit_bit);
+                nx.node = pi_node(it);
+                nx.born = born + x + 1u;
+                apply_actions<NC>(nx, pi_open(it), pi_close(it), i, 1u);
+                nx.first += 1;
+                insert(nx);
+            } else if (rc) {  // :176-193, the cell is present
+                const int k = int(rc) - 1;
+                const bool fresh = (pi_created(it) >> k) & 1u;
+                const uint32_t L = fresh ? 0u : root.len[k < NC ? k : 0];
+                const uint32_t vs = root.start[k < NC ? k : 0];
+                if (n - i >= L && (L == 0 || rd.span_equal(vs, i, L))) {
+                    cfg_t nx;
+                    prog_working<NC>(nx, root, pi_created(it), pi_created_open(it),
+                                     pi_prior_reads(it) & ~digit_bit);
+                    nx.node = pi_node(it);
+                    nx.born = born + x + 1u;
+                    nx.first += L;
+                    apply_actions<NC>(nx, pi_open(it), pi_close(it), i, L);
+                    insert(nx);
+                }
+            }
+        }
+        born += cntp + 1u;
+    }
+
+    RXM_HD void step(const MfaView &t, const ProgView &pv, const Reader &rd, uint32_t i) {
+        cfg_t *cur = buf[nb ^ 1u];
+        const uint32_t ncur = cnt[nb ^ 1u];
+        cnt[nb] = 0;
+        uint64_t last = 0;
+        bool have_last = false;
+        for (uint32_t r = 0; r < ncur; r++) {
+            uint32_t best = 0;
+            uint64_t bestkey = ~uint64_t(0);
+            for (uint32_t j = 0; j < ncur; j++) {
+                const uint64_t key = (uint64_t(cur[j].first) << 32) | cur[j].node;
+                if (key < bestkey && (!have_last || key > last)) {
+                    bestkey = key;
+                    best = j;
+                }
+            }
+            last = bestkey;
+            have_last = true;
+            eval(t, pv, rd, cur[best], i);
+        }
+    }
+
+    RXM_HD int run(const MfaView &t, const ProgView &pv, const Reader &rd) {
+        const uint32_t n = rd.n;
+        overflow = false;
+        born = 0;
+        steps_run = steps_skipped = 0;
+        nb = 1;
+        cnt[0] = 1;
+        cnt[1] = 0;
+        cfg_t &c0 = buf[0][0];
+        c0.first = 0;
+        c0.born = 0;
+        c0.flags = 0;
+        c0.node = t.start;
+#pragma unroll
+        for (int k = 0; k < NC; k++) {
+            c0.start[k] = 0;
+            c0.len[k] = 0;
+        }
+        for (uint32_t i = 0;; i++) {
+            if (i < n && cnt[nb ^ 1u] == 0) break;
+            step(t, pv, rd, i);
+            steps_run++;
+            nb ^= 1u;
+            if (overflow) return 2;
+            if (i == n) break;
+            // fast-forward over idle steps: see MfaSim::run
+            const cfg_t *now = buf[nb ^ 1u];
+            const cfg_t *prev = buf[nb];
+            const uint32_t m = cnt[nb ^ 1u];
+            if (m == 0 || m != cnt[nb] || i + 2 >= n) continue;
+            uint32_t ev = n;
+            bool idle = true;
+            for (uint32_t j = 0; j < m && idle; j++) {
+                const cfg_t &c = now[j];
+                if (c.first <= i) idle = false;
+                if (c.first < ev) ev = c.first;
+                if (t.reversed && !(c.node == t.finish && c.first == n)) {
+                    uint32_t need = 0;
+#pragma unroll
+                    for (int k = 0; k < NC; k++) {
+                        const uint32_t fl = (c.flags >> (3 * k)) & 7u;
+                        if ((fl & 1u) && ((fl & 2u) || !(fl & 4u))) need += c.len[k];
+                    }
+                    const uint32_t ps = n - need + 1;
+                    if (ps < ev) ev = ps;
+                }
+                bool found = false;
+                for (uint32_t q = 0; q < m; q++)
+                    if (prev[q].node == c.node) {
+                        found = cfg_same<NC>(prev[q], c);
+                        break;
+                    }
+                if (!found) idle = false;
+            }
+            if (idle && ev > i + 2) {
+                steps_skipped += ev - 2 - i;
+                i = ev - 2;
+            }
+        }
+        const cfg_t *f = buf[nb ^ 1u];
+        for (uint32_t j = 0; j < cnt[nb ^ 1u]; j++)
+            if (f[j].node == t.finish) return 1;
+        return 0;
+    }
+};
+
 }  // namespace rxm
 #endif

@@ -182,6 +182,101 @@ int plan_dfa(const rxm_tables &t, DfaPlan &out, std::string *err) {
     return RXM_OK;
 }
 
+namespace {
+struct ProgGen {
+    const rxm_tables &t;
+    std::vector<ProgItem> &items;
+    size_t root_start = 0;
+    bool too_big = false;
+    std::vector<std::pair<uint32_t, uint32_t>> found;  // (node, mask) pairs that can become roots
+
+    static bool is_cell_edge(const rxm_tables &t, uint32_t e, uint32_t &k) {
+        if (t.edge_kind[e] != RXM_EDGE_LIT) return false;
+        const uint8_t s = t.edge_sym[e];
+        if (s < '1' || s > '9') return false;
+        k = uint32_t(s - '1');
+        return true;
+    }
+
+    void gen(uint32_t v, uint32_t X, uint32_t C, uint32_t O, uint32_t prior, bool below_finish, int depth) {
+        if (too_big) return;
+        if (depth > 64 || items.size() - root_start >= kProgMaxPerRoot || items.size() >= kProgMaxItems) {
+            too_big = true;
+            return;
+        }
+        const size_t me = items.size();
+        ProgItem en{};
+        en.a = 0u | (below_finish ? 2u : 0u) | (v << 16);
+        en.b = (C << 18);
+        en.c = O | (prior << 9);
+        items.push_back(en);
+        found.emplace_back(v, X);
+        const bool below = below_finish || v == t.finish;
+        uint32_t reads_here = 0;
+        bool has_leaf = false;
+        for (uint32_t e = t.edge_begin[v]; e < t.edge_begin[v + 1]; e++) {
+            uint32_t k = 0;
+            const bool cell = is_cell_edge(t, e, k);
+            if (t.edge_kind[e] == RXM_EDGE_EPS) {
+                gen(t.edge_to[e], X, C, O, prior | reads_here, below, depth + 1);
+            } else if (cell && !((X >> k) & 1u)) {
+                const uint32_t bit = 1u << k;
+                const uint32_t op = ((t.edge_open[e] >> k) & 1u) ? bit : 0u;
+                gen(t.edge_to[e], X | bit, C | bit, O | op, prior | reads_here, below, depth + 1);
+            } else {
+                has_leaf = true;
+                ProgItem lf{};
+                lf.a = 1u | (below ? 2u : 0u) | (uint32_t(t.edge_kind[e]) << 4) | (uint32_t(t.edge_sym[e]) << 6) |
+                       (uint32_t(t.edge_to[e]) << 16);
+                lf.b = uint32_t(t.edge_open[e]) | (uint32_t(t.edge_close[e]) << 9) | (C << 18);
+                lf.c = O | ((prior | reads_here) << 9) | (cell ? ((k + 1u) << 18) : 0u);
+                items.push_back(lf);
+                // successor's cells: everything present here plus cells its open actions create
+                found.emplace_back(t.edge_to[e], X | uint32_t(t.edge_open[e]));
+                if (cell) reads_here |= 1u << k;
+            }
+            if (too_big) return;
+        }
+        if (has_leaf) items[me].a |= 4u;
+    }
+};
+}  // namespace
+
+int compile_programs(const rxm_tables &t, MfaProgram &out, std::string *err) {
+    out = MfaProgram();
+    if (t.n_cells > kProgMaxCells) {
+        if (err) *err = "more than " + std::to_string(kProgMaxCells) + " memory cells";
+        return RXM_ERR_UNSUPPORTED;
+    }
+    out.n_cells = t.n_cells;
+    const uint32_t nm = 1u << t.n_cells;
+    out.begin.assign(size_t(t.n_states) * nm, 0xffffffffu);
+    out.count.assign(size_t(t.n_states) * nm, 0);
+    ProgGen g{t, out.items};
+    std::vector<std::pair<uint32_t, uint32_t>> work{{t.start, 0u}};
+    while (!work.empty()) {
+        const auto [v, X] = work.back();
+        work.pop_back();
+        const size_t key = (size_t(v) << t.n_cells) | X;
+        if (out.begin[key] != 0xffffffffu) continue;
+        g.root_start = out.items.size();
+        g.found.clear();
+        out.begin[key] = uint32_t(out.items.size());
+        g.gen(v, X, 0, 0, 0, false, 0);
+        if (g.too_big) {
+            if (err) *err = "edge program too large";
+            return RXM_ERR_UNSUPPORTED;
+        }
+        out.count[key] = uint32_t(out.items.size() - g.root_start);
+        out.max_count = std::max(out.max_count, out.count[key]);
+        for (const auto &f : g.found) {
+            const size_t k2 = (size_t(f.first) << t.n_cells) | (f.second & (nm - 1));
+            if (out.begin[k2] == 0xffffffffu) work.push_back(f);
+        }
+    }
+    return RXM_OK;
+}
+
 int check_mfa(const rxm_tables &t, std::string *err) {
     // epsilon-only cycles make MFA::evaluateState (mfa.cpp:143-147) recurse forever
     std::vector<uint8_t> color(t.n_states, 0);

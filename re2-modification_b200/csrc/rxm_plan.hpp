@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "rxm_host_tables.hpp"
+#include "rxm_mfa_core.cuh"  // ProgItem
 
 namespace rxm {
 
@@ -33,6 +34,33 @@ constexpr int kMaxEpsDepth = 256;  // deeper == epsilon cycle: the reference ove
 
 // RXM_OK, or RXM_ERR_UNSUPPORTED (too many DFA states / epsilon cycle) with *err set.
 int plan_dfa(const rxm_tables &t, DfaPlan &out, std::string *err);
+
+// ---- MFA "edge programs" ---------------------------------------------------------------
+// MFA::evaluateState (mfa.cpp:136-200) recurses through epsilon edges and through read
+// edges whose cell is absent (mfa.cpp:143-160).  Which of those recursions happen depends
+// only on WHICH cells the configuration has, so for every reachable (node, set of existing
+// cells) the whole depth-first walk is flattened on the host into a list of items in the
+// reference's visiting order:
+//   ENTER  a call of evaluateState on node v (the root call or a recursive one)
+//   LEAF   a non-recursive edge met in that call (letter, '.', never, read of a present cell)
+// with, per item, the cells created on the way down (absent-cell edges), which cells earlier
+// read edges of the enclosing calls have marked is_read (Variable::read, mfa.cpp:177), and
+// whether the item lies below a call on `finish` (skipped when first == len, mfa.cpp:138).
+// The item index doubles as the creation order of everything the walk allocates.
+constexpr uint32_t kProgMaxCells = 4;      // programs are keyed by (node, 2^cells masks)
+constexpr uint32_t kProgMaxItems = 1u << 16;
+constexpr uint32_t kProgMaxPerRoot = 4096;
+
+struct MfaProgram {
+    uint32_t n_cells = 0;
+    std::vector<ProgItem> items;
+    std::vector<uint32_t> begin;  // [node << n_cells | mask] -> first item, 0xffffffff if unreachable
+    std::vector<uint32_t> count;  // [node << n_cells | mask] -> number of items
+    uint32_t max_count = 0;
+};
+
+// RXM_OK, or RXM_ERR_UNSUPPORTED (more than kProgMaxCells cells, program too large).
+int compile_programs(const rxm_tables &t, MfaProgram &out, std::string *err);
 
 // Static checks for an MFA table (epsilon cycles, sizes).  RXM_OK or RXM_ERR_UNSUPPORTED.
 int check_mfa(const rxm_tables &t, std::string *err);

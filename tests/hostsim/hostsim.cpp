@@ -47,6 +47,45 @@ extern "C" int hostsim_mfa_batch(const rxm_tables *t, const uint8_t *chars, cons
     return rxm_dispatch_ok ? 0 : 2;
 }
 
+template <int NC, int CAP, int DMAX>
+static void run_prog_batch(const rxm::MfaView &v, const rxm::ProgView &pv, const uint8_t *chars,
+                           const uint64_t *off, uint64_t n, uint8_t *out) {
+    auto *sim = new rxm::ProgSim<NC, CAP>();
+    for (uint64_t i = 0; i < n; i++) {
+        rxm::Reader rd{chars + off[i], uint32_t(off[i + 1] - off[i]), v.reversed};
+        out[i] = uint8_t(sim->run(v, pv, rd));
+        g_steps_run += sim->steps_run;
+        g_steps_skipped += sim->steps_skipped;
+    }
+    delete sim;
+}
+
+// Edge programs (rxm_plan.cpp: compile_programs) run by the sequential interpreter.
+extern "C" int hostsim_prog_batch(const rxm_tables *t, const uint8_t *chars, const uint64_t *off,
+                                  uint64_t n, uint8_t *out, uint32_t *info2) {
+    rxm::MfaProgram prog;
+    std::string err;
+    int st = rxm::compile_programs(*t, prog, &err);
+    if (st != RXM_OK) return st;
+    if (info2) {
+        info2[0] = uint32_t(prog.items.size());
+        info2[1] = prog.max_count;
+    }
+    std::vector<uint16_t> eb(t->n_states + 1);
+    for (uint32_t q = 0; q <= t->n_states; q++) eb[q] = uint16_t(t->edge_begin[q]);
+    std::vector<uint64_t> er(t->n_edges);
+    for (uint32_t e = 0; e < t->n_edges; e++)
+        er[e] = rxm::pack_edge(t->edge_kind[e], t->edge_sym[e], t->edge_to[e], t->edge_open[e],
+                               t->edge_close[e]);
+    rxm::MfaView v{eb.data(), er.data(), t->n_states, t->start, t->finish, t->reversed};
+    rxm::ProgView pv{prog.items.data(), prog.begin.data(), prog.count.data(), prog.n_cells};
+    bool rxm_dispatch_ok = true;
+#define CALL(NC, CAP, DMAX) run_prog_batch<NC, CAP, DMAX>(v, pv, chars, off, n, out)
+    RXM_MFA_DISPATCH(t->n_cells, t->n_states, CALL);
+#undef CALL
+    return rxm_dispatch_ok ? 0 : 2;
+}
+
 // DFA built by the planner, stepped on the host (checks plan_dfa against the oracle).
 extern "C" int hostsim_dfa_batch(const rxm_tables *t, const uint8_t *chars, const uint64_t *off,
                                  uint64_t n, uint8_t *out, uint32_t *info3) {
