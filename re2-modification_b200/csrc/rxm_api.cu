@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -57,6 +58,12 @@ struct rxm_matcher {
     // K2: MFA tables
     uint16_t *d_edge_begin = nullptr;
     uint64_t *d_edges = nullptr;
+
+    // K3: edge programs
+    rxm::MfaProgram prog;
+    rxm::ProgItem *d_items = nullptr;
+    uint32_t *d_prog_begin = nullptr;
+    uint32_t *d_prog_count = nullptr;
 
     // staging workspace for host buffers
     uint8_t *d_chars = nullptr;
@@ -155,6 +162,18 @@ extern "C" int rxm_tables_upload(const rxm_tables *host_tables, int device, rxm_
         if ((st = upload_vec(eb, &m->d_edge_begin)) != RXM_OK) return fail(st);
         if ((st = upload_vec(er, &m->d_edges)) != RXM_OK) return fail(st);
         m->info.engine = RXM_ENGINE_K2_THREAD;
+        // K3 (warp per string) needs the edge programs; automata they cannot express stay on K2
+        std::string perr;
+        const char *force = getenv("RXM_MFA_ENGINE");  // "k2" / "k3": tuning and tests
+        if (!(force && std::strcmp(force, "k2") == 0) && rxm::compile_programs(t, m->prog, &perr) == RXM_OK) {
+            if ((st = upload_vec(m->prog.items, &m->d_items)) != RXM_OK) return fail(st);
+            if ((st = upload_vec(m->prog.begin, &m->d_prog_begin)) != RXM_OK) return fail(st);
+            if ((st = upload_vec(m->prog.count, &m->d_prog_count)) != RXM_OK) return fail(st);
+            m->info.engine = RXM_ENGINE_K3_WARP;
+        } else if (force && std::strcmp(force, "k3") == 0) {
+            err = "RXM_MFA_ENGINE=k3 but the edge programs cannot be built: " + perr;
+            return fail(RXM_ERR_UNSUPPORTED);
+        }
     }
     // [0] strings that hit a kernel limit, [1] K2/K3 work counter
     if (cudaMalloc(reinterpret_cast<void **>(&m->d_overflow), 2 * sizeof(unsigned long long)) != cudaSuccess)
@@ -177,6 +196,9 @@ extern "C" int rxm_free(rxm_handle h) {
     cudaFree(h->d_k1_accept);
     cudaFree(h->d_edge_begin);
     cudaFree(h->d_edges);
+    cudaFree(h->d_items);
+    cudaFree(h->d_prog_begin);
+    cudaFree(h->d_prog_count);
     cudaFree(h->d_chars);
     cudaFree(h->d_offsets);
     cudaFree(h->d_bits);
@@ -223,6 +245,13 @@ static int launch_on_device(rxm_matcher *m, const uint8_t *d_chars, const uint64
         rxm::K1Launch a{m->d_k1_table, m->d_k1_accept, d_chars, d_offsets, n, d_out, m->d_recs, m->d_hist,
                         m->d_hist + rxm::K1_BUCKETS, m->d_overflow, m->sm_count, stream};
         st = rxm::k1_launch(m->k1, a, &launched);
+    } else if (m->info.engine == RXM_ENGINE_K3_WARP) {
+        rxm::MfaView v{m->d_edge_begin, m->d_edges, m->tables.n_states(), m->tables.start,
+                       m->tables.finish, m->tables.reversed};
+        rxm::ProgView gp{m->d_items, m->d_prog_begin, m->d_prog_count, m->prog.n_cells};
+        st = rxm::k3_launch(v, gp, uint32_t(m->prog.items.size()), uint32_t(m->prog.begin.size()),
+                            m->tables.n_cells, d_chars, d_offsets, n, d_out, m->d_overflow, m->d_overflow + 1,
+                            m->sm_count, stream, &launched);
     } else {
         rxm::MfaView v{m->d_edge_begin, m->d_edges, m->tables.n_states(), m->tables.start,
                        m->tables.finish, m->tables.reversed};

@@ -1,0 +1,399 @@
+// K3 -- MFA, one WARP per string, sm_100a.
+// Replaces MFA::match (mfa.cpp:215-236) for whole batches; meant for long strings and
+// large automata, where one thread per string (K2) serialises everything.
+//
+// The warp keeps the successor set as one slot per node in shared memory.
+// A slot is a 64-bit ORDER KEY  first:28 | lowest cell name:4 | creation stamp:32  -- the
+// reference's std::set<MemoryState> order for one node -- plus the cell payload.  A step
+// takes the live configurations in (first, node) order; for each one the 32 lanes evaluate
+// the items of its host-compiled edge program (rxm_plan.cpp: compile_programs) in parallel:
+// lane x handles item x (a call entry or a non-recursive edge), builds the successor it
+// produces, and claims the target slot with atomicMin on the key; the lane whose key
+// stands after the warp has synchronised writes the payload.  The item index is the
+// creation order inside one evaluateState walk, so stamps are base + index.
+// Backreference blocks are compared by the whole warp, 128 bytes per iteration.
+// Idle steps (every configuration waiting inside a block) are skipped exactly as in K2.
+#include "rxm_kernels.cuh"
+
+namespace rxm {
+
+namespace {
+
+constexpr uint64_t K3_EMPTY = ~0ull;
+constexpr uint32_t FULL = 0xffffffffu;
+constexpr int K3_WARPS = 8;
+
+__device__ __forceinline__ uint64_t k3_key(uint32_t first, uint32_t flags, uint32_t born) {
+    return (uint64_t(first) << 36) | (uint64_t(lowvar(flags)) << 32) | born;
+}
+
+// mem[pa, pa+L) == mem[pb, pb+L) ?  Whole warp, 4 bytes per lane per iteration, any alignment.
+__device__ __forceinline__ bool warp_span_equal(const uint8_t *pa, const uint8_t *pb, uint32_t L, uint32_t lane) {
+    if (pa == pb || L == 0) return true;
+    const uint32_t ba = uint32_t(reinterpret_cast<uintptr_t>(pa)) & 3u, bb = uint32_t(reinterpret_cast<uintptr_t>(pb)) & 3u;
+    const uint32_t *wa = reinterpret_cast<const uint32_t *>(pa - ba);
+    const uint32_t *wb = reinterpret_cast<const uint32_t *>(pb - bb);
+    for (uint32_t base = 0; base < L; base += 128u) {
+        const uint32_t off = base + lane * 4u;
+        bool ne = false;
+        if (off < L) {
+            const uint32_t rem = L - off, take = rem < 4u ? rem : 4u;
+            const uint32_t idx = off >> 2;
+            const uint32_t a0 = __ldg(wa + idx), b0 = __ldg(wb + idx);
+            const uint32_t a1 = (ba + take > 4u) ? __ldg(wa + idx + 1) : 0u;  // only if bytes < L live there
+            const uint32_t b1 = (bb + take > 4u) ? __ldg(wb + idx + 1) : 0u;
+            uint32_t x = __funnelshift_r(a0, a1, ba * 8u) ^ __funnelshift_r(b0, b1, bb * 8u);
+            if (take < 4u) x &= (1u << (8u * take)) - 1u;
+            ne = x != 0u;
+        }
+        if (__any_sync(FULL, ne)) return false;
+    }
+    return true;
+}
+
+template <int NC>
+struct K3Cfg {  // a configuration in registers
+    uint32_t first, born, flags, node;
+    uint32_t start[NC], len[NC];
+};
+
+template <int NC>
+__device__ __forceinline__ void k3_working(K3Cfg<NC> &w, const K3Cfg<NC> &root, uint32_t created,
+                                           uint32_t created_open, uint32_t marks) {
+    w = root;
+#pragma unroll
+    for (int k = 0; k < NC; k++) {
+        if ((created >> k) & 1u) {
+            const uint32_t fl = ((created_open >> k) & 1u) ? 3u : 1u;
+            w.flags = (w.flags & ~(7u << (3 * k))) | (fl << (3 * k));
+            w.start[k] = root.first;
+            w.len[k] = 0;
+        }
+        if ((marks >> k) & 1u) w.flags |= 4u << (3 * k);
+    }
+}
+
+// doMemoryWriteActions (mfa.cpp:80-105) -- same as apply_actions<NC> on K3Cfg
+template <int NC>
+__device__ __forceinline__ void k3_apply(K3Cfg<NC> &m, uint32_t open_mask, uint32_t close_mask, uint32_t tstart,
+                                         uint32_t tlen) {
+#pragma unroll
+    for (int k = 0; k < NC; k++) {
+        const uint32_t o = (open_mask >> k) & 1u, c = (close_mask >> k) & 1u;
+        uint32_t f = (m.flags >> (3 * k)) & 7u;
+        if (o) {
+            f = 3u;
+            m.start[k] = tstart;
+            m.len[k] = tlen;
+        } else if (f & 1u) {
+            if (c) f &= ~2u;
+            else if (f & 2u) {
+                if (m.len[k] == 0) m.start[k] = tstart;
+                m.len[k] += tlen;
+            }
+        }
+        m.flags = (m.flags & ~(7u << (3 * k))) | (f << (3 * k));
+    }
+}
+
+template <int NC>
+__device__ __forceinline__ uint32_t k3_need(uint32_t flags, const uint32_t *len) {  // is_siffix_long_enough
+    uint32_t need = 0;
+#pragma unroll
+    for (int k = 0; k < NC; k++) {
+        const uint32_t fl = (flags >> (3 * k)) & 7u;
+        if ((fl & 1u) && ((fl & 2u) || !(fl & 4u))) need += len[k];
+    }
+    return need;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(K3_WARPS * 32)
+k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, uint32_t items_in_smem,
+                   const uint8_t *__restrict__ chars, const uint64_t *__restrict__ offsets, uint64_t n,
+                   uint8_t *__restrict__ out, unsigned long long *__restrict__ overflow,
+                   unsigned long long *__restrict__ next_string) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    // ---- block-shared program tables ----
+    uint32_t *s_begin = reinterpret_cast<uint32_t *>(smem);
+    uint32_t *s_count = s_begin + n_keys;
+    size_t o = (size_t(n_keys) * 8 + 15) & ~size_t(15);
+    ProgItem *s_items = reinterpret_cast<ProgItem *>(smem + o);
+    if (items_in_smem) o += size_t(n_items) * sizeof(ProgItem);
+    for (uint32_t i = threadIdx.x; i < n_keys; i += blockDim.x) {
+        s_begin[i] = gp.begin[i];
+        s_count[i] = gp.count[i];
+    }
+    if (items_in_smem) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(gp.items);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_items);
+        for (uint32_t i = threadIdx.x; i < n_items; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const ProgItem *items = items_in_smem ? s_items : gp.items;
+    // ---- per-warp frontier: two buffers of SP slots ----
+    const uint32_t SP = (v.n_states + 31u) & ~31u;
+    const size_t per_warp = size_t(SP) * 2 * (8 + 4 + 8 * NC);
+    uint8_t *wb = smem + o + size_t(warp) * per_warp;
+    uint64_t *keys = reinterpret_cast<uint64_t *>(wb);                    // [2][SP]
+    uint32_t *flg = reinterpret_cast<uint32_t *>(wb + size_t(SP) * 16);   // [2][SP]
+    uint32_t *stt = flg + 2 * SP;                                         // [2][SP][NC]
+    uint32_t *lnn = stt + 2 * SP * NC;                                    // [2][SP][NC]
+
+    for (;;) {
+        unsigned long long si = 0;
+        if (lane == 0) si = atomicAdd(next_string, 1ull);
+        si = __shfl_sync(FULL, si, 0);
+        if (si >= n) break;
+        const uint64_t sb = offsets[si], se = offsets[si + 1];
+        if (se - sb >= (1ull << 28)) {  // first must fit 28 bits of the order key
+            if (lane == 0) {
+                atomicAdd(overflow, 1ull);
+                out[si] = 0;
+            }
+            continue;
+        }
+        const uint8_t *s = chars + sb;
+        const uint32_t n32 = uint32_t(se - sb);
+        for (uint32_t q = lane; q < 2 * SP; q += 32) keys[q] = K3_EMPTY;
+        __syncwarp();
+        if (lane == 0) {  // (0, start, {})  mfa.cpp:217-219
+            keys[v.start] = k3_key(0, 0, 0);
+            flg[v.start] = 0;
+        }
+        __syncwarp();
+        uint32_t cur = 0, born = 0;
+        bool ovf = false;
+        for (uint32_t i = 0;; i++) {
+            uint64_t *K = keys + cur * SP, *KN = keys + (cur ^ 1u) * SP;
+            bool live = false;
+            for (uint32_t q = lane; q < SP; q += 32) {
+                live |= (K[q] != K3_EMPTY);
+                KN[q] = K3_EMPTY;
+            }
+            live = __any_sync(FULL, live);
+            if (i < n32 && !live) break;  // :224-225
+            __syncwarp();
+            uint32_t done = 0;  // bit j: slot lane + 32 j already expanded in this step
+            for (;;) {
+                // next configuration in set order (first, node): mfa.cpp:206
+                uint32_t bf = 0xffffffffu, bn = 0xffffffffu;
+                for (uint32_t j = 0, q = lane; q < SP; j++, q += 32) {
+                    if ((done >> j) & 1u) continue;
+                    const uint64_t k = K[q];
+                    if (k == K3_EMPTY) continue;
+                    const uint32_t f = uint32_t(k >> 36);
+                    if (f < bf) {
+                        bf = f;
+                        bn = q;
+                    }
+                }
+                const uint32_t mf = __reduce_min_sync(FULL, bf);
+                if (mf == 0xffffffffu) break;
+                const uint32_t mn = __reduce_min_sync(FULL, bf == mf ? bn : 0xffffffffu);
+                if (bf == mf && bn == mn) done |= 1u << (mn >> 5);
+                // ---- evaluateState on slot mn ----
+                K3Cfg<NC> root;
+                root.first = mf;
+                root.born = uint32_t(K[mn]);
+                root.node = mn;
+                root.flags = flg[cur * SP + mn];
+#pragma unroll
+                for (int k = 0; k < NC; k++) {
+                    root.start[k] = stt[(cur * SP + mn) * NC + k];
+                    root.len[k] = lnn[(cur * SP + mn) * NC + k];
+                }
+                const bool fin = (mf == n32);
+                if (!(mn == v.finish && fin) && v.reversed && k3_need<NC>(root.flags, root.len) > n32 - i) continue;
+                const uint32_t pkey = (mn << gp.n_cells) | (exists_mask(root.flags) & ((1u << gp.n_cells) - 1u));
+                const uint32_t pb = s_begin[pkey];
+                if (pb == 0xffffffffu) {
+                    ovf = true;
+                    continue;
+                }
+                const uint32_t pc = s_count[pkey];
+                const bool active = (i != n32 && i == mf);
+                const bool waiting = (i != n32 && i < mf);
+                const uint32_t ch = active ? uint32_t(v.reversed ? s[n32 - 1u - i] : s[i]) : 0u;
+                const uint32_t digit_bit = (active && ch >= '1' && ch <= '9') ? (1u << (ch - '1')) : 0u;
+                for (uint32_t x0 = 0; x0 < pc; x0 += 32) {
+                    const uint32_t x = x0 + lane;
+                    bool have = false, need_cmp = false;
+                    uint32_t cmp_vs = 0, cmp_L = 0;
+                    K3Cfg<NC> cand;
+                    ProgItem it{};
+                    if (x < pc) {
+                        it = items[pb + x];
+                        if (!(fin && pi_skip_final(it))) {
+                            if (!pi_is_leaf(it)) {
+                                const uint32_t vv = pi_node(it);
+                                if ((vv == v.finish && fin) || (waiting && pi_has_leaf(it))) {  // :138-140 / :195-197
+                                    k3_working<NC>(cand, root, pi_created(it), pi_created_open(it), 0u);
+                                    cand.node = vv;
+                                    if (x != 0) cand.born = born + x + 1u;
+                                    have = true;
+                                }
+                            } else if (active) {
+                                const uint32_t kind = pi_kind(it), rc = pi_read_cell(it);
+                                if (kind == kEdgeAny || (kind == kEdgeLit && pi_sym(it) == ch)) {  // :171-175
+                                    k3_working<NC>(cand, root, pi_created(it), pi_created_open(it),
+                                                   pi_prior_reads(it) & ~digit_bit);
+                                    cand.node = pi_node(it);
+                                    cand.born = born + x + 1u;
+                                    k3_apply<NC>(cand, pi_open(it), pi_close(it), i, 1u);
+                                    cand.first += 1;
+                                    have = true;
+                                } else if (rc) {  // :176-193
+                                    const int k = int(rc) - 1;
+                                    const bool fresh = (pi_created(it) >> k) & 1u;
+                                    uint32_t L = 0, vs = 0;
+#pragma unroll
+                                    for (int kk = 0; kk < NC; kk++)
+                                        if (kk == k) {
+                                            L = fresh ? 0u : root.len[kk];
+                                            vs = root.start[kk];
+                                        }
+                                    if (n32 - i >= L) {
+                                        need_cmp = true;
+                                        cmp_vs = vs;
+                                        cmp_L = L;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    // backreference blocks: the whole warp compares each pending span
+                    uint32_t cm = __ballot_sync(FULL, need_cmp);
+                    bool cmp_ok = false;
+                    while (cm) {
+                        const int src = __ffs(int(cm)) - 1;
+                        cm &= cm - 1u;
+                        const uint32_t vs = __shfl_sync(FULL, cmp_vs, src), L = __shfl_sync(FULL, cmp_L, src);
+                        bool eq;
+                        if (!v.reversed) eq = warp_span_equal(s + vs, s + i, L, lane);
+                        else eq = warp_span_equal(s + (n32 - vs - L), s + (n32 - i - L), L, lane);
+                        if (int(lane) == src) cmp_ok = eq;
+                    }
+                    if (need_cmp && cmp_ok) {
+                        k3_working<NC>(cand, root, pi_created(it), pi_created_open(it),
+                                       pi_prior_reads(it) & ~digit_bit);
+                        cand.node = pi_node(it);
+                        cand.born = born + x + 1u;
+                        cand.first += cmp_L;
+                        k3_apply<NC>(cand, pi_open(it), pi_close(it), i, cmp_L);
+                        have = true;
+                    }
+                    // claim the target slot: smallest order key wins
+                    uint64_t k64 = 0;
+                    if (have) {
+                        k64 = k3_key(cand.first, cand.flags, cand.born);
+                        atomicMin(reinterpret_cast<unsigned long long *>(&KN[cand.node]), (unsigned long long)k64);
+                    }
+                    __syncwarp();
+                    if (have && KN[cand.node] == k64) {
+                        const uint32_t slot = (cur ^ 1u) * SP + cand.node;
+                        flg[slot] = cand.flags;
+#pragma unroll
+                        for (int k = 0; k < NC; k++) {
+                            stt[slot * NC + k] = cand.start[k];
+                            lnn[slot * NC + k] = cand.len[k];
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (born > 0xfff00000u - pc) ovf = true;
+                born += pc + 1u;
+            }
+            cur ^= 1u;  // states = new_states (:212)
+            __syncwarp();
+            if (ovf || i == n32) break;
+            // ---- fast-forward over idle steps (see MfaSim::run) ----
+            if (i + 2 < n32) {
+                bool same = true;
+                uint32_t ev = n32;
+                for (uint32_t q = lane; q < SP; q += 32) {
+                    const uint64_t ka = keys[cur * SP + q], kb = keys[(cur ^ 1u) * SP + q];
+                    const bool va = ka != K3_EMPTY, vb2 = kb != K3_EMPTY;
+                    if (va != vb2) same = false;
+                    else if (va) {
+                        const uint32_t fa = uint32_t(ka >> 36), fb = uint32_t(kb >> 36);
+                        const uint32_t sa = cur * SP + q, sb2 = (cur ^ 1u) * SP + q;
+                        const uint32_t fla = flg[sa];
+                        if (fa != fb || fla != flg[sb2] || fa <= i) same = false;
+                        uint32_t need = 0;
+#pragma unroll
+                        for (int k = 0; k < NC; k++) {
+                            const uint32_t fl = (fla >> (3 * k)) & 7u;
+                            if (fl & 1u) {
+                                const uint32_t la = lnn[sa * NC + k];
+                                if (la != lnn[sb2 * NC + k] || (la && stt[sa * NC + k] != stt[sb2 * NC + k])) same = false;
+                                if ((fl & 2u) || !(fl & 4u)) need += la;
+                            }
+                        }
+                        if (fa < ev) ev = fa;
+                        if (v.reversed && !(q == v.finish && fa == n32)) {
+                            const uint32_t ps = n32 - need + 1u;
+                            if (ps < ev) ev = ps;
+                        }
+                    }
+                }
+                same = __all_sync(FULL, same);
+                ev = __reduce_min_sync(FULL, ev);
+                if (same && ev > i + 2) i = ev - 2;  // the loop increment makes the next step ev - 1
+            }
+        }
+        if (lane == 0) {
+            if (ovf) {
+                atomicAdd(overflow, 1ull);
+                out[si] = 0;
+            } else {
+                out[si] = keys[cur * SP + v.finish] != K3_EMPTY ? 1 : 0;  // :230-235
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <int NC>
+int launch_k3(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n_keys, const uint8_t *d_chars,
+              const uint64_t *d_offsets, uint64_t n, uint8_t *d_out, unsigned long long *d_overflow,
+              unsigned long long *d_next, int sm_count, cudaStream_t stream) {
+    const uint32_t SP = (v.n_states + 31u) & ~31u;
+    const size_t per_warp = size_t(SP) * 2 * (8 + 4 + 8 * NC);
+    const size_t tab = (size_t(n_keys) * 8 + 15) & ~size_t(15);
+    const bool in_smem = size_t(n_items) * sizeof(ProgItem) <= 64 * 1024;
+    const size_t smem = tab + (in_smem ? size_t(n_items) * sizeof(ProgItem) : 0) + K3_WARPS * per_warp;
+    if (smem > 200 * 1024) return RXM_ERR_UNSUPPORTED;
+    auto kern = k3_mfa_warp_kernel<NC>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+        return RXM_ERR_CUDA;
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, K3_WARPS * 32, smem) != cudaSuccess || nb <= 0)
+        return RXM_ERR_CUDA;
+    uint64_t blocks = uint64_t(sm_count) * nb;
+    const uint64_t need = (n + K3_WARPS - 1) / K3_WARPS;
+    if (blocks > need) blocks = need;
+    if (cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), stream) != cudaSuccess) return RXM_ERR_CUDA;
+    kern<<<unsigned(blocks), K3_WARPS * 32, smem, stream>>>(v, gp, n_items, n_keys, in_smem ? 1u : 0u, d_chars,
+                                                           d_offsets, n, d_out, d_overflow, d_next);
+    return RXM_OK;
+}
+
+}  // namespace
+
+int k3_launch(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n_keys, uint32_t n_cells,
+              const uint8_t *d_chars, const uint64_t *d_offsets, uint64_t n, uint8_t *d_out,
+              unsigned long long *d_overflow, unsigned long long *d_next, int sm_count, cudaStream_t stream,
+              int *launched) {
+    *launched = 0;
+    int st;
+    if (n_cells <= 1) st = launch_k3<1>(v, gp, n_items, n_keys, d_chars, d_offsets, n, d_out, d_overflow, d_next, sm_count, stream);
+    else if (n_cells <= 2) st = launch_k3<2>(v, gp, n_items, n_keys, d_chars, d_offsets, n, d_out, d_overflow, d_next, sm_count, stream);
+    else if (n_cells <= 4) st = launch_k3<4>(v, gp, n_items, n_keys, d_chars, d_offsets, n, d_out, d_overflow, d_next, sm_count, stream);
+    else return RXM_ERR_UNSUPPORTED;
+    if (st == RXM_OK) *launched = 1;
+    return st;
+}
+
+}  // namespace rxm

@@ -65,5 +65,11 @@ int k2_launch(const MfaView &dev_view, uint32_t n_cells, uint32_t n_edges, const
               unsigned long long *d_next /* work counter */, int sm_count, cudaStream_t stream,
               int *launched);
 
+// ---- K3: MFA, one warp per string, over host-compiled edge programs --------------------------
+int k3_launch(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n_keys, uint32_t n_cells,
+              const uint8_t *d_chars, const uint64_t *d_offsets, uint64_t n, uint8_t *d_out,
+              unsigned long long *d_overflow, unsigned long long *d_next, int sm_count, cudaStream_t stream,
+              int *launched);
+
 }  // namespace rxm
 #endif

@@ -26,8 +26,10 @@
 
 #if defined(__CUDACC__)
 #define RXM_HD __host__ __device__ __forceinline__
+#define RXM_UNROLL _Pragma("unroll")
 #else
 #define RXM_HD inline
+#define RXM_UNROLL
 #endif
 
 namespace rxm {
@@ -122,7 +124,7 @@ struct Reader {
 template <int NC>
 RXM_HD void apply_actions(Cfg<NC> &m, uint32_t open_mask, uint32_t close_mask, uint32_t tstart,
                           uint32_t tlen) {
-#pragma unroll
+RXM_UNROLL
     for (int k = 0; k < NC; k++) {
         const uint32_t o = (open_mask >> k) & 1u, c = (close_mask >> k) & 1u;
         uint32_t f = (m.flags >> (3 * k)) & 7u;
@@ -146,7 +148,7 @@ RXM_HD void apply_actions(Cfg<NC> &m, uint32_t open_mask, uint32_t close_mask, u
 template <int NC>
 RXM_HD bool cfg_same(const Cfg<NC> &a, const Cfg<NC> &b) {
     if (a.first != b.first || a.node != b.node || a.flags != b.flags) return false;
-#pragma unroll
+RXM_UNROLL
     for (int k = 0; k < NC; k++)
         if (fl_exists(a.flags, k) && (a.len[k] != b.len[k] || (a.len[k] && a.start[k] != b.start[k]))) return false;
     return true;
@@ -200,7 +202,7 @@ struct MfaSim {
         }
         if (t.reversed) {  // is_siffix_long_enough, mfa.cpp:116-133
             uint32_t need = 0;
-#pragma unroll
+RXM_UNROLL
             for (int k = 0; k < NC; k++) {
                 const uint32_t fl = (w.flags >> (3 * k)) & 7u;
                 if ((fl & 1u) && ((fl & 2u) || !(fl & 4u))) need += w.len[k];
@@ -328,7 +330,7 @@ struct MfaSim {
         c0.born = 0;
         c0.flags = 0;
         c0.node = t.start;
-#pragma unroll
+RXM_UNROLL
         for (int k = 0; k < NC; k++) {
             c0.start[k] = 0;
             c0.len[k] = 0;
@@ -359,7 +361,7 @@ struct MfaSim {
                 if (c.first < ev) ev = c.first;
                 if (t.reversed && !(c.node == t.finish && c.first == n)) {
                     uint32_t need = 0;
-#pragma unroll
+RXM_UNROLL
                     for (int k = 0; k < NC; k++) {
                         const uint32_t fl = (c.flags >> (3 * k)) & 7u;
                         if ((fl & 1u) && ((fl & 2u) || !(fl & 4u))) need += c.len[k];
@@ -420,7 +422,7 @@ struct ProgView {
 
 RXM_HD uint32_t exists_mask(uint32_t flags) {  // bit k <- flags bit 3k
     uint32_t m = 0;
-#pragma unroll
+RXM_UNROLL
     for (int k = 0; k < 9; k++) m |= ((flags >> (3 * k)) & 1u) << k;
     return m;
 }
@@ -431,7 +433,7 @@ template <int NC>
 RXM_HD void prog_working(Cfg<NC> &w, const Cfg<NC> &root, uint32_t created, uint32_t created_open,
                          uint32_t marks) {
     w = root;
-#pragma unroll
+RXM_UNROLL
     for (int k = 0; k < NC; k++) {
         if ((created >> k) & 1u) {
             const uint32_t fl = ((created_open >> k) & 1u) ? 3u : 1u;
@@ -476,7 +478,7 @@ struct ProgSim {
         const bool fin = (root.first == n);
         if (!(root.node == t.finish && fin) && t.reversed) {  // mfa.cpp:141 (after the :138 test)
             uint32_t need = 0;
-#pragma unroll
+RXM_UNROLL
             for (int k = 0; k < NC; k++) {
                 const uint32_t fl = (root.flags >> (3 * k)) & 7u;
                 if ((fl & 1u) && ((fl & 2u) || !(fl & 4u))) need += root.len[k];
@@ -575,7 +577,7 @@ struct ProgSim {
         c0.born = 0;
         c0.flags = 0;
         c0.node = t.start;
-#pragma unroll
+RXM_UNROLL
         for (int k = 0; k < NC; k++) {
             c0.start[k] = 0;
             c0.len[k] = 0;
@@ -600,7 +602,7 @@ struct ProgSim {
                 if (c.first < ev) ev = c.first;
                 if (t.reversed && !(c.node == t.finish && c.first == n)) {
                     uint32_t need = 0;
-#pragma unroll
+RXM_UNROLL
                     for (int k = 0; k < NC; k++) {
                         const uint32_t fl = (c.flags >> (3 * k)) & 7u;
                         if ((fl & 1u) && ((fl & 2u) || !(fl & 4u))) need += c.len[k];

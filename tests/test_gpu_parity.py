@@ -13,11 +13,40 @@ rxm = H.rxm
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", CASE_NAMES)
-def test_golden_host_buffers(name):
+def _engine_cases():
+    out = []
+    for name in CASE_NAMES:
+        if BY_NAME[name]["kind"] == "nfa":
+            out.append((name, None))
+        else:
+            out += [(name, "k2"), (name, "k3")]
+    return out
+
+
+def _matcher(t, engine):
+    """engine: None (planner's choice) or "k2"/"k3" (RXM_MFA_ENGINE override at upload)."""
+    import os
+    old = os.environ.get("RXM_MFA_ENGINE")
+    if engine:
+        os.environ["RXM_MFA_ENGINE"] = engine
+    try:
+        m = rxm.Matcher(t, 0)
+    finally:
+        if engine:
+            if old is None:
+                del os.environ["RXM_MFA_ENGINE"]
+            else:
+                os.environ["RXM_MFA_ENGINE"] = old
+    if engine:
+        assert rxm.ENGINE_NAMES[m.plan().engine] == {"k2": "K2_THREAD", "k3": "K3_WARP"}[engine]
+    return m
+
+
+@pytest.mark.parametrize("name,engine", _engine_cases())
+def test_golden_host_buffers(name, engine):
     t, strings, bits = load_case(name)
     chars, off = H.make_batch(strings)
-    m = rxm.Matcher(t, 0)
+    m = _matcher(t, engine)
     got = m.match_host(chars, off)
     assert m.launch_count() >= 1
     assert m.overflow_count() == 0
@@ -61,12 +90,13 @@ def test_nfa_random_batches_vs_oracle(name):
     m.close()
 
 
+@pytest.mark.parametrize("engine", ["k2", "k3"])
 @pytest.mark.parametrize("name", ["ex01_fwd", "ex02_fwd", "ex02_rev", "ex05_fwd", "ex05_rev",
                                   "ex08_rev", "ex09_fwd", "ex14_rev", "ex15_rev", "ex17_rev"])
-def test_mfa_random_batches_vs_oracle(name):
+def test_mfa_random_batches_vs_oracle(name, engine):
     t, _, _ = load_case(name)
     rng = np.random.default_rng(7)
-    m = rxm.Matcher(t, 0)
+    m = _matcher(t, engine)
     for (n, lo, hi, alpha) in ((4000, 0, 30, b"ab"), (2000, 1, 60, b"aaab"), (1000, 1, 40, b"abc"),
                                (300, 100, 400, b"aaaaab")):
         chars, off = _random_batch(rng, n, lo, hi, alpha)
@@ -74,6 +104,28 @@ def test_mfa_random_batches_vs_oracle(name):
         want = H.oracle_bits(t, chars, off)
         assert np.array_equal(got, want), int((got != want).sum())
     m.close()
+
+
+@pytest.mark.parametrize("engine", ["k2", "k3"])
+def test_mfa_long_blocks_and_attack_strings(engine):
+    """Long backreference blocks (idle-step skipping, warp-wide block compare) and the
+    reference's attack strings (pump.txt recipes) up to 16 K chars, forward and reversed."""
+    W = H.load_workloads()
+    cases = [("ex05_fwd", ["aa"], "b", "aacaac"), ("ex05_rev", ["aa"], "b", "aacaac"),
+             ("ex02_fwd", ["bbaa", "aaba", "bbaa"], "c", ""), ("ex02_rev", ["bbaa", "aaba", "bbaa"], "c", ""),
+             ("ex01_fwd", ["a"], "b", ""), ("ex09_fwd", ["bbaaa"], "c", "")]
+    for name, pump, suffix, prefix in cases:
+        t, _, _ = load_case(name)
+        strings = W.attack_strings(pump, suffix, prefix, [50, 300, 1000, 4000, 16000])
+        for k in (100, 1000, 5000):  # x c x c x x x with a long x
+            x = b"a" * k
+            strings += [x + b"c" + x + b"c" + x + x + x, x + b"c" + x + b"c" + x + x[:-1] + b"b" + x]
+        chars, off = H.make_batch(strings)
+        want = H.oracle_bits(t, chars, off)
+        m = _matcher(t, engine)
+        got = m.match_host(chars, off)
+        assert np.array_equal(got, want), (name, [len(strings[i]) for i in np.nonzero(got != want)[0]])
+        m.close()
 
 
 def test_empty_batch_and_empty_strings():
