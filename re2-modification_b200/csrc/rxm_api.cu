@@ -75,7 +75,8 @@ struct rxm_matcher {
     // K1 bucket-pass workspace
     rxm::K1Rec *d_recs = nullptr;
     size_t cap_recs = 0;
-    uint32_t *d_hist = nullptr;          // [K1_BUCKETS] + task counter
+    uint32_t *d_hist = nullptr;          // [cap_tiles][K1_BUCKETS] + task counter
+    size_t cap_tiles = 0;
 
     unsigned long long *d_overflow = nullptr;  // strings that hit a kernel limit
     uint64_t launches = 0;
@@ -241,9 +242,17 @@ static int launch_on_device(rxm_matcher *m, const uint8_t *d_chars, const uint64
             CU(cudaMalloc(reinterpret_cast<void **>(&m->d_recs), want * sizeof(rxm::K1Rec)));
             m->cap_recs = want;
         }
-        if (!m->d_hist) CU(cudaMalloc(reinterpret_cast<void **>(&m->d_hist), (rxm::K1_BUCKETS + 32) * sizeof(uint32_t)));
+        const size_t ntiles = size_t((n + rxm::K1_TILE_STRINGS - 1) / rxm::K1_TILE_STRINGS);
+        if (ntiles > m->cap_tiles) {
+            cudaFree(m->d_hist);
+            m->d_hist = nullptr;
+            m->cap_tiles = 0;
+            const size_t want = ntiles + (ntiles >> 3) + 1;
+            CU(cudaMalloc(reinterpret_cast<void **>(&m->d_hist), (want * rxm::K1_BUCKETS + 64 + rxm::K1_BUCKETS) * sizeof(uint32_t)));
+            m->cap_tiles = want;
+        }
         rxm::K1Launch a{m->d_k1_table, m->d_k1_accept, d_chars, d_offsets, n, d_out, m->d_recs, m->d_hist,
-                        m->d_hist + rxm::K1_BUCKETS, m->d_overflow, m->sm_count, stream};
+                        m->d_hist + m->cap_tiles * rxm::K1_BUCKETS, m->d_overflow, m->sm_count, stream};
         st = rxm::k1_launch(m->k1, a, &launched);
     } else if (m->info.engine == RXM_ENGINE_K3_WARP) {
         rxm::MfaView v{m->d_edge_begin, m->d_edges, m->tables.n_states(), m->tables.start,

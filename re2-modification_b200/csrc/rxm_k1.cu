@@ -77,30 +77,54 @@ __host__ __device__ __forceinline__ uint32_t len_bucket(uint32_t len) {
 
 __device__ __forceinline__ uint32_t clamp_len(uint64_t len) { return len >= 0x7fffffffull ? 0u : uint32_t(len); }
 
+// Pass 1: per-tile bucket counts, written as one row of tile_counts per tile (no global
+// atomics); strings longer than 2^31-2 are reported.
+constexpr int K1_TILE = 4096;
 __global__ void __launch_bounds__(256)
-k1_hist_kernel(const uint64_t *__restrict__ offsets, uint64_t n, uint32_t *__restrict__ hist,
+k1_hist_kernel(const uint64_t *__restrict__ offsets, uint64_t n, uint32_t *__restrict__ tile_counts,
                unsigned long long *__restrict__ overflow) {
     __shared__ uint32_t sh[K1_BUCKETS];
-    for (uint32_t i = threadIdx.x; i < K1_BUCKETS; i += blockDim.x) sh[i] = 0;
-    __syncthreads();
-    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
-    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint64_t len = offsets[i + 1] - offsets[i];
-        if (len >= 0x7fffffffull) atomicAdd(overflow, 1ull);  // reported; such a string gets bit 0
-        atomicAdd(&sh[len_bucket(clamp_len(len))], 1u);
+    const uint64_t ntiles = (n + K1_TILE - 1) / K1_TILE;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (uint32_t i = threadIdx.x; i < K1_BUCKETS; i += blockDim.x) sh[i] = 0;
+        __syncthreads();
+        const uint64_t lo = tile * K1_TILE, hi = (lo + K1_TILE < n) ? lo + K1_TILE : n;
+        for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+            const uint64_t len = offsets[i + 1] - offsets[i];
+            if (len >= 0x7fffffffull) atomicAdd(overflow, 1ull);  // reported; such a string gets bit 0
+            atomicAdd(&sh[len_bucket(clamp_len(len))], 1u);
+        }
+        __syncthreads();
+        uint32_t *row = tile_counts + tile * K1_BUCKETS;
+        for (uint32_t i = threadIdx.x; i < K1_BUCKETS; i += blockDim.x) row[i] = sh[i];
+        __syncthreads();
     }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < K1_BUCKETS; i += blockDim.x)
-        if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
 
-// counts -> first record slot of each bucket, longest bucket first; resets the task counter
-__global__ void __launch_bounds__(1024) k1_cursor_kernel(uint32_t *__restrict__ hist, uint32_t *__restrict__ task_counter) {
+// Pass 2a: per bucket, exclusive prefix over tiles (in place) and the bucket total.
+__global__ void __launch_bounds__(128)
+k1_colscan_kernel(uint32_t *__restrict__ tile_counts, uint32_t ntiles, uint32_t *__restrict__ totals) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= K1_BUCKETS) return;
+    uint32_t run = 0;
+    for (uint32_t tl = 0; tl < ntiles; tl++) {  // coalesced across the block's buckets
+        uint32_t *p = &tile_counts[size_t(tl) * K1_BUCKETS + b];
+        const uint32_t x = *p;
+        *p = run;
+        run += x;
+    }
+    totals[b] = run;
+}
+
+// Pass 2b: bucket totals -> first record slot of each bucket, longest bucket first; one block.
+// Also resets the task counter.
+__global__ void __launch_bounds__(1024)
+k1_cursor_kernel(uint32_t *__restrict__ totals, uint32_t *__restrict__ task_counter) {
     static_assert(K1_BUCKETS == 2048, "two buckets per thread");
     __shared__ uint32_t part[1024];
     const uint32_t t = threadIdx.x;
     const uint32_t b0 = K1_BUCKETS - 1 - 2 * t, b1 = b0 - 1;  // descending length
-    const uint32_t c0 = hist[b0], c1 = hist[b1];
+    const uint32_t c0 = totals[b0], c1 = totals[b1];
     part[t] = c0 + c1;
     __syncthreads();
     for (uint32_t d = 1; d < 1024; d <<= 1) {
@@ -109,34 +133,23 @@ __global__ void __launch_bounds__(1024) k1_cursor_kernel(uint32_t *__restrict__ 
         part[t] += v;
         __syncthreads();
     }
-    const uint32_t ex = part[t] - (c0 + c1);  // exclusive
-    hist[b0] = ex;
-    hist[b1] = ex + c0;
+    const uint32_t ex = part[t] - (c0 + c1);
+    totals[b0] = ex;
+    totals[b1] = ex + c0;
     if (t == 0) *task_counter = 0;
 }
 
-// Records are placed with ONE global atomic per (tile, bucket): the tile's strings are
-// counted in shared memory, a slot range is reserved per bucket, and the strings then take
-// their slots from the shared-memory copy of the range.
-constexpr int K1_TILE = 8192;
+// Pass 3: every string takes its record slot from its tile's shared-memory copy of the bases.
 __global__ void __launch_bounds__(256)
-k1_scatter_kernel(const uint64_t *__restrict__ offsets, uint64_t n, uint32_t *__restrict__ cursor,
-                  K1Rec *__restrict__ recs) {
+k1_scatter_kernel(const uint64_t *__restrict__ offsets, uint64_t n, const uint32_t *__restrict__ tile_bases,
+                  const uint32_t *__restrict__ bucket_base, K1Rec *__restrict__ recs) {
     __shared__ uint32_t cnt[K1_BUCKETS];
     const uint64_t ntiles = (n + K1_TILE - 1) / K1_TILE;
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint64_t lo = tile * K1_TILE;
-        const uint64_t hi = (lo + K1_TILE < n) ? lo + K1_TILE : n;
-        for (uint32_t i = threadIdx.x; i < K1_BUCKETS; i += blockDim.x) cnt[i] = 0;
+        const uint32_t *row = tile_bases + tile * K1_BUCKETS;
+        for (uint32_t i = threadIdx.x; i < K1_BUCKETS; i += blockDim.x) cnt[i] = row[i] + bucket_base[i];
         __syncthreads();
-        for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x)
-            atomicAdd(&cnt[len_bucket(clamp_len(offsets[i + 1] - offsets[i]))], 1u);
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < K1_BUCKETS; i += blockDim.x) {
-            const uint32_t c = cnt[i];
-            if (c) cnt[i] = atomicAdd(&cursor[i], c);  // now the first slot of this tile's range
-        }
-        __syncthreads();
+        const uint64_t lo = tile * K1_TILE, hi = (lo + K1_TILE < n) ? lo + K1_TILE : n;
         for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
             const uint64_t b = offsets[i];
             const uint32_t len = clamp_len(offsets[i + 1] - b);
@@ -475,20 +488,21 @@ int launch_classed(const K1Tables &kt, const K1Launch &a) {
 
 int k1_launch(const K1Tables &kt, const K1Launch &a, int *launched) {
     *launched = 0;
-    // workspace: recs | hist/cursor[K1_BUCKETS] | task counter
-    const int threads = 256;
-    uint64_t blocks = (a.n + threads - 1) / threads;
+    // workspace: recs | tile_counts[ntiles][K1_BUCKETS] | task counter
+    const uint64_t ntiles = (a.n + K1_TILE - 1) / K1_TILE;
+    uint64_t blocks = ntiles;
     const uint64_t cap = uint64_t(a.sm_count) * 8;
     if (blocks > cap) blocks = cap;
-    if (cudaMemsetAsync(a.d_hist, 0, K1_BUCKETS * sizeof(uint32_t), a.stream) != cudaSuccess) return RXM_ERR_CUDA;
-    k1_hist_kernel<<<unsigned(blocks), threads, 0, a.stream>>>(a.d_offsets, a.n, a.d_hist, a.d_overflow);
-    k1_cursor_kernel<<<1, 1024, 0, a.stream>>>(a.d_hist, a.d_task_counter);
-    k1_scatter_kernel<<<unsigned(blocks), threads, 0, a.stream>>>(a.d_offsets, a.n, a.d_hist, a.d_recs);
-    *launched = 3;
+    k1_hist_kernel<<<unsigned(blocks), 256, 0, a.stream>>>(a.d_offsets, a.n, a.d_hist, a.d_overflow);
+    uint32_t *totals = a.d_task_counter + 32;  // [K1_BUCKETS] after the task counter
+    k1_colscan_kernel<<<K1_BUCKETS / 128, 128, 0, a.stream>>>(a.d_hist, uint32_t(ntiles), totals);
+    k1_cursor_kernel<<<1, 1024, 0, a.stream>>>(totals, a.d_task_counter);
+    k1_scatter_kernel<<<unsigned(blocks), 256, 0, a.stream>>>(a.d_offsets, a.n, a.d_hist, totals, a.d_recs);
+    *launched = 4;
     int st;
     if (kt.mode == K1_DIRECT) st = kt.reversed ? launch_direct_l<true>(kt, a) : launch_direct_l<false>(kt, a);
     else st = kt.reversed ? launch_classed<true>(kt, a) : launch_classed<false>(kt, a);
-    if (st == RXM_OK) *launched = 4;
+    if (st == RXM_OK) *launched = 5;
     return st;
 }
 

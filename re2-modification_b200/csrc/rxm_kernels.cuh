@@ -41,6 +41,7 @@ struct __align__(16) K1Rec {
     uint32_t idx;              // original string index (where the result bit goes)
 };
 constexpr uint32_t K1_BUCKETS = 2048;
+constexpr uint32_t K1_TILE_STRINGS = 4096;  // strings per bucket-pass tile
 
 struct K1Launch {
     const uint8_t *d_table;
@@ -50,7 +51,7 @@ struct K1Launch {
     uint64_t n;
     uint8_t *d_out;
     K1Rec *d_recs;               // [n]        workspace
-    uint32_t *d_hist;            // [K1_BUCKETS] workspace (counts, then cursors)
+    uint32_t *d_hist;            // [ntiles][K1_BUCKETS] workspace (per-tile counts, then bases)
     uint32_t *d_task_counter;    // [1]        workspace
     unsigned long long *d_overflow;
     int sm_count;
