@@ -42,6 +42,12 @@ WORKLOADS = {
     "config3": ("ex05_fwd", "{a*}:1c{&1}:2c(&1|&2)*", [],
                 "config3: example 5 {a*}:1c{&1}:2c(&1|&2)* on x c x c x^m strings of 64-4096 chars, "
                 "50% corrupted in the last block"),
+    "config4": ("ex02_fwd+ex02_rev", "{(a|bb)*}:1aaba(&1|bb*aa)*", [],
+                "config4: example 2 {(a|bb)*}:1aaba(&1|bb*aa)* forward AND -reverse tables on attack strings "
+                "(bbaa)^k aaba (bbaa)^k [c], lengths log-uniform 435-65536"),
+    "config5": ("ex01..ex10 forward", "README examples 1-10", [],
+                "config5: all 10 README examples, per GPU 100k strings each (pumped / near-miss / random, "
+                "16-512 chars), one matcher call per example per step"),
 }
 
 
@@ -173,6 +179,38 @@ def cpu_baseline(W, rxm, wl, tables, regex, flags):
                          "C restatement oracle/rxm_oracle.c, one thread",
                "input_mb_s": float(offsets[-1]) / t / 1e6}
     return res
+
+
+def cpu_baseline_jobs(jobs, wl):
+    """configs 4/5: the reference on a bounded sample of every job (string-parallel)."""
+    cores = host_cores()
+    binary, bname = reference_binary()
+    if not binary:
+        return {"value": None, "unit": "strings/s", "cores": 0, "kind": "port",
+                "sample": "oracle/_ref not built on this box"}
+    tot_n, tot_t, tot_b = 0, 0.0, 0
+    for j in jobs:
+        off = j["offsets"].cpu().numpy().astype(np.uint64)
+        lens = np.diff(off)
+        # the reference is O(len^2) per string (mfa.cpp:136,203 copy the input per call):
+        # only strings up to 8K chars are sampled, one per core (config 4) / 40 per core (config 5)
+        idx = np.nonzero(lens <= 8192)[0][: cores * (1 if wl == "config4" else 40)]
+        if len(idx) == 0:
+            continue
+        ch = j["chars"].cpu().numpy()
+        parts = [ch[int(off[i]):int(off[i + 1])] for i in idx]
+        so = np.zeros(len(idx) + 1, dtype=np.uint64)
+        np.cumsum([len(p) for p in parts], out=so[1:])
+        sc = np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint8)
+        t, _ = run_reference_parallel(binary, j["regex"], j["flags"], sc, so, cores)
+        tot_n += len(idx)
+        tot_t += t
+        tot_b += int(so[-1])
+    return {"value": tot_n / tot_t if tot_t else None, "unit": "strings/s", "cores": cores, "kind": "reference",
+            "build": bname + " (-O2 build of the unmodified reference sources)",
+            "sample": f"{tot_n} strings ({tot_b} bytes) of the same workload with length <= 8192, "
+                      f"string-parallel over {cores} processes, jobs timed one after another",
+            "input_mb_s": tot_b / tot_t / 1e6 if tot_t else None}
 
 
 def reference_arm(args, W, rxm):
@@ -326,17 +364,54 @@ def main():
 
     wl = args.workload
     case, regex, flags, desc = WORKLOADS[wl]
-    tables = rxm.Tables.load(os.path.join(CASES, case + ".rxt"))
-    n = args.strings
-    chars, offsets = make_workload(W, wl, tables.text, n, 1000 + rank, dev)
-    total_bytes = int(offsets[-1])
-    out = torch.empty(n, dtype=torch.uint8, device=dev)
-    m = rxm.Matcher(tables, local_rank)
+    # a step runs every job once; single-expression workloads have one job
+    jobs = []  # dicts: name, regex, flags, tables, chars, offsets, n, bytes, out, matcher
+    if wl in ("config2", "config3"):
+        tables = rxm.Tables.load(os.path.join(CASES, case + ".rxt"))
+        ch, of = make_workload(W, wl, tables.text, args.strings, 1000 + rank, dev)
+        jobs.append({"name": case, "regex": regex, "flags": flags, "tables": tables, "chars": ch, "offsets": of})
+    elif wl == "config4":
+        n4 = args.strings if args.strings != 1_000_000 else 4096
+        c_np, o_np = W.attack_batch(["bbaa", "aaba", "bbaa"], "c", "", n4, 435, 65536, 1000 + rank)
+        ch, of = torch.from_numpy(c_np).to(dev), torch.from_numpy(o_np.astype(np.int64)).to(dev)
+        for cname, fl in (("ex02_fwd", []), ("ex02_rev", ["-reverse"])):
+            jobs.append({"name": cname, "regex": regex, "flags": fl,
+                         "tables": rxm.Tables.load(os.path.join(CASES, cname + ".rxt")), "chars": ch, "offsets": of})
+    else:  # config5
+        per = args.strings // 10 if args.strings != 1_000_000 else 100_000
+        for ex in range(1, 11):
+            c_np, o_np = W.mixed_example_batch(ex, per, 1000 * ex + rank)
+            jobs.append({"name": f"ex{ex:02d}_fwd", "regex": W.README_EXAMPLES[ex][0], "flags": [],
+                         "tables": rxm.Tables.load(os.path.join(CASES, f"ex{ex:02d}_fwd.rxt")),
+                         "chars": torch.from_numpy(c_np).to(dev),
+                         "offsets": torch.from_numpy(o_np.astype(np.int64)).to(dev)})
+    for j in jobs:
+        j["n"] = int(j["offsets"].numel() - 1)
+        j["bytes"] = int(j["offsets"][-1])
+        j["out"] = torch.empty(j["n"], dtype=torch.uint8, device=dev)
+        j["matcher"] = rxm.Matcher(j["tables"], local_rank)
+    n = sum(j["n"] for j in jobs)
+    total_bytes = sum(j["bytes"] for j in jobs)
+    tables, chars, offsets, out, m = (jobs[0][k] for k in ("tables", "chars", "offsets", "out", "matcher"))
     plan = m.plan()
     stream = torch.cuda.current_stream().cuda_stream
 
+    class _AllMatchers:  # launch / overflow counters over every job's handle
+        def launch_count(self):
+            return sum(j["matcher"].launch_count() for j in jobs)
+
+        def overflow_count(self):
+            return sum(j["matcher"].overflow_count() for j in jobs)
+
+        def close(self):
+            for j in jobs:
+                j["matcher"].close()
+    M = _AllMatchers()
+
     def step_device():
-        m.match_ptrs(chars.data_ptr(), offsets.data_ptr(), n, out.data_ptr(), stream)
+        for j in jobs:
+            j["matcher"].match_ptrs(j["chars"].data_ptr(), j["offsets"].data_ptr(), j["n"],
+                                    j["out"].data_ptr(), stream)
 
     # ---- kernel-resident timing (inputs already in HBM) ---------------------------------
     for _ in range(args.warmup):
@@ -346,20 +421,20 @@ def main():
     gpu_id = getattr(props, "uuid", None)
     gpu_id = f"GPU-{gpu_id}" if gpu_id and not str(gpu_id).startswith("GPU-") else (gpu_id or local_rank)
     sampler = ClockSampler(gpu_id)
-    launches0 = m.launch_count()
+    launches0 = M.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     # the timed region is padded so nvidia-smi (100 ms period) sees it
     t_pad = time.perf_counter()
     while time.perf_counter() - t_pad < 0.5:
         step_device()
         torch.cuda.synchronize()
-    launches0 = m.launch_count()
+    launches0 = M.launch_count()
     ev[0].record()
     for k in range(args.steps):
         step_device()
         ev[k + 1].record()
     barrier()
-    launches = m.launch_count() - launches0
+    launches = M.launch_count() - launches0
     while time.perf_counter() - t_pad < 1.2:
         step_device()
         torch.cuda.synchronize()
@@ -370,31 +445,37 @@ def main():
     n_all = sum_over_ranks(float(n))
     bytes_all = sum_over_ranks(float(total_bytes))
     value = n_all / (ms_per_step / 1e3)
-    if m.overflow_count():
+    if M.overflow_count():
         raise SystemExit("bench.py: strings hit a kernel limit")
 
     # ---- parity spot check against the oracle (outside every timed region) ---------------
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import helpers as H
-    k_chk = min(n, 3000)
-    off_h = offsets[:k_chk + 1].cpu().numpy().astype(np.uint64)
-    chars_h = chars[:int(off_h[-1])].cpu().numpy()
-    want = H.oracle_bits(tables, chars_h, off_h)
-    got = out[:k_chk].cpu().numpy()
-    if not np.array_equal(got, want):
-        raise SystemExit(f"bench.py: {int((got != want).sum())} of {k_chk} bits differ from the oracle")
-    match_frac = float(out.float().mean().item())
+    k_chk = 0
+    for j in jobs:
+        kj = min(j["n"], 3000 if j["bytes"] / max(1, j["n"]) < 5000 else 64)
+        off_h = j["offsets"][:kj + 1].cpu().numpy().astype(np.uint64)
+        chars_h = j["chars"][:int(off_h[-1])].cpu().numpy()
+        want = H.oracle_bits(j["tables"], chars_h, off_h)
+        got = j["out"][:kj].cpu().numpy()
+        if not np.array_equal(got, want):
+            raise SystemExit(f"bench.py: {j['name']}: {int((got != want).sum())} of {kj} bits differ from the oracle")
+        k_chk += kj
+    match_frac = float(sum(float(j["out"].float().sum().item()) for j in jobs) / max(1, n))
 
     # ---- end to end through the C ABI with HOST buffers -----------------------------------
-    h_chars = torch.empty(total_bytes, dtype=torch.uint8, pin_memory=True)
-    h_chars.copy_(chars)
-    h_off = torch.empty(n + 1, dtype=torch.int64, pin_memory=True)
-    h_off.copy_(offsets)
-    h_out = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    for j in jobs:
+        j["h_chars"] = torch.empty(j["bytes"], dtype=torch.uint8, pin_memory=True)
+        j["h_chars"].copy_(j["chars"])
+        j["h_off"] = torch.empty(j["n"] + 1, dtype=torch.int64, pin_memory=True)
+        j["h_off"].copy_(j["offsets"])
+        j["h_out"] = torch.empty(j["n"], dtype=torch.uint8, pin_memory=True)
     torch.cuda.synchronize()
 
     def step_host():
-        m.match_ptrs(h_chars.data_ptr(), h_off.data_ptr(), n, h_out.data_ptr(), stream)
+        for j in jobs:
+            j["matcher"].match_ptrs(j["h_chars"].data_ptr(), j["h_off"].data_ptr(), j["n"],
+                                    j["h_out"].data_ptr(), stream)
 
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
@@ -405,14 +486,15 @@ def main():
         step_host()
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    if not torch.equal(h_out, out.cpu()):
-        raise SystemExit("bench.py: host-buffer path and device-pointer path disagree")
+    for j in jobs:
+        if not torch.equal(j["h_out"], j["out"].cpu()):
+            raise SystemExit("bench.py: host-buffer path and device-pointer path disagree")
     e2e_value = n_all * e2e_steps / e2e_s
 
     # ---- uniform i.i.d. variant of config 2 (early exit) -----------------------------------
     extra = {}
     if wl == "config2":
-        del h_chars
+        del jobs[0]["h_chars"]
         u_chars, u_off = make_workload(W, wl, tables.text, n, 2000 + rank, dev, uniform=True)
         for _ in range(3):
             m.match_ptrs(u_chars.data_ptr(), u_off.data_ptr(), n, out.data_ptr(), stream)
@@ -454,7 +536,8 @@ def main():
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": desc, "strings_per_gpu": n, "bytes_per_gpu": total_bytes,
                        "mean_len": total_bytes / n, "match_fraction": match_frac,
-                       "engine": rxm.ENGINE_NAMES.get(plan.engine, str(plan.engine)),
+                       "engine": "+".join(sorted({rxm.ENGINE_NAMES.get(j["matcher"].plan().engine, "?") for j in jobs})),
+                       "jobs_per_step": len(jobs),
                        "l2": "inputs (%.2f GB per GPU) are larger than the 126 MB L2" % (total_bytes / 1e9),
                        "sharding": "by string index, one rank per GPU, no data-path collective"},
             "input_gb_s": bytes_all / (ms_per_step / 1e3) / 1e9,
@@ -463,7 +546,7 @@ def main():
                          "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": algo_bytes},
             "e2e": {"value": e2e_value, "unit": "strings/s",
-                    "h2d_bytes_per_step": total_bytes + 8 * (n + 1), "d2h_bytes_per_step": n + 8,
+                    "h2d_bytes_per_step": total_bytes + 8 * (n + len(jobs)), "d2h_bytes_per_step": n + 8 * len(jobs),
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
                     "input_gb_s": bytes_all * e2e_steps / e2e_s / 1e9},
             "gpu_launches": int(launches),
@@ -472,9 +555,12 @@ def main():
         }
         line.update(extra)
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(W, rxm, wl, tables, regex, flags)
+            if wl in ("config2", "config3"):
+                line["cpu_baseline"] = cpu_baseline(W, rxm, wl, tables, regex, flags)
+            else:
+                line["cpu_baseline"] = cpu_baseline_jobs(jobs, wl)
         print(json.dumps(line), flush=True)
-    m.close()
+    M.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -209,3 +209,77 @@ def shard_range(n_total: int, rank: int, world: int):
     lo = min(n_total, rank * per)
     hi = min(n_total, lo + per)
     return lo, hi
+
+
+# --------------------------------------------------------------------------------------
+# configs 4 and 5: attack strings / mixed example batches (host-side generation, numpy)
+# --------------------------------------------------------------------------------------
+
+README_EXAMPLES = {  # README.md:78-89 (test/example_N/regexp.txt + pump.txt)
+    1: ("({a*}:1&1)*", ["a"], "b", ""),
+    2: ("{(a|bb)*}:1aaba(&1|bb*aa)*", ["bbaa", "aaba", "bbaa"], "c", ""),
+    3: ("{{a*}:1(&1)*}:2b&2a*", ["a", "b", "a"], "aab", ""),
+    4: ("({a*}:1&1a*)*", ["a"], "b", ""),
+    5: ("{a*}:1c{&1}:2c(&1|&2)*", ["aa"], "b", "aacaac"),
+    6: ("({a*}:1b|&1)*", ["a"], "c", "aaab"),
+    7: ("({a*}:1)*b&1", ["a", "b", "a"], "b", ""),
+    8: ("(({a*}:1|b)(&1|b))*", ["a", "b", "a"], "c", "bb"),
+    9: ("(({aa*b}:1(&1)*)|b(b|a*)*)*", ["bbaaa"], "c", ""),
+    10: ("({a*}:1b|b&1)*c&1", ["aababba"], "cab", ""),
+}
+
+
+def _pumped(nn, pump):
+    pump_count = len(pump) // 2 + 1
+    del_count = len(pump) - pump_count
+    reps = max(1, ((nn - del_count) // pump_count - 1) // len(pump[0]))
+    res = pump[0] * reps
+    while len(res) + len(pump[0]) < (nn - del_count) // pump_count:
+        res += pump[0]
+    return res if len(pump) == 1 else (res + pump[1]) * del_count + res
+
+
+def attack_batch(pump, suffix, prefix, n, lo, hi, seed, log_uniform=True):
+    """n attack strings prefix + pumped(size) [+ suffix] (matchers/example_runner.cpp:15-29,
+    matcher.py:26-38), size log-uniform (or uniform) in [lo, hi]; half carry the failing suffix.
+    -> (chars uint8[], offsets uint64[n+1]) numpy."""
+    rng = np.random.default_rng(seed)
+    if log_uniform:
+        sizes = np.exp(rng.uniform(np.log(lo), np.log(hi), size=n)).astype(np.int64)
+    else:
+        sizes = rng.integers(lo, hi + 1, size=n)
+    with_suffix = rng.random(n) < 0.5
+    parts = []
+    for sz, ws in zip(sizes, with_suffix):
+        body = _pumped(int(sz), pump)
+        parts.append((prefix + body + (suffix if ws else "")).encode())
+    lens = np.fromiter((len(p) for p in parts), dtype=np.uint64, count=n)
+    offsets = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(lens, out=offsets[1:])
+    chars = np.frombuffer(b"".join(parts), dtype=np.uint8).copy()
+    return chars, offsets
+
+
+def mixed_example_batch(example, n, seed, lo=16, hi=512):
+    """Config 5 per-example batch: one third pumped attack strings, one third near misses of
+    them (one edit), one third random strings over the expression's letters."""
+    regex, pump, suffix, prefix = README_EXAMPLES[example]
+    rng = np.random.default_rng(seed)
+    letters = sorted({c for c in regex if c.isalpha()})
+    parts = []
+    for j in range(n):
+        kind = j % 3
+        sz = int(rng.integers(lo, hi + 1))
+        if kind == 2:
+            parts.append(bytes(rng.choice(np.frombuffer("".join(letters).encode(), dtype=np.uint8), size=sz)))
+            continue
+        s = prefix + _pumped(sz, pump) + (suffix if rng.random() < 0.5 else "")
+        if kind == 1 and len(s) > 1:
+            k = int(rng.integers(0, len(s)))
+            s = s[:k] + letters[int(rng.integers(0, len(letters)))] + s[k + 1:]
+        parts.append(s.encode())
+    lens = np.fromiter((len(p) for p in parts), dtype=np.uint64, count=n)
+    offsets = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(lens, out=offsets[1:])
+    chars = np.frombuffer(b"".join(parts), dtype=np.uint8).copy()
+    return chars, offsets
