@@ -4,13 +4,13 @@
 //
 // The warp keeps the successor set as one slot per node in shared memory.
 // A slot is a 64-bit ORDER KEY  first:28 | lowest cell name:4 | creation stamp:32  -- the
-// reference's std::set<MemoryState> order for one node -- plus the cell payload.  A step
-// takes the live configurations in (first, node) order; for each one the 32 lanes evaluate
-// the items of its host-compiled edge program (rxm_plan.cpp: compile_programs) in parallel:
-// lane x handles item x (a call entry or a non-recursive edge), builds the successor it
-// produces, and claims the target slot with atomicMin on the key; the lane whose key
-// stands after the warp has synchronised writes the payload.  The item index is the
-// creation order inside one evaluateState walk, so stamps are base + index.
+// reference's std::set<MemoryState> order for one node -- plus the cell payload.  In a step
+// ALL live configurations are expanded at once: the items of their host-compiled edge
+// programs (rxm_plan.cpp: compile_programs) are laid end to end and dealt to the lanes, 32
+// per pass; a lane builds the successor its item produces (a call entry or a non-recursive
+// edge) and claims the target slot with atomicMin on the key; the lane whose key stands
+// after the warp has synchronised writes the payload.  Creation order needs no counter:
+// prog_stamp (rxm_mfa_core.cuh) orders exactly where the reference's order is consulted.
 // Backreference blocks are compared by the whole warp, 128 bytes per iteration.
 // Idle steps (every configuration waiting inside a block) are skipped exactly as in K2.
 #include "rxm_kernels.cuh"
@@ -134,12 +134,15 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
     const ProgItem *items = items_in_smem ? s_items : gp.items;
     // ---- per-warp frontier: two buffers of SP slots ----
     const uint32_t SP = (v.n_states + 31u) & ~31u;
-    const size_t per_warp = size_t(SP) * 2 * (8 + 4 + 8 * NC);
+    const size_t per_warp = size_t(SP) * 2 * (8 + 4 + 8 * NC) + size_t(SP) * 12 + 16;
     uint8_t *wb = smem + o + size_t(warp) * per_warp;
     uint64_t *keys = reinterpret_cast<uint64_t *>(wb);                    // [2][SP]
     uint32_t *flg = reinterpret_cast<uint32_t *>(wb + size_t(SP) * 16);   // [2][SP]
     uint32_t *stt = flg + 2 * SP;                                         // [2][SP][NC]
     uint32_t *lnn = stt + 2 * SP * NC;                                    // [2][SP][NC]
+    uint32_t *l_node = lnn + 2 * SP * NC;                                 // [SP]   live list: node,
+    uint32_t *l_pb = l_node + SP;                                         // [SP]   first program item,
+    uint32_t *l_off = l_pb + SP;                                          // [SP+1] start in the laid-out items
 
     for (;;) {
         unsigned long long si = 0;
@@ -163,153 +166,172 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
             flg[v.start] = 0;
         }
         __syncwarp();
-        uint32_t cur = 0, born = 0;
+        uint32_t cur = 0;
         bool ovf = false;
         for (uint32_t i = 0;; i++) {
             uint64_t *K = keys + cur * SP, *KN = keys + (cur ^ 1u) * SP;
-            bool live = false;
-            for (uint32_t q = lane; q < SP; q += 32) {
-                live |= (K[q] != K3_EMPTY);
+            // ---- A. list the live configurations and lay their programs end to end ----
+            uint32_t m = 0, T = 0;
+            bool any_active = false;
+            for (uint32_t q = lane; q < SP; q += 32) {  // warp-uniform trip count
+                const uint64_t k = K[q];
                 KN[q] = K3_EMPTY;
-            }
-            live = __any_sync(FULL, live);
-            if (i < n32 && !live) break;  // :224-225
-            __syncwarp();
-            uint32_t done = 0;  // bit j: slot lane + 32 j already expanded in this step
-            for (;;) {
-                // next configuration in set order (first, node): mfa.cpp:206
-                uint32_t bf = 0xffffffffu, bn = 0xffffffffu;
-                for (uint32_t j = 0, q = lane; q < SP; j++, q += 32) {
-                    if ((done >> j) & 1u) continue;
-                    const uint64_t k = K[q];
-                    if (k == K3_EMPTY) continue;
+                const bool lv = (k != K3_EMPTY);
+                uint32_t pb = 0, pc = 0;
+                if (lv) {
                     const uint32_t f = uint32_t(k >> 36);
-                    if (f < bf) {
-                        bf = f;
-                        bn = q;
+                    const uint32_t fl = flg[cur * SP + q];
+                    any_active |= (f == i);
+                    bool pruned = false;
+                    if (v.reversed && !(q == v.finish && f == n32)) {  // mfa.cpp:141
+                        uint32_t need = 0;
+#pragma unroll
+                        for (int kk = 0; kk < NC; kk++) {
+                            const uint32_t c3 = (fl >> (3 * kk)) & 7u;
+                            if ((c3 & 1u) && ((c3 & 2u) || !(c3 & 4u))) need += lnn[(cur * SP + q) * NC + kk];
+                        }
+                        pruned = need > n32 - i;
+                    }
+                    if (!pruned) {
+                        const uint32_t pkey = (q << gp.n_cells) | (exists_mask(fl) & ((1u << gp.n_cells) - 1u));
+                        pb = s_begin[pkey];
+                        if (pb == 0xffffffffu) ovf = true;  // a (node, cells) pair the host analysis missed
+                        else pc = s_count[pkey];
                     }
                 }
-                const uint32_t mf = __reduce_min_sync(FULL, bf);
-                if (mf == 0xffffffffu) break;
-                const uint32_t mn = __reduce_min_sync(FULL, bf == mf ? bn : 0xffffffffu);
-                if (bf == mf && bn == mn) done |= 1u << (mn >> 5);
-                // ---- evaluateState on slot mn ----
-                K3Cfg<NC> root;
-                root.first = mf;
-                root.born = uint32_t(K[mn]);
-                root.node = mn;
-                root.flags = flg[cur * SP + mn];
+                const uint32_t bal = __ballot_sync(FULL, lv);
+                uint32_t inc = pc;  // inclusive scan of the item counts over the lanes
 #pragma unroll
-                for (int k = 0; k < NC; k++) {
-                    root.start[k] = stt[(cur * SP + mn) * NC + k];
-                    root.len[k] = lnn[(cur * SP + mn) * NC + k];
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t u = __shfl_up_sync(FULL, inc, d);
+                    if (int(lane) >= d) inc += u;
                 }
-                const bool fin = (mf == n32);
-                if (!(mn == v.finish && fin) && v.reversed && k3_need<NC>(root.flags, root.len) > n32 - i) continue;
-                const uint32_t pkey = (mn << gp.n_cells) | (exists_mask(root.flags) & ((1u << gp.n_cells) - 1u));
-                const uint32_t pb = s_begin[pkey];
-                if (pb == 0xffffffffu) {
-                    ovf = true;
-                    continue;
+                if (lv) {
+                    const uint32_t j = m + __popc(bal & ((1u << lane) - 1u));
+                    l_node[j] = q;
+                    l_pb[j] = pb;
+                    l_off[j] = T + inc - pc;
                 }
-                const uint32_t pc = s_count[pkey];
-                const bool active = (i != n32 && i == mf);
-                const bool waiting = (i != n32 && i < mf);
-                const uint32_t ch = active ? uint32_t(v.reversed ? s[n32 - 1u - i] : s[i]) : 0u;
-                const uint32_t digit_bit = (active && ch >= '1' && ch <= '9') ? (1u << (ch - '1')) : 0u;
-                for (uint32_t x0 = 0; x0 < pc; x0 += 32) {
-                    const uint32_t x = x0 + lane;
-                    bool have = false, need_cmp = false;
-                    uint32_t cmp_vs = 0, cmp_L = 0;
-                    K3Cfg<NC> cand;
-                    ProgItem it{};
-                    if (x < pc) {
-                        it = items[pb + x];
-                        if (!(fin && pi_skip_final(it))) {
-                            if (!pi_is_leaf(it)) {
-                                const uint32_t vv = pi_node(it);
-                                if ((vv == v.finish && fin) || (waiting && pi_has_leaf(it))) {  // :138-140 / :195-197
-                                    k3_working<NC>(cand, root, pi_created(it), pi_created_open(it), 0u);
-                                    cand.node = vv;
-                                    if (x != 0) cand.born = born + x + 1u;
-                                    have = true;
-                                }
-                            } else if (active) {
-                                const uint32_t kind = pi_kind(it), rc = pi_read_cell(it);
-                                if (kind == kEdgeAny || (kind == kEdgeLit && pi_sym(it) == ch)) {  // :171-175
-                                    k3_working<NC>(cand, root, pi_created(it), pi_created_open(it),
-                                                   pi_prior_reads(it) & ~digit_bit);
-                                    cand.node = pi_node(it);
-                                    cand.born = born + x + 1u;
-                                    k3_apply<NC>(cand, pi_open(it), pi_close(it), i, 1u);
-                                    cand.first += 1;
-                                    have = true;
-                                } else if (rc) {  // :176-193
-                                    const int k = int(rc) - 1;
-                                    const bool fresh = (pi_created(it) >> k) & 1u;
-                                    uint32_t L = 0, vs = 0;
+                m += __popc(bal);
+                T += __shfl_sync(FULL, inc, 31);
+            }
+            ovf = __any_sync(FULL, ovf);
+            if (i < n32 && m == 0) break;  // :224-225
+            any_active = __any_sync(FULL, any_active);
+            if (lane == 0) l_off[m] = T;
+            __syncwarp();
+            const uint32_t ch = (i < n32) ? uint32_t(v.reversed ? s[n32 - 1u - i] : s[i]) : 0u;
+            const uint32_t digit_bit = (i < n32 && ch >= '1' && ch <= '9') ? (1u << (ch - '1')) : 0u;
+            // ---- B. expand: one item per lane per pass ----
+            for (uint32_t t0 = 0; t0 < T; t0 += 32) {
+                const uint32_t tt = t0 + lane;
+                bool have = false, need_cmp = false;
+                uint32_t cmp_vs = 0, cmp_L = 0;
+                K3Cfg<NC> cand, root;
+                ProgItem it{};
+                if (tt < T) {
+                    uint32_t j = 0;
+                    while (l_off[j + 1] <= tt) j++;
+                    const uint32_t x = tt - l_off[j], rn = l_node[j];
+                    const uint64_t rk = K[rn];
+                    root.first = uint32_t(rk >> 36);
+                    root.born = 0;
+                    root.node = rn;
+                    root.flags = flg[cur * SP + rn];
 #pragma unroll
-                                    for (int kk = 0; kk < NC; kk++)
-                                        if (kk == k) {
-                                            L = fresh ? 0u : root.len[kk];
-                                            vs = root.start[kk];
-                                        }
-                                    if (n32 - i >= L) {
-                                        need_cmp = true;
-                                        cmp_vs = vs;
-                                        cmp_L = L;
+                    for (int k = 0; k < NC; k++) {
+                        root.start[k] = stt[(cur * SP + rn) * NC + k];
+                        root.len[k] = lnn[(cur * SP + rn) * NC + k];
+                    }
+                    const bool fin = (root.first == n32);
+                    const bool active = (i != n32 && i == root.first);
+                    const bool waiting = (i != n32 && i < root.first);
+                    it = items[l_pb[j] + x];
+                    if (!(fin && pi_skip_final(it))) {
+                        if (!pi_is_leaf(it)) {
+                            const uint32_t vv = pi_node(it);
+                            if ((vv == v.finish && fin) || (waiting && pi_has_leaf(it))) {  // :138-140 / :195-197
+                                k3_working<NC>(cand, root, pi_created(it), pi_created_open(it), 0u);
+                                cand.node = vv;
+                                cand.born = (x != 0) ? prog_stamp(true, rn, x) : 0u;
+                                have = true;
+                            }
+                        } else if (active) {
+                            const uint32_t kind = pi_kind(it), rc = pi_read_cell(it);
+                            if (kind == kEdgeAny || (kind == kEdgeLit && pi_sym(it) == ch)) {  // :171-175
+                                k3_working<NC>(cand, root, pi_created(it), pi_created_open(it),
+                                               pi_prior_reads(it) & ~digit_bit);
+                                cand.node = pi_node(it);
+                                cand.born = prog_stamp(false, rn, x);
+                                k3_apply<NC>(cand, pi_open(it), pi_close(it), i, 1u);
+                                cand.first += 1;
+                                have = true;
+                            } else if (rc) {  // :176-193
+                                const int k = int(rc) - 1;
+                                const bool fresh = (pi_created(it) >> k) & 1u;
+                                uint32_t L = 0, vs = 0;
+#pragma unroll
+                                for (int kk = 0; kk < NC; kk++)
+                                    if (kk == k) {
+                                        L = fresh ? 0u : root.len[kk];
+                                        vs = root.start[kk];
                                     }
+                                if (n32 - i >= L) {
+                                    need_cmp = true;
+                                    cmp_vs = vs;
+                                    cmp_L = L;
+                                    cand.born = prog_stamp(false, rn, x);
                                 }
                             }
                         }
                     }
-                    // backreference blocks: the whole warp compares each pending span
-                    uint32_t cm = __ballot_sync(FULL, need_cmp);
-                    bool cmp_ok = false;
-                    while (cm) {
-                        const int src = __ffs(int(cm)) - 1;
-                        cm &= cm - 1u;
-                        const uint32_t vs = __shfl_sync(FULL, cmp_vs, src), L = __shfl_sync(FULL, cmp_L, src);
-                        bool eq;
-                        if (!v.reversed) eq = warp_span_equal(s + vs, s + i, L, lane);
-                        else eq = warp_span_equal(s + (n32 - vs - L), s + (n32 - i - L), L, lane);
-                        if (int(lane) == src) cmp_ok = eq;
-                    }
-                    if (need_cmp && cmp_ok) {
-                        k3_working<NC>(cand, root, pi_created(it), pi_created_open(it),
-                                       pi_prior_reads(it) & ~digit_bit);
-                        cand.node = pi_node(it);
-                        cand.born = born + x + 1u;
-                        cand.first += cmp_L;
-                        k3_apply<NC>(cand, pi_open(it), pi_close(it), i, cmp_L);
-                        have = true;
-                    }
-                    // claim the target slot: smallest order key wins
-                    uint64_t k64 = 0;
-                    if (have) {
-                        k64 = k3_key(cand.first, cand.flags, cand.born);
-                        atomicMin(reinterpret_cast<unsigned long long *>(&KN[cand.node]), (unsigned long long)k64);
-                    }
-                    __syncwarp();
-                    if (have && KN[cand.node] == k64) {
-                        const uint32_t slot = (cur ^ 1u) * SP + cand.node;
-                        flg[slot] = cand.flags;
-#pragma unroll
-                        for (int k = 0; k < NC; k++) {
-                            stt[slot * NC + k] = cand.start[k];
-                            lnn[slot * NC + k] = cand.len[k];
-                        }
-                    }
-                    __syncwarp();
                 }
-                if (born > 0xfff00000u - pc) ovf = true;
-                born += pc + 1u;
+                // backreference blocks: the whole warp compares each pending span
+                uint32_t cm = __ballot_sync(FULL, need_cmp);
+                bool cmp_ok = false;
+                while (cm) {
+                    const int src = __ffs(int(cm)) - 1;
+                    cm &= cm - 1u;
+                    const uint32_t vs = __shfl_sync(FULL, cmp_vs, src), L = __shfl_sync(FULL, cmp_L, src);
+                    bool eq;
+                    if (!v.reversed) eq = warp_span_equal(s + vs, s + i, L, lane);
+                    else eq = warp_span_equal(s + (n32 - vs - L), s + (n32 - i - L), L, lane);
+                    if (int(lane) == src) cmp_ok = eq;
+                }
+                if (need_cmp && cmp_ok) {
+                    const uint32_t stamp = cand.born;
+                    k3_working<NC>(cand, root, pi_created(it), pi_created_open(it),
+                                   pi_prior_reads(it) & ~digit_bit);
+                    cand.node = pi_node(it);
+                    cand.born = stamp;
+                    cand.first += cmp_L;
+                    k3_apply<NC>(cand, pi_open(it), pi_close(it), i, cmp_L);
+                    have = true;
+                }
+                // claim the target slot: smallest order key wins
+                uint64_t k64 = 0;
+                if (have) {
+                    k64 = k3_key(cand.first, cand.flags, cand.born);
+                    atomicMin(reinterpret_cast<unsigned long long *>(&KN[cand.node]), (unsigned long long)k64);
+                }
+                __syncwarp();
+                if (have && KN[cand.node] == k64) {
+                    const uint32_t slot = (cur ^ 1u) * SP + cand.node;
+                    flg[slot] = cand.flags;
+#pragma unroll
+                    for (int k = 0; k < NC; k++) {
+                        stt[slot * NC + k] = cand.start[k];
+                        lnn[slot * NC + k] = cand.len[k];
+                    }
+                }
+                __syncwarp();
             }
             cur ^= 1u;  // states = new_states (:212)
             __syncwarp();
             if (ovf || i == n32) break;
-            // ---- fast-forward over idle steps (see MfaSim::run) ----
-            if (i + 2 < n32) {
+            // ---- C. fast-forward over idle steps (see MfaSim::run); only after a step in which
+            //         no configuration was active ----
+            if (!any_active && i + 2 < n32) {
                 bool same = true;
                 uint32_t ev = n32;
                 for (uint32_t q = lane; q < SP; q += 32) {
@@ -360,7 +382,7 @@ int launch_k3(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n
               const uint64_t *d_offsets, uint64_t n, uint8_t *d_out, unsigned long long *d_overflow,
               unsigned long long *d_next, int sm_count, cudaStream_t stream) {
     const uint32_t SP = (v.n_states + 31u) & ~31u;
-    const size_t per_warp = size_t(SP) * 2 * (8 + 4 + 8 * NC);
+    const size_t per_warp = size_t(SP) * 2 * (8 + 4 + 8 * NC) + size_t(SP) * 12 + 16;
     const size_t tab = (size_t(n_keys) * 8 + 15) & ~size_t(15);
     const bool in_smem = size_t(n_items) * sizeof(ProgItem) <= 64 * 1024;
     const size_t smem = tab + (in_smem ? size_t(n_items) * sizeof(ProgItem) : 0) + K3_WARPS * per_warp;

@@ -445,6 +445,24 @@ RXM_UNROLL
     }
 }
 
+// Creation order WITHOUT a counter.  Inside one step, everything that is inserted into the
+// successor set is either (a) the re-insertion of the configuration that already sits on
+// that node (mfa.cpp:195-197 / 138-140 on the root call) -- it was created in an earlier
+// step, so it is older than anything created now -- or (b) created in this step by source
+// configuration c (visited in (first, node) order) at item x of its program.  Two candidates
+// only ever compete when they land on the same node with the same `first` and lowest cell:
+//   * successors of LEAF items come from ACTIVE sources (first == i): all the same `first`,
+//     so their visiting order is the node order;
+//   * ENTER items only insert for WAITING / final sources (first > i), and their `first` is
+//     the source's, so two of them tie only if the sources' `first` agree: node order again;
+//   * an active source is visited before every waiting one.
+// Hence (0 for (a)) or 1 + (ENTER? 1:0) << 19 | source node << 12 | item index orders exactly
+// like the reference's allocation order wherever that order is consulted, and the sources
+// of a step can be expanded in ANY order (K3 expands them all at once).
+RXM_HD uint32_t prog_stamp(bool is_enter, uint32_t src_node, uint32_t item) {
+    return 1u + ((is_enter ? 1u : 0u) << 19) + (src_node << 12) + item;
+}
+
 // Sequential interpreter of the edge programs: same results as MfaSim, no recursion.
 template <int NC, int CAP>
 struct ProgSim {
@@ -506,7 +524,7 @@ RXM_UNROLL
                     cfg_t w;
                     prog_working<NC>(w, root, pi_created(it), pi_created_open(it), 0u);
                     w.node = v;
-                    if (x != 0) w.born = born + x + 1u;
+                    w.born = (x != 0) ? prog_stamp(true, root.node, x) : 0u;
                     insert(w);
                 }
                 continue;
@@ -518,7 +536,7 @@ RXM_UNROLL
                 cfg_t nx;
                 prog_working<NC>(nx, root, pi_created(it), pi_created_open(it), pi_prior_reads(it) & ~digit_bit);
                 nx.node = pi_node(it);
-                nx.born = born + x + 1u;
+                nx.born = prog_stamp(false, root.node, x);
                 apply_actions<NC>(nx, pi_open(it), pi_close(it), i, 1u);
                 nx.first += 1;
                 insert(nx);
@@ -532,36 +550,20 @@ RXM_UNROLL
                     prog_working<NC>(nx, root, pi_created(it), pi_created_open(it),
                                      pi_prior_reads(it) & ~digit_bit);
                     nx.node = pi_node(it);
-                    nx.born = born + x + 1u;
+                    nx.born = prog_stamp(false, root.node, x);
                     nx.first += L;
                     apply_actions<NC>(nx, pi_open(it), pi_close(it), i, L);
                     insert(nx);
                 }
             }
         }
-        born += cntp + 1u;
     }
 
     RXM_HD void step(const MfaView &t, const ProgView &pv, const Reader &rd, uint32_t i) {
         cfg_t *cur = buf[nb ^ 1u];
         const uint32_t ncur = cnt[nb ^ 1u];
         cnt[nb] = 0;
-        uint64_t last = 0;
-        bool have_last = false;
-        for (uint32_t r = 0; r < ncur; r++) {
-            uint32_t best = 0;
-            uint64_t bestkey = ~uint64_t(0);
-            for (uint32_t j = 0; j < ncur; j++) {
-                const uint64_t key = (uint64_t(cur[j].first) << 32) | cur[j].node;
-                if (key < bestkey && (!have_last || key > last)) {
-                    bestkey = key;
-                    best = j;
-                }
-            }
-            last = bestkey;
-            have_last = true;
-            eval(t, pv, rd, cur[best], i);
-        }
+        for (uint32_t j = 0; j < ncur; j++) eval(t, pv, rd, cur[j], i);  // any order: see prog_stamp
     }
 
     RXM_HD int run(const MfaView &t, const ProgView &pv, const Reader &rd) {
