@@ -64,6 +64,8 @@ struct rxm_matcher {
     rxm::ProgItem *d_items = nullptr;
     uint32_t *d_prog_begin = nullptr;
     uint32_t *d_prog_count = nullptr;
+    uint32_t k3_tile = 32;  // lanes per string
+    bool k3_tile_forced = false;
 
     // staging workspace for host buffers
     uint8_t *d_chars = nullptr;
@@ -171,6 +173,15 @@ extern "C" int rxm_tables_upload(const rxm_tables *host_tables, int device, rxm_
             if ((st = upload_vec(m->prog.begin, &m->d_prog_begin)) != RXM_OK) return fail(st);
             if ((st = upload_vec(m->prog.count, &m->d_prog_count)) != RXM_OK) return fail(st);
             m->info.engine = RXM_ENGINE_K3_WARP;
+            // short programs: several strings per warp (a step's items fit one pass of the tile)
+            m->k3_tile = m->prog.max_count <= 8 ? 8 : (m->prog.max_count <= 16 ? 16 : 32);
+            if (const char *tl = getenv("RXM_K3_TILE")) {
+                const int x = atoi(tl);
+                if (x == 8 || x == 16 || x == 32) {
+                    m->k3_tile = uint32_t(x);
+                    m->k3_tile_forced = true;
+                }
+            }
         } else if (force && std::strcmp(force, "k3") == 0) {
             err = "RXM_MFA_ENGINE=k3 but the edge programs cannot be built: " + perr;
             return fail(RXM_ERR_UNSUPPORTED);
@@ -226,8 +237,9 @@ extern "C" int rxm_overflow_count(rxm_handle h, uint64_t *count) {
     return RXM_OK;
 }
 
+// total_chars: offsets[n] - offsets[0] if the caller knows it, else ~0ull
 static int launch_on_device(rxm_matcher *m, const uint8_t *d_chars, const uint64_t *d_offsets,
-                            uint64_t n, uint8_t *d_out, cudaStream_t stream) {
+                            uint64_t n, uint8_t *d_out, cudaStream_t stream, uint64_t total_chars) {
     CU(cudaMemsetAsync(m->d_overflow, 0, sizeof(unsigned long long), stream));
     if (n == 0) return RXM_OK;
     int launched = 0;
@@ -258,8 +270,22 @@ static int launch_on_device(rxm_matcher *m, const uint8_t *d_chars, const uint64
         rxm::MfaView v{m->d_edge_begin, m->d_edges, m->tables.n_states(), m->tables.start,
                        m->tables.finish, m->tables.reversed};
         rxm::ProgView gp{m->d_items, m->d_prog_begin, m->d_prog_count, m->prog.n_cells};
+        // Lanes per string: short programs let 2 or 4 strings share a warp, which pays for
+        // many short strings; long strings want the whole warp (per-string latency, wide
+        // block compares).  The mean length decides; with device buffers it costs one 8-byte
+        // read-back of offsets[n].
+        uint32_t tile = m->k3_tile;
+        if (tile < 32 && !m->k3_tile_forced) {
+            if (total_chars == ~0ull) {
+                uint64_t ends[1] = {0};
+                CU(cudaMemcpyAsync(ends, d_offsets + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+                CU(cudaStreamSynchronize(stream));
+                total_chars = ends[0];
+            }
+            if (total_chars / n > 4096) tile = 32;
+        }
         st = rxm::k3_launch(v, gp, uint32_t(m->prog.items.size()), uint32_t(m->prog.begin.size()),
-                            m->tables.n_cells, d_chars, d_offsets, n, d_out, m->d_overflow, m->d_overflow + 1,
+                            m->tables.n_cells, tile, d_chars, d_offsets, n, d_out, m->d_overflow, m->d_overflow + 1,
                             m->sm_count, stream, &launched);
     } else {
         rxm::MfaView v{m->d_edge_begin, m->d_edges, m->tables.n_states(), m->tables.start,
@@ -285,7 +311,7 @@ extern "C" int rxm_match_batch(rxm_handle h, const uint8_t *chars, const uint64_
     const bool dev_out = is_device_ptr(out_bits);
     const bool dev_chars = chars ? is_device_ptr(chars) : dev_off;
     if (dev_off && dev_out && dev_chars)
-        return launch_on_device(m, chars, offsets, n, out_bits, stream);
+        return launch_on_device(m, chars, offsets, n, out_bits, stream, ~0ull);
     if (dev_off || dev_out || (chars && dev_chars)) return RXM_ERR_INVALID;  // all host or all device
 
     // host buffers: stage through the handle's workspace
@@ -315,7 +341,7 @@ extern "C" int rxm_match_batch(rxm_handle h, const uint8_t *chars, const uint64_
     }
     if (total) CU(cudaMemcpyAsync(m->d_chars, chars, total, cudaMemcpyHostToDevice, stream));
     CU(cudaMemcpyAsync(m->d_offsets, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
-    int st = launch_on_device(m, m->d_chars, m->d_offsets, n, m->d_bits, stream);
+    int st = launch_on_device(m, m->d_chars, m->d_offsets, n, m->d_bits, stream, total);
     if (st != RXM_OK) return st;
     unsigned long long ovf = 0;
     if (n) CU(cudaMemcpyAsync(out_bits, m->d_bits, n, cudaMemcpyDeviceToHost, stream));

@@ -20,7 +20,6 @@ namespace rxm {
 namespace {
 
 constexpr uint64_t K3_EMPTY = ~0ull;
-constexpr uint32_t FULL = 0xffffffffu;
 constexpr int K3_WARPS = 8;
 
 __device__ __forceinline__ uint64_t k3_key(uint32_t first, uint32_t flags, uint32_t born) {
@@ -28,12 +27,14 @@ __device__ __forceinline__ uint64_t k3_key(uint32_t first, uint32_t flags, uint3
 }
 
 // mem[pa, pa+L) == mem[pb, pb+L) ?  Whole warp, 4 bytes per lane per iteration, any alignment.
-__device__ __forceinline__ bool warp_span_equal(const uint8_t *pa, const uint8_t *pb, uint32_t L, uint32_t lane) {
+template <int TILE>
+__device__ __forceinline__ bool warp_span_equal(const uint8_t *pa, const uint8_t *pb, uint32_t L, uint32_t lane,
+                                                uint32_t tmask) {
     if (pa == pb || L == 0) return true;
     const uint32_t ba = uint32_t(reinterpret_cast<uintptr_t>(pa)) & 3u, bb = uint32_t(reinterpret_cast<uintptr_t>(pb)) & 3u;
     const uint32_t *wa = reinterpret_cast<const uint32_t *>(pa - ba);
     const uint32_t *wb = reinterpret_cast<const uint32_t *>(pb - bb);
-    for (uint32_t base = 0; base < L; base += 128u) {
+    for (uint32_t base = 0; base < L; base += 4u * TILE) {
         const uint32_t off = base + lane * 4u;
         bool ne = false;
         if (off < L) {
@@ -46,9 +47,17 @@ __device__ __forceinline__ bool warp_span_equal(const uint8_t *pa, const uint8_t
             if (take < 4u) x &= (1u << (8u * take)) - 1u;
             ne = x != 0u;
         }
-        if (__any_sync(FULL, ne)) return false;
+        if (__any_sync(tmask, ne)) return false;
     }
     return true;
+}
+
+template <int NC>
+__device__ __forceinline__ uint32_t exists_mask_n(uint32_t flags) {  // bit k <- flags bit 3k, k < NC
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < NC; k++) m |= ((flags >> (3 * k)) & 1u) << k;
+    return m;
 }
 
 template <int NC>
@@ -107,14 +116,19 @@ __device__ __forceinline__ uint32_t k3_need(uint32_t flags, const uint32_t *len)
     return need;
 }
 
-template <int NC>
+// TILE lanes cooperate on one string (TILE = 32: the whole warp; 16 / 8: two / four strings
+// per warp when the edge programs are short -- the items of a step fit one pass anyway).
+template <int NC, int TILE>
 __global__ void __launch_bounds__(K3_WARPS * 32)
 k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, uint32_t items_in_smem,
                    const uint8_t *__restrict__ chars, const uint64_t *__restrict__ offsets, uint64_t n,
                    uint8_t *__restrict__ out, unsigned long long *__restrict__ overflow,
                    unsigned long long *__restrict__ next_string) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & (TILE - 1u);              // rank inside the tile
+    const uint32_t tile = threadIdx.x / TILE;                     // tile index inside the block
+    const uint32_t tshift = (threadIdx.x & 31u) & ~(TILE - 1u);   // first warp lane of this tile
+    const uint32_t FULL = (TILE == 32) ? 0xffffffffu : (((1u << TILE) - 1u) << tshift);
     // ---- block-shared program tables ----
     uint32_t *s_begin = reinterpret_cast<uint32_t *>(smem);
     uint32_t *s_count = s_begin + n_keys;
@@ -135,7 +149,7 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
     // ---- per-warp frontier: two buffers of SP slots ----
     const uint32_t SP = (v.n_states + 31u) & ~31u;
     const size_t per_warp = size_t(SP) * 2 * (8 + 4 + 8 * NC) + size_t(SP) * 12 + 16;
-    uint8_t *wb = smem + o + size_t(warp) * per_warp;
+    uint8_t *wb = smem + o + size_t(tile) * per_warp;
     uint64_t *keys = reinterpret_cast<uint64_t *>(wb);                    // [2][SP]
     uint32_t *flg = reinterpret_cast<uint32_t *>(wb + size_t(SP) * 16);   // [2][SP]
     uint32_t *stt = flg + 2 * SP;                                         // [2][SP][NC]
@@ -144,36 +158,55 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
     uint32_t *l_pb = l_node + SP;                                         // [SP]   first program item,
     uint32_t *l_off = l_pb + SP;                                          // [SP+1] start in the laid-out items
 
+    // All tiles of a warp run the loop below in LOCK-STEP: one iteration is, per tile, either
+    // "take the next string" or "one step of the string in hand".  Tiles therefore execute the
+    // same instructions on different strings instead of drifting apart (which would serialise
+    // them); a tile that is out of work idles until every tile of the warp is.
+    bool have_str = false, exhausted = false;
+    unsigned long long si = 0;
+    const uint8_t *s = nullptr;
+    uint32_t n32 = 0, cur = 0, i = 0;
+    bool ovf = false;
     for (;;) {
-        unsigned long long si = 0;
-        if (lane == 0) si = atomicAdd(next_string, 1ull);
-        si = __shfl_sync(FULL, si, 0);
-        if (si >= n) break;
-        const uint64_t sb = offsets[si], se = offsets[si + 1];
-        if (se - sb >= (1ull << 28)) {  // first must fit 28 bits of the order key
-            if (lane == 0) {
-                atomicAdd(overflow, 1ull);
-                out[si] = 0;
+        if (TILE != 32) __syncwarp(0xffffffffu);
+        if (!have_str && !exhausted) {
+            if (lane == 0) si = atomicAdd(next_string, 1ull);
+            si = __shfl_sync(FULL, si, 0, TILE);
+            if (si >= n) {
+                exhausted = true;
+            } else {
+                const uint64_t sb = offsets[si], se = offsets[si + 1];
+                if (se - sb >= (1ull << 28)) {  // first must fit 28 bits of the order key
+                    if (lane == 0) {
+                        atomicAdd(overflow, 1ull);
+                        out[si] = 0;
+                    }
+                } else {
+                    s = chars + sb;
+                    n32 = uint32_t(se - sb);
+                    for (uint32_t q = lane; q < 2 * SP; q += TILE) keys[q] = K3_EMPTY;
+                    __syncwarp(FULL);
+                    if (lane == 0) {  // (0, start, {})  mfa.cpp:217-219
+                        keys[v.start] = k3_key(0, 0, 0);
+                        flg[v.start] = 0;
+                    }
+                    __syncwarp(FULL);
+                    cur = 0;
+                    i = 0;
+                    ovf = false;
+                    have_str = true;
+                }
             }
-            continue;
         }
-        const uint8_t *s = chars + sb;
-        const uint32_t n32 = uint32_t(se - sb);
-        for (uint32_t q = lane; q < 2 * SP; q += 32) keys[q] = K3_EMPTY;
-        __syncwarp();
-        if (lane == 0) {  // (0, start, {})  mfa.cpp:217-219
-            keys[v.start] = k3_key(0, 0, 0);
-            flg[v.start] = 0;
-        }
-        __syncwarp();
-        uint32_t cur = 0;
-        bool ovf = false;
-        for (uint32_t i = 0;; i++) {
+        if (__all_sync(0xffffffffu, exhausted && !have_str)) break;
+        if (!have_str) continue;
+        bool finished = false;
+        {
             uint64_t *K = keys + cur * SP, *KN = keys + (cur ^ 1u) * SP;
             // ---- A. list the live configurations and lay their programs end to end ----
             uint32_t m = 0, T = 0;
             bool any_active = false;
-            for (uint32_t q = lane; q < SP; q += 32) {  // warp-uniform trip count
+            for (uint32_t q = lane; q < SP; q += TILE) {  // tile-uniform trip count
                 const uint64_t k = K[q];
                 KN[q] = K3_EMPTY;
                 const bool lv = (k != K3_EMPTY);
@@ -193,17 +226,17 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
                         pruned = need > n32 - i;
                     }
                     if (!pruned) {
-                        const uint32_t pkey = (q << gp.n_cells) | (exists_mask(fl) & ((1u << gp.n_cells) - 1u));
+                        const uint32_t pkey = (q << gp.n_cells) | exists_mask_n<NC>(fl);
                         pb = s_begin[pkey];
                         if (pb == 0xffffffffu) ovf = true;  // a (node, cells) pair the host analysis missed
                         else pc = s_count[pkey];
                     }
                 }
-                const uint32_t bal = __ballot_sync(FULL, lv);
-                uint32_t inc = pc;  // inclusive scan of the item counts over the lanes
+                const uint32_t bal = (__ballot_sync(FULL, lv) >> tshift) & ((TILE == 32) ? 0xffffffffu : ((1u << TILE) - 1u));
+                uint32_t inc = pc;  // inclusive scan of the item counts over the tile's lanes
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t u = __shfl_up_sync(FULL, inc, d);
+                for (int d = 1; d < TILE; d <<= 1) {
+                    const uint32_t u = __shfl_up_sync(FULL, inc, d, TILE);
                     if (int(lane) >= d) inc += u;
                 }
                 if (lv) {
@@ -213,17 +246,18 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
                     l_off[j] = T + inc - pc;
                 }
                 m += __popc(bal);
-                T += __shfl_sync(FULL, inc, 31);
+                T += __shfl_sync(FULL, inc, TILE - 1, TILE);
             }
             ovf = __any_sync(FULL, ovf);
-            if (i < n32 && m == 0) break;  // :224-225
             any_active = __any_sync(FULL, any_active);
+            if (i < n32 && m == 0) finished = true;  // :224-225
+            else {
             if (lane == 0) l_off[m] = T;
-            __syncwarp();
+            __syncwarp(FULL);
             const uint32_t ch = (i < n32) ? uint32_t(v.reversed ? s[n32 - 1u - i] : s[i]) : 0u;
             const uint32_t digit_bit = (i < n32 && ch >= '1' && ch <= '9') ? (1u << (ch - '1')) : 0u;
             // ---- B. expand: one item per lane per pass ----
-            for (uint32_t t0 = 0; t0 < T; t0 += 32) {
+            for (uint32_t t0 = 0; t0 < T; t0 += TILE) {
                 const uint32_t tt = t0 + lane;
                 bool have = false, need_cmp = false;
                 uint32_t cmp_vs = 0, cmp_L = 0;
@@ -287,15 +321,15 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
                     }
                 }
                 // backreference blocks: the whole warp compares each pending span
-                uint32_t cm = __ballot_sync(FULL, need_cmp);
+                uint32_t cm = (__ballot_sync(FULL, need_cmp) >> tshift) & ((TILE == 32) ? 0xffffffffu : ((1u << TILE) - 1u));
                 bool cmp_ok = false;
                 while (cm) {
                     const int src = __ffs(int(cm)) - 1;
                     cm &= cm - 1u;
-                    const uint32_t vs = __shfl_sync(FULL, cmp_vs, src), L = __shfl_sync(FULL, cmp_L, src);
+                    const uint32_t vs = __shfl_sync(FULL, cmp_vs, src, TILE), L = __shfl_sync(FULL, cmp_L, src, TILE);
                     bool eq;
-                    if (!v.reversed) eq = warp_span_equal(s + vs, s + i, L, lane);
-                    else eq = warp_span_equal(s + (n32 - vs - L), s + (n32 - i - L), L, lane);
+                    if (!v.reversed) eq = warp_span_equal<TILE>(s + vs, s + i, L, lane, FULL);
+                    else eq = warp_span_equal<TILE>(s + (n32 - vs - L), s + (n32 - i - L), L, lane, FULL);
                     if (int(lane) == src) cmp_ok = eq;
                 }
                 if (need_cmp && cmp_ok) {
@@ -314,7 +348,7 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
                     k64 = k3_key(cand.first, cand.flags, cand.born);
                     atomicMin(reinterpret_cast<unsigned long long *>(&KN[cand.node]), (unsigned long long)k64);
                 }
-                __syncwarp();
+                __syncwarp(FULL);
                 if (have && KN[cand.node] == k64) {
                     const uint32_t slot = (cur ^ 1u) * SP + cand.node;
                     flg[slot] = cand.flags;
@@ -324,17 +358,17 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
                         lnn[slot * NC + k] = cand.len[k];
                     }
                 }
-                __syncwarp();
+                __syncwarp(FULL);
             }
             cur ^= 1u;  // states = new_states (:212)
-            __syncwarp();
-            if (ovf || i == n32) break;
+            __syncwarp(FULL);
+            if (ovf || i == n32) finished = true;
             // ---- C. fast-forward over idle steps (see MfaSim::run); only after a step in which
             //         no configuration was active ----
-            if (!any_active && i + 2 < n32) {
+            else if (!any_active && i + 2 < n32) {
                 bool same = true;
                 uint32_t ev = n32;
-                for (uint32_t q = lane; q < SP; q += 32) {
+                for (uint32_t q = lane; q < SP; q += TILE) {
                     const uint64_t ka = keys[cur * SP + q], kb = keys[(cur ^ 1u) * SP + q];
                     const bool va = ka != K3_EMPTY, vb2 = kb != K3_EMPTY;
                     if (va != vb2) same = false;
@@ -362,39 +396,45 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
                 }
                 same = __all_sync(FULL, same);
                 ev = __reduce_min_sync(FULL, ev);
-                if (same && ev > i + 2) i = ev - 2;  // the loop increment makes the next step ev - 1
+                if (same && ev > i + 2) i = ev - 2;  // the increment below makes the next step ev - 1
             }
+            }  // else of (i < n32 && m == 0)
+            i++;
         }
-        if (lane == 0) {
-            if (ovf) {
-                atomicAdd(overflow, 1ull);
-                out[si] = 0;
-            } else {
-                out[si] = keys[cur * SP + v.finish] != K3_EMPTY ? 1 : 0;  // :230-235
+        if (finished) {
+            if (lane == 0) {
+                if (ovf) {
+                    atomicAdd(overflow, 1ull);
+                    out[si] = 0;
+                } else {
+                    out[si] = keys[cur * SP + v.finish] != K3_EMPTY ? 1 : 0;  // :230-235
+                }
             }
+            __syncwarp(FULL);
+            have_str = false;
         }
-        __syncwarp();
     }
 }
 
-template <int NC>
+template <int NC, int TILE>
 int launch_k3(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n_keys, const uint8_t *d_chars,
               const uint64_t *d_offsets, uint64_t n, uint8_t *d_out, unsigned long long *d_overflow,
               unsigned long long *d_next, int sm_count, cudaStream_t stream) {
+    constexpr int TILES = K3_WARPS * 32 / TILE;  // strings in flight per block
     const uint32_t SP = (v.n_states + 31u) & ~31u;
-    const size_t per_warp = size_t(SP) * 2 * (8 + 4 + 8 * NC) + size_t(SP) * 12 + 16;
+    const size_t per_tile = size_t(SP) * 2 * (8 + 4 + 8 * NC) + size_t(SP) * 12 + 16;
     const size_t tab = (size_t(n_keys) * 8 + 15) & ~size_t(15);
     const bool in_smem = size_t(n_items) * sizeof(ProgItem) <= 64 * 1024;
-    const size_t smem = tab + (in_smem ? size_t(n_items) * sizeof(ProgItem) : 0) + K3_WARPS * per_warp;
+    const size_t smem = tab + (in_smem ? size_t(n_items) * sizeof(ProgItem) : 0) + TILES * per_tile;
     if (smem > 200 * 1024) return RXM_ERR_UNSUPPORTED;
-    auto kern = k3_mfa_warp_kernel<NC>;
+    auto kern = k3_mfa_warp_kernel<NC, TILE>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
         return RXM_ERR_CUDA;
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, K3_WARPS * 32, smem) != cudaSuccess || nb <= 0)
         return RXM_ERR_CUDA;
     uint64_t blocks = uint64_t(sm_count) * nb;
-    const uint64_t need = (n + K3_WARPS - 1) / K3_WARPS;
+    const uint64_t need = (n + TILES - 1) / TILES;
     if (blocks > need) blocks = need;
     if (cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), stream) != cudaSuccess) return RXM_ERR_CUDA;
     kern<<<unsigned(blocks), K3_WARPS * 32, smem, stream>>>(v, gp, n_items, n_keys, in_smem ? 1u : 0u, d_chars,
@@ -402,17 +442,26 @@ int launch_k3(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n
     return RXM_OK;
 }
 
+template <int NC>
+int launch_k3_tile(uint32_t tile, const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n_keys,
+                   const uint8_t *d_chars, const uint64_t *d_offsets, uint64_t n, uint8_t *d_out,
+                   unsigned long long *d_overflow, unsigned long long *d_next, int sm_count, cudaStream_t stream) {
+    if (tile <= 8) return launch_k3<NC, 8>(v, gp, n_items, n_keys, d_chars, d_offsets, n, d_out, d_overflow, d_next, sm_count, stream);
+    if (tile <= 16) return launch_k3<NC, 16>(v, gp, n_items, n_keys, d_chars, d_offsets, n, d_out, d_overflow, d_next, sm_count, stream);
+    return launch_k3<NC, 32>(v, gp, n_items, n_keys, d_chars, d_offsets, n, d_out, d_overflow, d_next, sm_count, stream);
+}
+
 }  // namespace
 
 int k3_launch(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n_keys, uint32_t n_cells,
-              const uint8_t *d_chars, const uint64_t *d_offsets, uint64_t n, uint8_t *d_out,
+              uint32_t tile, const uint8_t *d_chars, const uint64_t *d_offsets, uint64_t n, uint8_t *d_out,
               unsigned long long *d_overflow, unsigned long long *d_next, int sm_count, cudaStream_t stream,
               int *launched) {
     *launched = 0;
     int st;
-    if (n_cells <= 1) st = launch_k3<1>(v, gp, n_items, n_keys, d_chars, d_offsets, n, d_out, d_overflow, d_next, sm_count, stream);
-    else if (n_cells <= 2) st = launch_k3<2>(v, gp, n_items, n_keys, d_chars, d_offsets, n, d_out, d_overflow, d_next, sm_count, stream);
-    else if (n_cells <= 4) st = launch_k3<4>(v, gp, n_items, n_keys, d_chars, d_offsets, n, d_out, d_overflow, d_next, sm_count, stream);
+    if (n_cells <= 1) st = launch_k3_tile<1>(tile, v, gp, n_items, n_keys, d_chars, d_offsets, n, d_out, d_overflow, d_next, sm_count, stream);
+    else if (n_cells <= 2) st = launch_k3_tile<2>(tile, v, gp, n_items, n_keys, d_chars, d_offsets, n, d_out, d_overflow, d_next, sm_count, stream);
+    else if (n_cells <= 4) st = launch_k3_tile<4>(tile, v, gp, n_items, n_keys, d_chars, d_offsets, n, d_out, d_overflow, d_next, sm_count, stream);
     else return RXM_ERR_UNSUPPORTED;
     if (st == RXM_OK) *launched = 1;
     return st;

@@ -68,7 +68,7 @@ int k2_launch(const MfaView &dev_view, uint32_t n_cells, uint32_t n_edges, const
 
 // ---- K3: MFA, one warp per string, over host-compiled edge programs --------------------------
 int k3_launch(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n_keys, uint32_t n_cells,
-              const uint8_t *d_chars, const uint64_t *d_offsets, uint64_t n, uint8_t *d_out,
+              uint32_t tile /* lanes per string: 8, 16 or 32 */, const uint8_t *d_chars, const uint64_t *d_offsets, uint64_t n, uint8_t *d_out,
               unsigned long long *d_overflow, unsigned long long *d_next, int sm_count, cudaStream_t stream,
               int *launched);
 

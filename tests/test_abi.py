@@ -64,3 +64,44 @@ def test_no_device_is_an_error_not_a_fallback():
     with pytest.raises(rxm.RxmError) as e:
         rxm.Matcher(t, 0)
     assert e.value.status in (rxm.RXM_ERR_NO_DEVICE, rxm.RXM_ERR_CUDA)
+
+
+# ---- planner limits: reported as RXM_ERR_UNSUPPORTED at upload, never a fallback ------------
+EPS_CYCLE_NFA = """rxm-tables 1
+kind nfa
+reversed 0
+states 3
+start 0
+finish 2
+cells 0
+edges 3
+0 E - 1
+1 E - 0
+1 L a 2
+end
+"""
+
+EPS_CYCLE_MFA = """rxm-tables 1
+kind mfa
+reversed 0
+states 3
+start 0
+finish 2
+cells 1
+edges 3
+0 E - 1
+1 E - 0
+1 L a 2 o1
+end
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("text", [EPS_CYCLE_NFA, EPS_CYCLE_MFA])
+def test_epsilon_cycle_is_unsupported(text):
+    """The reference recurses without bound on an epsilon cycle (automata.cpp:108-110,
+    mfa.cpp:143-147: stack overflow); the planner refuses the table instead."""
+    t = rxm.Tables(text)
+    with pytest.raises(rxm.RxmError) as e:
+        rxm.Matcher(t, 0)
+    assert e.value.status == rxm.RXM_ERR_UNSUPPORTED
