@@ -235,20 +235,30 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     return v;
 }
 
-// CH = bytes per lane per stage, STAGES = ring depth.  Lane stride CH+16 keeps the
-// per-lane LDS.128 and the cooperative 16-byte cp.async writes bank-conflict free.
-template <bool REV, class Step, int CH, int STAGES>
+template <bool REV>
+__device__ __forceinline__ uint32_t vec_byte(const uint32_t (&w)[4], int k) {  // k-th byte in READING order
+    const int mb = REV ? 15 - k : k;
+    return __byte_perm(w[mb >> 2], 0, 0x4440 + (mb & 3));
+}
+
+// CH = bytes per lane per stage, STAGES = ring depth, NS = strings walked by one lane at the
+// same time (independent lookup chains: the LDS -> IMAD -> LDS chain of one string is ~34
+// cycles per byte, so two interleaved chains double what a resident warp can issue).
+// Lane stride CH+16 keeps the per-lane LDS.128 and the cooperative 16-byte cp.async writes
+// bank-conflict free.
+template <bool REV, class Step, int CH, int STAGES, int NS>
 __device__ __forceinline__ void k1_scan_body(const Step st, const uint8_t *__restrict__ chars,
                                              const K1Rec *__restrict__ recs, uint64_t n,
                                              uint8_t *__restrict__ out, const uint8_t *accept,
                                              uint32_t start_state, uint32_t *__restrict__ task_counter,
                                              uint32_t ring_base /* this warp's ring, smem address */) {
     constexpr int LS = CH + 16;             // lane stride in the ring
-    constexpr int STAGE_BYTES = 32 * LS;
+    constexpr int STR_BYTES = 32 * LS;      // one string slot of every lane
+    constexpr int STAGE_BYTES = NS * STR_BYTES;
     constexpr int VPC = CH / 16;            // vectors per chunk
     constexpr int LPT = CH / 16;            // lanes cooperating on one target lane's chunk
     constexpr int TPI = 32 / LPT;           // target lanes served per cp.async instruction
-    constexpr int NI = 32 / TPI;            // cp.async instructions per round (== LPT)
+    constexpr int NI = 32 / TPI;            // cp.async instructions per round and string (== LPT)
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t part = lane % LPT;       // which 16-byte piece of the chunk this lane copies
     const uint32_t tsub = lane / LPT;       // which of the TPI targets
@@ -258,65 +268,72 @@ __device__ __forceinline__ void k1_scan_body(const Step st, const uint8_t *__res
         uint32_t task = 0;
         if (lane == 0) task = atomicAdd(task_counter, 1u);
         task = __shfl_sync(0xffffffffu, task, 0);
-        const uint64_t first = uint64_t(task) * 32u;
+        const uint64_t first = uint64_t(task) * (32u * NS);
         if (first >= n) break;
-        K1Rec rec;
-        rec.start = 0;
-        rec.len = 0;
-        rec.idx = 0xffffffffu;
-        if (first + lane < n) rec = recs[first + lane];
 
-        // The lane's "stream": 16-byte vectors covering [p, p+len), anchored at the
-        // aligned vector that holds the first byte read (forward: the string's first
-        // byte; reversed: its last byte).  h = pad bytes in front of the stream.
-        const uint8_t *p = chars + rec.start;
-        const uint32_t len = rec.len;
-        uint32_t h;
-        const uint8_t *anchor;  // forward: address of vector 0; reversed: END of vector 0
-        if (!REV) {
-            h = uint32_t(reinterpret_cast<uintptr_t>(p)) & 15u;
-            anchor = p - h;
-        } else {
-            const uint8_t *e = p + len;
-            h = (16u - (uint32_t(reinterpret_cast<uintptr_t>(e)) & 15u)) & 15u;
-            anchor = e + h;
-        }
-        const uint32_t nbytes = len ? h + len : 0u;  // stream length incl. front pad
-        const uint32_t nvec = (nbytes + 15u) >> 4;
-        // vectors [vlo, vhi) are complete (no pad, no tail) in EVERY lane of the warp
-        const uint32_t vlo = __reduce_max_sync(0xffffffffu, h ? 1u : 0u);
-        const uint32_t vhi = __reduce_min_sync(0xffffffffu, nbytes >> 4);
-        const uint32_t nrounds = (__reduce_max_sync(0xffffffffu, nvec) + VPC - 1) / VPC;
-
-        // sources / limits of the target lanes this lane copies for (round-invariant)
-        const uint8_t *src[NI];
-        uint32_t src_lim[NI];
+        // A lane's "stream" for string s: 16-byte vectors covering [p, p+len), anchored at the
+        // aligned vector that holds the first byte read (forward: the string's first byte;
+        // reversed: its last byte).  h = pad bytes in front of the stream.
+        uint32_t idx[NS], h[NS], nbytes[NS], q[NS];
+        const uint8_t *src[NS][NI];
+        uint32_t src_lim[NS][NI];
         uint32_t dst_off[NI];
+        uint32_t vlo = 0, vhi = 0xffffffffu, nvmax = 0;
 #pragma unroll
-        for (int g = 0; g < NI; g++) {
-            const uint32_t t = uint32_t(g) * TPI + tsub;
-            const uint64_t a = __shfl_sync(0xffffffffu, uint64_t(reinterpret_cast<uintptr_t>(anchor)), int(t));
-            const uint32_t nv = __shfl_sync(0xffffffffu, nvec, int(t));
-            src_lim[g] = nv * 16u - part * 16u;  // copy while round offset < this
-            if (nv * 16u < part * 16u) src_lim[g] = 0;
-            if (!REV) src[g] = reinterpret_cast<const uint8_t *>(uintptr_t(a)) + part * 16u;
-            else src[g] = reinterpret_cast<const uint8_t *>(uintptr_t(a)) - (part + 1u) * 16u;
-            dst_off[g] = ring_base + t * LS + part * 16u;
+        for (int s = 0; s < NS; s++) {
+            K1Rec rec;
+            rec.start = 0;
+            rec.len = 0;
+            rec.idx = 0xffffffffu;
+            if (first + uint32_t(s) * 32u + lane < n) rec = recs[first + uint32_t(s) * 32u + lane];
+            idx[s] = rec.idx;
+            q[s] = start_state;
+            const uint8_t *p = chars + rec.start;
+            const uint32_t len = rec.len;
+            const uint8_t *anchor;  // forward: address of vector 0; reversed: END of vector 0
+            if (!REV) {
+                h[s] = uint32_t(reinterpret_cast<uintptr_t>(p)) & 15u;
+                anchor = p - h[s];
+            } else {
+                const uint8_t *e = p + len;
+                h[s] = (16u - (uint32_t(reinterpret_cast<uintptr_t>(e)) & 15u)) & 15u;
+                anchor = e + h[s];
+            }
+            nbytes[s] = len ? h[s] + len : 0u;  // stream length incl. front pad
+            const uint32_t nvec = (nbytes[s] + 15u) >> 4;
+            // vectors [vlo, vhi) are complete (no pad, no tail) in EVERY stream of the warp
+            vlo = max(vlo, __reduce_max_sync(0xffffffffu, h[s] ? 1u : 0u));
+            vhi = min(vhi, __reduce_min_sync(0xffffffffu, nbytes[s] >> 4));
+            nvmax = max(nvmax, __reduce_max_sync(0xffffffffu, nvec));
+            // sources / limits of the target lanes this lane copies for (round-invariant)
+#pragma unroll
+            for (int g = 0; g < NI; g++) {
+                const uint32_t t = uint32_t(g) * TPI + tsub;
+                const uint64_t a = __shfl_sync(0xffffffffu, uint64_t(reinterpret_cast<uintptr_t>(anchor)), int(t));
+                const uint32_t nv = __shfl_sync(0xffffffffu, nvec, int(t));
+                src_lim[s][g] = nv * 16u > part * 16u ? nv * 16u - part * 16u : 0u;  // copy while round offset < this
+                if (!REV) src[s][g] = reinterpret_cast<const uint8_t *>(uintptr_t(a)) + part * 16u;
+                else src[s][g] = reinterpret_cast<const uint8_t *>(uintptr_t(a)) - (part + 1u) * 16u;
+                if (s == 0) dst_off[g] = ring_base + t * LS + part * 16u;
+            }
         }
+        const uint32_t nrounds = (nvmax + VPC - 1) / VPC;
         uint32_t issued = 0;  // rounds issued so far
         auto issue_round = [&]() {
             const uint32_t sb = (issued % STAGES) * STAGE_BYTES;
             const uint32_t boff = issued * CH;
 #pragma unroll
-            for (int g = 0; g < NI; g++) {
-                cp_async16(dst_off[g] + sb, src[g], boff < src_lim[g]);
-                src[g] = !REV ? src[g] + CH : src[g] - CH;
+            for (int s = 0; s < NS; s++) {
+#pragma unroll
+                for (int g = 0; g < NI; g++) {
+                    cp_async16(dst_off[g] + sb + uint32_t(s) * STR_BYTES, src[s][g], boff < src_lim[s][g]);
+                    src[s][g] = !REV ? src[s][g] + CH : src[s][g] - CH;
+                }
             }
             cp_async_commit();
             issued++;
         };
 
-        uint32_t q = start_state;
 #pragma unroll
         for (int s = 0; s < STAGES - 1; s++) issue_round();
         for (uint32_t r = 0; r < nrounds; r++) {
@@ -326,44 +343,66 @@ __device__ __forceinline__ void k1_scan_body(const Step st, const uint8_t *__res
             const uint32_t my = my_ring + (r % STAGES) * STAGE_BYTES;
             const uint32_t v0 = r * VPC;
             if (v0 >= vlo && v0 + VPC <= vhi) {
-                // interior round: every vector complete in every lane
+                // interior round: every vector complete in every stream; the NS chains interleave
 #pragma unroll
-                for (int j = 0; j < VPC; j++) q = step_vec<REV>(st, q, lds128(my + uint32_t(j) * 16u));
+                for (int j = 0; j < VPC; j++) {
+                    uint32_t w[NS][4];
+#pragma unroll
+                    for (int s = 0; s < NS; s++) {
+                        const uint4 v = lds128(my + uint32_t(s) * STR_BYTES + uint32_t(j) * 16u);
+                        w[s][0] = v.x;
+                        w[s][1] = v.y;
+                        w[s][2] = v.z;
+                        w[s][3] = v.w;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 16; k++) {
+#pragma unroll
+                        for (int s = 0; s < NS; s++) q[s] = st(q[s], vec_byte<REV>(w[s], k));
+                    }
+                }
             } else {
 #pragma unroll 1
                 for (int j = 0; j < VPC; j++) {
                     const uint32_t lo = (v0 + uint32_t(j)) * 16u;  // stream offset of this vector
-                    if (lo >= nbytes) break;
-                    const uint4 v = lds128(my + uint32_t(j) * 16u);
-                    if (lo >= h && lo + 16u <= nbytes) {
-                        q = step_vec<REV>(st, q, v);
-                    } else {
-                        // boundary vector: byte k in READING order sits at stream offset lo + k;
-                        // its index in memory order is k (forward) or 15 - k (reversed)
-                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                        for (int k = 0; k < 16; k++) {
-                            const uint32_t pos = lo + uint32_t(k);
-                            const int mb = REV ? 15 - k : k;
-                            const uint32_t byte = (w[mb >> 2] >> (8 * (mb & 3))) & 0xffu;
-                            if (pos >= h && pos < nbytes) q = st(q, byte);
+                    for (int s = 0; s < NS; s++) {
+                        if (lo >= nbytes[s]) continue;
+                        const uint4 v = lds128(my + uint32_t(s) * STR_BYTES + uint32_t(j) * 16u);
+                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                        if (lo >= h[s] && lo + 16u <= nbytes[s]) {
+#pragma unroll
+                            for (int k = 0; k < 16; k++) q[s] = st(q[s], vec_byte<REV>(w, k));
+                        } else {
+                            // boundary vector: byte k in READING order sits at stream offset lo + k
+#pragma unroll
+                            for (int k = 0; k < 16; k++) {
+                                const uint32_t pos = lo + uint32_t(k);
+                                const uint32_t byte = vec_byte<REV>(w, k);
+                                if (pos >= h[s] && pos < nbytes[s]) q[s] = st(q[s], byte);
+                            }
                         }
                     }
                 }
             }
             __syncwarp();
             // every live stream's active set is empty (automata.cpp:186-188)
-            if (__all_sync(0xffffffffu, q == 0u || (r + 1u) * CH >= nbytes)) break;
+            bool idle = true;
+#pragma unroll
+            for (int s = 0; s < NS; s++) idle = idle && (q[s] == 0u || (r + 1u) * CH >= nbytes[s]);
+            if (__all_sync(0xffffffffu, idle)) break;
         }
         cp_async_wait<0>();
         __syncwarp();
-        if (rec.idx != 0xffffffffu) out[rec.idx] = accept[q];
+#pragma unroll
+        for (int s = 0; s < NS; s++)
+            if (idx[s] != 0xffffffffu) out[idx[s]] = accept[q[s]];
     }
 }
 
 constexpr int K1_WARPS = 8;
 
-template <bool REV, int L, int CH, int STAGES>
+template <bool REV, int L, int CH, int STAGES, int NS>
 __global__ void __launch_bounds__(K1_WARPS * 32)
 k1_dfa_direct_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict__ recs, uint64_t n,
                      uint8_t *__restrict__ out, const uint8_t *__restrict__ g_table,
@@ -380,8 +419,8 @@ k1_dfa_direct_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict_
     __syncthreads();
     const uint32_t ring0 = uint32_t(__cvta_generic_to_shared(ring));
     const DirectStep<L> st{s_table};
-    k1_scan_body<REV, DirectStep<L>, CH, STAGES>(st, chars, recs, n, out, s_accept, start, task_counter,
-                                                 ring0 + (threadIdx.x >> 5) * (STAGES * 32 * (CH + 16)));
+    k1_scan_body<REV, DirectStep<L>, CH, STAGES, NS>(st, chars, recs, n, out, s_accept, start, task_counter,
+                                                     ring0 + (threadIdx.x >> 5) * (STAGES * NS * 32 * (CH + 16)));
 }
 
 template <bool REV, int CH, int STAGES>
@@ -399,16 +438,16 @@ k1_dfa_classed_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict
     const uint32_t sbase = uint32_t(__cvta_generic_to_shared(smem));
     const uint32_t ring0 = (sbase + table_bytes + accept_bytes + 127u) & ~127u;
     const ClassedStep st{smem, reinterpret_cast<const uint16_t *>(smem + 256), n_states};
-    k1_scan_body<REV, ClassedStep, CH, STAGES>(st, chars, recs, n, out, smem + table_bytes, start, task_counter,
-                                               ring0 + (threadIdx.x >> 5) * (STAGES * 32 * (CH + 16)));
+    k1_scan_body<REV, ClassedStep, CH, STAGES, 1>(st, chars, recs, n, out, smem + table_bytes, start, task_counter,
+                                                  ring0 + (threadIdx.x >> 5) * (STAGES * 32 * (CH + 16)));
 }
 
 // ring geometry variants (RXM_K1_VARIANT=0..2 selects one for tuning; default 0)
-struct V0 { static constexpr int CH = 64, STAGES = 2; };
-struct V1 { static constexpr int CH = 64, STAGES = 3; };
-struct V2 { static constexpr int CH = 128, STAGES = 2; };
-struct V3 { static constexpr int CH = 32, STAGES = 2; };
-struct V4 { static constexpr int CH = 32, STAGES = 3; };
+struct V0 { static constexpr int CH = 64, STAGES = 2, NS = 1; };
+struct V1 { static constexpr int CH = 32, STAGES = 2, NS = 2; };
+struct V2 { static constexpr int CH = 64, STAGES = 2, NS = 2; };
+struct V3 { static constexpr int CH = 32, STAGES = 3, NS = 2; };
+struct V4 { static constexpr int CH = 32, STAGES = 2, NS = 1; };
 
 inline int k1_variant() {
     static int v = -1;
@@ -429,13 +468,13 @@ int blocks_per_sm(Kern kern, size_t smem) {
 
 template <bool REV, int L, class V>
 int launch_direct_v(const K1Tables &kt, const K1Launch &a) {
-    const size_t smem = size_t(K1_WARPS) * V::STAGES * 32 * (V::CH + 16);
-    auto kern = k1_dfa_direct_kernel<REV, L, V::CH, V::STAGES>;
+    const size_t smem = size_t(K1_WARPS) * V::STAGES * V::NS * 32 * (V::CH + 16);
+    auto kern = k1_dfa_direct_kernel<REV, L, V::CH, V::STAGES, V::NS>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
         return RXM_ERR_CUDA;
     int nb = blocks_per_sm(kern, smem);
     if (nb <= 0) return RXM_ERR_CUDA;
-    const uint64_t tasks = (a.n + 31) / 32;
+    const uint64_t tasks = (a.n + 32 * V::NS - 1) / (32 * V::NS);
     uint64_t blocks = uint64_t(a.sm_count) * nb;
     const uint64_t need = (tasks + K1_WARPS - 1) / K1_WARPS;
     if (blocks > need) blocks = need;
