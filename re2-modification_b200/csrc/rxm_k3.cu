@@ -365,7 +365,7 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
             if (ovf || i == n32) finished = true;
             // ---- C. fast-forward over idle steps (see MfaSim::run); only after a step in which
             //         no configuration was active ----
-            else if (!any_active && i + 2 < n32) {
+            else if (!any_active && i + 1 < n32) {
                 bool same = true;
                 uint32_t ev = n32;
                 for (uint32_t q = lane; q < SP; q += TILE) {
@@ -396,7 +396,9 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
                 }
                 same = __all_sync(FULL, same);
                 ev = __reduce_min_sync(FULL, ev);
-                if (same && ev > i + 2) i = ev - 2;  // the increment below makes the next step ev - 1
+                // prog_stamp does not depend on the step index: further idle steps reproduce this
+                // set bit for bit, so jump straight to the event step (the increment below adds 1)
+                if (same && ev > i + 1) i = ev - 1;
             }
             }  // else of (i < n32 && m == 0)
             i++;

@@ -591,11 +591,13 @@ RXM_UNROLL
             nb ^= 1u;
             if (overflow) return 2;
             if (i == n) break;
-            // fast-forward over idle steps: see MfaSim::run
+            // Fast-forward over idle steps as in MfaSim::run, but with prog_stamp the stamps do not
+            // depend on the step index: once an idle step reproduces its input set, every further
+            // idle step reproduces it BIT FOR BIT, so the jump goes straight to the event step.
             const cfg_t *now = buf[nb ^ 1u];
             const cfg_t *prev = buf[nb];
             const uint32_t m = cnt[nb ^ 1u];
-            if (m == 0 || m != cnt[nb] || i + 2 >= n) continue;
+            if (m == 0 || m != cnt[nb] || i + 1 >= n) continue;
             uint32_t ev = n;
             bool idle = true;
             for (uint32_t j = 0; j < m && idle; j++) {
@@ -620,9 +622,9 @@ RXM_UNROLL
                     }
                 if (!found) idle = false;
             }
-            if (idle && ev > i + 2) {
-                steps_skipped += ev - 2 - i;
-                i = ev - 2;
+            if (idle && ev > i + 1) {
+                steps_skipped += ev - 1 - i;
+                i = ev - 1;  // the loop increment makes the next step ev
             }
         }
         const cfg_t *f = buf[nb ^ 1u];
