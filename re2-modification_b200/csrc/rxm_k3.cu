@@ -147,7 +147,7 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
     __syncthreads();
     const ProgItem *items = items_in_smem ? s_items : gp.items;
     // ---- per-warp frontier: two buffers of SP slots ----
-    const uint32_t SP = (v.n_states + 31u) & ~31u;
+    const uint32_t SP = (v.n_states + TILE - 1u) & ~(TILE - 1u);  // slots, a whole number of tile passes
     const size_t per_warp = size_t(SP) * 2 * (8 + 4 + 8 * NC) + size_t(SP) * 12 + 16;
     uint8_t *wb = smem + o + size_t(tile) * per_warp;
     uint64_t *keys = reinterpret_cast<uint64_t *>(wb);                    // [2][SP]
@@ -325,12 +325,14 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
                 bool cmp_ok = false;
                 while (cm) {
                     const int src = __ffs(int(cm)) - 1;
-                    cm &= cm - 1u;
                     const uint32_t vs = __shfl_sync(FULL, cmp_vs, src, TILE), L = __shfl_sync(FULL, cmp_L, src, TILE);
                     bool eq;
                     if (!v.reversed) eq = warp_span_equal<TILE>(s + vs, s + i, L, lane, FULL);
                     else eq = warp_span_equal<TILE>(s + (n32 - vs - L), s + (n32 - i - L), L, lane, FULL);
-                    if (int(lane) == src) cmp_ok = eq;
+                    // every lane waiting for this very span takes the answer (e.g. &1 read from two nodes)
+                    const bool mine = need_cmp && cmp_vs == vs && cmp_L == L;
+                    if (mine) cmp_ok = eq;
+                    cm &= ~((__ballot_sync(FULL, mine) >> tshift) & ((TILE == 32) ? 0xffffffffu : ((1u << TILE) - 1u)));
                 }
                 if (need_cmp && cmp_ok) {
                     const uint32_t stamp = cand.born;
@@ -423,7 +425,7 @@ int launch_k3(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n
               const uint64_t *d_offsets, uint64_t n, uint8_t *d_out, unsigned long long *d_overflow,
               unsigned long long *d_next, int sm_count, cudaStream_t stream) {
     constexpr int TILES = K3_WARPS * 32 / TILE;  // strings in flight per block
-    const uint32_t SP = (v.n_states + 31u) & ~31u;
+    const uint32_t SP = (v.n_states + TILE - 1u) & ~uint32_t(TILE - 1);
     const size_t per_tile = size_t(SP) * 2 * (8 + 4 + 8 * NC) + size_t(SP) * 12 + 16;
     const size_t tab = (size_t(n_keys) * 8 + 15) & ~size_t(15);
     const bool in_smem = size_t(n_items) * sizeof(ProgItem) <= 64 * 1024;
