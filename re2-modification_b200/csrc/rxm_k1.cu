@@ -80,7 +80,8 @@ __device__ __forceinline__ uint32_t clamp_len(uint64_t len) { return len >= 0x7f
 // Pass 1: per-tile bucket counts, written as one row of tile_counts per tile (no global
 // atomics); strings longer than 2^31-2 are reported.
 constexpr int K1_TILE = 4096;
-__global__ void __launch_bounds__(256)
+constexpr int K1_BUCKET_THREADS = 1024;
+__global__ void __launch_bounds__(K1_BUCKET_THREADS)
 k1_hist_kernel(const uint64_t *__restrict__ offsets, uint64_t n, uint32_t *__restrict__ tile_counts,
                unsigned long long *__restrict__ overflow) {
     __shared__ uint32_t sh[K1_BUCKETS];
@@ -140,7 +141,7 @@ k1_cursor_kernel(uint32_t *__restrict__ totals, uint32_t *__restrict__ task_coun
 }
 
 // Pass 3: every string takes its record slot from its tile's shared-memory copy of the bases.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(K1_BUCKET_THREADS)
 k1_scatter_kernel(const uint64_t *__restrict__ offsets, uint64_t n, const uint32_t *__restrict__ tile_bases,
                   const uint32_t *__restrict__ bucket_base, K1Rec *__restrict__ recs) {
     __shared__ uint32_t cnt[K1_BUCKETS];
@@ -532,11 +533,11 @@ int k1_launch(const K1Tables &kt, const K1Launch &a, int *launched) {
     uint64_t blocks = ntiles;
     const uint64_t cap = uint64_t(a.sm_count) * 8;
     if (blocks > cap) blocks = cap;
-    k1_hist_kernel<<<unsigned(blocks), 256, 0, a.stream>>>(a.d_offsets, a.n, a.d_hist, a.d_overflow);
+    k1_hist_kernel<<<unsigned(blocks), K1_BUCKET_THREADS, 0, a.stream>>>(a.d_offsets, a.n, a.d_hist, a.d_overflow);
     uint32_t *totals = a.d_task_counter + 32;  // [K1_BUCKETS] after the task counter
     k1_colscan_kernel<<<K1_BUCKETS / 128, 128, 0, a.stream>>>(a.d_hist, uint32_t(ntiles), totals);
     k1_cursor_kernel<<<1, 1024, 0, a.stream>>>(totals, a.d_task_counter);
-    k1_scatter_kernel<<<unsigned(blocks), 256, 0, a.stream>>>(a.d_offsets, a.n, a.d_hist, totals, a.d_recs);
+    k1_scatter_kernel<<<unsigned(blocks), K1_BUCKET_THREADS, 0, a.stream>>>(a.d_offsets, a.n, a.d_hist, totals, a.d_recs);
     *launched = 4;
     int st;
     if (kt.mode == K1_DIRECT) st = kt.reversed ? launch_direct_l<true>(kt, a) : launch_direct_l<false>(kt, a);
