@@ -122,7 +122,9 @@ typedef struct rxm_plan_info {
     uint32_t n_cells;
     uint32_t reversed;
     uint32_t sm_count;
-    uint32_t reserved[7];
+    uint32_t dfa_stride;    /* K1_DFA: input bytes per table lookup in the scan's interior (1, or 4
+                               when all literals lie in one 4-letter window and there are <= 64 sets) */
+    uint32_t reserved[6];
 } rxm_plan_info;
 
 /* Copies `host_tables` (caller keeps ownership), plans, uploads to `device`. */

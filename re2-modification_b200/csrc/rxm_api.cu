@@ -74,11 +74,10 @@ struct rxm_matcher {
     uint8_t *d_bits = nullptr;
     size_t cap_n = 0;
 
-    // K1 bucket-pass workspace
+    // K1 tile-sort workspace
     rxm::K1Rec *d_recs = nullptr;
     size_t cap_recs = 0;
-    uint32_t *d_hist = nullptr;          // [cap_tiles][K1_BUCKETS] + task counter
-    size_t cap_tiles = 0;
+    uint32_t *d_k1_counter = nullptr;    // scan kernel's task counter
 
     unsigned long long *d_overflow = nullptr;  // strings that hit a kernel limit
     uint64_t launches = 0;
@@ -144,6 +143,7 @@ extern "C" int rxm_tables_upload(const rxm_tables *host_tables, int device, rxm_
         m->info.engine = RXM_ENGINE_K1_DFA;
         m->info.dfa_states = m->dfa.n_states;
         m->info.dfa_classes = m->dfa.n_classes;
+        m->info.dfa_stride = m->k1.quad ? 4 : 1;
         m->info.exact_step_differs = m->dfa.exact_step_differs;
     } else {
         st = rxm::check_mfa(t, &err);
@@ -216,7 +216,7 @@ extern "C" int rxm_free(rxm_handle h) {
     cudaFree(h->d_bits);
     cudaFree(h->d_overflow);
     cudaFree(h->d_recs);
-    cudaFree(h->d_hist);
+    cudaFree(h->d_k1_counter);
     delete h;
     return RXM_OK;
 }
@@ -254,17 +254,9 @@ static int launch_on_device(rxm_matcher *m, const uint8_t *d_chars, const uint64
             CU(cudaMalloc(reinterpret_cast<void **>(&m->d_recs), want * sizeof(rxm::K1Rec)));
             m->cap_recs = want;
         }
-        const size_t ntiles = size_t((n + rxm::K1_TILE_STRINGS - 1) / rxm::K1_TILE_STRINGS);
-        if (ntiles > m->cap_tiles) {
-            cudaFree(m->d_hist);
-            m->d_hist = nullptr;
-            m->cap_tiles = 0;
-            const size_t want = ntiles + (ntiles >> 3) + 1;
-            CU(cudaMalloc(reinterpret_cast<void **>(&m->d_hist), (want * rxm::K1_BUCKETS + 64 + rxm::K1_BUCKETS) * sizeof(uint32_t)));
-            m->cap_tiles = want;
-        }
-        rxm::K1Launch a{m->d_k1_table, m->d_k1_accept, d_chars, d_offsets, n, d_out, m->d_recs, m->d_hist,
-                        m->d_hist + m->cap_tiles * rxm::K1_BUCKETS, m->d_overflow, m->sm_count, stream};
+        if (!m->d_k1_counter) CU(cudaMalloc(reinterpret_cast<void **>(&m->d_k1_counter), 64 * sizeof(uint32_t)));
+        rxm::K1Launch a{m->d_k1_table, m->d_k1_accept, d_chars, d_offsets, n, d_out, m->d_recs,
+                        m->d_k1_counter, m->d_overflow, m->sm_count, stream};
         st = rxm::k1_launch(m->k1, a, &launched);
     } else if (m->info.engine == RXM_ENGINE_K3_WARP) {
         rxm::MfaView v{m->d_edge_begin, m->d_edges, m->tables.n_states(), m->tables.start,

@@ -2,12 +2,12 @@
 // Replaces Automata::match (automata.cpp:177-210) for whole batches.
 //
 // Data path (DESIGN.md "K1"):
-//   1. bucket pass   -- three tiny kernels build 16-byte records {start, len, index}
-//                       ordered by DESCENDING length bucket (counting sort on a
-//                       3 %-granular log scale).  Strings are not moved.
-//   2. scan kernel   -- persistent warps pull 32 consecutive records (== 32 strings
-//                       of nearly equal length) from an atomic task counter (longest
-//                       first).  The warp streams the 32 strings in lock-step:
+//   1. tile sort     -- one kernel builds 16-byte records {start, len, index}; every tile of
+//                       4096 strings is ordered by DESCENDING length bucket (counting sort
+//                       in shared memory on a 1/64-granular log scale).  Strings are not moved.
+//   2. scan kernel   -- persistent warps pull 32 consecutive records of a tile (== 32
+//                       strings of nearly equal length) from an atomic task counter, the
+//                       longest group of every tile first.  The warp streams the 32 strings in lock-step:
 //                       quarter-/eighth-warps copy 16-byte pieces of each lane's next
 //                       CH-byte chunk with cp.async.cg straight into a padded,
 //                       bank-conflict-free shared-memory ring (no register staging,
@@ -19,6 +19,7 @@
 //   path; everything between runs the unpredicated 16-step body.
 #include "rxm_kernels.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace rxm {
@@ -43,6 +44,34 @@ int k1_build_tables(const DfaPlan &p, K1Tables &kt, std::vector<uint8_t> &table,
         for (uint32_t b = 0; b < 256; b++)
             for (uint32_t s = 0; s < p.n_states; s++)
                 table[size_t(b) * sp + s] = uint8_t(p.trans[size_t(p.byte_class[b]) * p.n_states + s]);
+        // Quad stride: when every literal byte lies in one window [lo, lo+3] and the automaton
+        // has <= 64 sets, the scan's interior takes FOUR input bytes per lookup:
+        // Q[q][code], code = c3 | c2<<2 | c1<<4 | c0<<6 with ck = (byte k of the 32-bit word) - lo,
+        // composed in READING order (right-to-left automata read byte 3 first).  A byte outside
+        // the window sends its 16-byte vector to the per-byte table, so every input gets the
+        // same answer as with the per-byte scan.
+        int lit_lo = 256, lit_hi = -1;
+        for (int b = 0; b < 256; b++)
+            if (p.byte_class[b]) {
+                lit_lo = std::min(lit_lo, b);
+                lit_hi = std::max(lit_hi, b);
+            }
+        if (lit_hi < 0) lit_lo = lit_hi = 'a';
+        const char *noquad = getenv("RXM_K1_NOQUAD");
+        if (p.n_states <= 64 && lit_hi - lit_lo <= 3 && !(noquad && noquad[0] == '1')) {
+            const uint32_t lo = uint32_t(std::min(lit_lo, 252));
+            kt.quad = 1;
+            kt.quad_lo = lo;
+            const size_t base = table.size();
+            table.resize(base + size_t(256) * sp, 0);
+            for (uint32_t q = 0; q < p.n_states; q++)
+                for (uint32_t code = 0; code < 256; code++) {
+                    const uint32_t c[4] = {(code >> 6) & 3u, (code >> 4) & 3u, (code >> 2) & 3u, code & 3u};
+                    uint32_t r = q;
+                    for (int k = 0; k < 4; k++) r = table[size_t(lo + c[p.reversed ? 3 - k : k]) * sp + r];
+                    table[base + size_t(q) * 256 + code] = uint8_t(r);
+                }
+        }
     } else {
         kt.mode = K1_CLASSED;
         const size_t bytes = 256 + 2 * size_t(p.n_classes) * p.n_states;
@@ -77,89 +106,79 @@ __host__ __device__ __forceinline__ uint32_t len_bucket(uint32_t len) {
 
 __device__ __forceinline__ uint32_t clamp_len(uint64_t len) { return len >= 0x7fffffffull ? 0u : uint32_t(len); }
 
-// Pass 1: per-tile bucket counts, written as one row of tile_counts per tile (no global
-// atomics); strings longer than 2^31-2 are reported.
-constexpr int K1_TILE = 4096;
-constexpr int K1_BUCKET_THREADS = 1024;
-__global__ void __launch_bounds__(K1_BUCKET_THREADS)
-k1_hist_kernel(const uint64_t *__restrict__ offsets, uint64_t n, uint32_t *__restrict__ tile_counts,
-               unsigned long long *__restrict__ overflow) {
-    __shared__ uint32_t sh[K1_BUCKETS];
+// One kernel: every tile of K1_TILE consecutive strings is counting-sorted by DESCENDING length
+// bucket inside shared memory and written out as K1_TILE records (strings are not moved).
+// 32 consecutive records of a tile differ in length by ~1/64 of the tile's length range, which is
+// all the scan needs for lock-step lanes; the scan's task order (group g of every tile before
+// group g+1 of any) then runs the long groups of ALL tiles first without a global sort.
+// Strings longer than 2^31-2 are reported and get bit 0.
+constexpr int K1_TILE = int(K1_TILE_STRINGS);
+constexpr int K1_SORT_THREADS = 1024;
+constexpr int K1_SORT_PER_THREAD = K1_TILE / K1_SORT_THREADS;
+__global__ void __launch_bounds__(K1_SORT_THREADS)
+k1_tilesort_kernel(const uint64_t *__restrict__ offsets, uint64_t n, K1Rec *__restrict__ recs,
+                   uint32_t *__restrict__ task_counter, unsigned long long *__restrict__ overflow) {
+    static_assert(K1_BUCKETS == 2 * K1_SORT_THREADS, "two buckets per thread in the prefix pass");
+    __shared__ uint32_t cnt[K1_BUCKETS];
+    __shared__ uint32_t wsum[K1_SORT_THREADS / 32];
+    const uint32_t t = threadIdx.x;
+    if (blockIdx.x == 0 && t == 0) *task_counter = 0;
     const uint64_t ntiles = (n + K1_TILE - 1) / K1_TILE;
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (uint32_t i = threadIdx.x; i < K1_BUCKETS; i += blockDim.x) sh[i] = 0;
+        cnt[t] = 0;
+        cnt[t + K1_SORT_THREADS] = 0;
         __syncthreads();
-        const uint64_t lo = tile * K1_TILE, hi = (lo + K1_TILE < n) ? lo + K1_TILE : n;
-        for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-            const uint64_t len = offsets[i + 1] - offsets[i];
-            if (len >= 0x7fffffffull) atomicAdd(overflow, 1ull);  // reported; such a string gets bit 0
-            atomicAdd(&sh[len_bucket(clamp_len(len))], 1u);
+        const uint64_t lo = tile * K1_TILE;
+        uint64_t beg[K1_SORT_PER_THREAD];
+        uint32_t len[K1_SORT_PER_THREAD], bkt[K1_SORT_PER_THREAD];
+#pragma unroll
+        for (int k = 0; k < K1_SORT_PER_THREAD; k++) {
+            const uint64_t i = lo + uint32_t(k) * K1_SORT_THREADS + t;
+            bkt[k] = 0xffffffffu;
+            if (i < n) {
+                beg[k] = offsets[i];
+                const uint64_t l = offsets[i + 1] - beg[k];
+                if (l >= 0x7fffffffull) atomicAdd(overflow, 1ull);
+                len[k] = clamp_len(l);
+                bkt[k] = len_bucket(len[k]);
+                atomicAdd(&cnt[bkt[k]], 1u);
+            }
         }
         __syncthreads();
-        uint32_t *row = tile_counts + tile * K1_BUCKETS;
-        for (uint32_t i = threadIdx.x; i < K1_BUCKETS; i += blockDim.x) row[i] = sh[i];
+        // exclusive prefix over the buckets, longest first: thread t owns buckets b0 > b1
+        const uint32_t b0 = K1_BUCKETS - 1 - 2 * t, b1 = b0 - 1;
+        const uint32_t c0 = cnt[b0], c1 = cnt[b1];
+        uint32_t inc = c0 + c1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
+            if ((t & 31u) >= uint32_t(d)) inc += v;
+        }
+        if ((t & 31u) == 31u) wsum[t >> 5] = inc;
         __syncthreads();
-    }
-}
-
-// Pass 2a: per bucket, exclusive prefix over tiles (in place) and the bucket total.
-__global__ void __launch_bounds__(128)
-k1_colscan_kernel(uint32_t *__restrict__ tile_counts, uint32_t ntiles, uint32_t *__restrict__ totals) {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= K1_BUCKETS) return;
-    uint32_t run = 0;
-    for (uint32_t tl = 0; tl < ntiles; tl++) {  // coalesced across the block's buckets
-        uint32_t *p = &tile_counts[size_t(tl) * K1_BUCKETS + b];
-        const uint32_t x = *p;
-        *p = run;
-        run += x;
-    }
-    totals[b] = run;
-}
-
-// Pass 2b: bucket totals -> first record slot of each bucket, longest bucket first; one block.
-// Also resets the task counter.
-__global__ void __launch_bounds__(1024)
-k1_cursor_kernel(uint32_t *__restrict__ totals, uint32_t *__restrict__ task_counter) {
-    static_assert(K1_BUCKETS == 2048, "two buckets per thread");
-    __shared__ uint32_t part[1024];
-    const uint32_t t = threadIdx.x;
-    const uint32_t b0 = K1_BUCKETS - 1 - 2 * t, b1 = b0 - 1;  // descending length
-    const uint32_t c0 = totals[b0], c1 = totals[b1];
-    part[t] = c0 + c1;
-    __syncthreads();
-    for (uint32_t d = 1; d < 1024; d <<= 1) {
-        const uint32_t v = (t >= d) ? part[t - d] : 0;
+        if (t < 32) {
+            uint32_t w = wsum[t];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, w, d);
+                if (t >= uint32_t(d)) w += v;
+            }
+            wsum[t] = w;
+        }
         __syncthreads();
-        part[t] += v;
+        const uint32_t ex = inc - (c0 + c1) + ((t >> 5) ? wsum[(t >> 5) - 1] : 0u);
+        cnt[b0] = ex;
+        cnt[b1] = ex + c0;
         __syncthreads();
-    }
-    const uint32_t ex = part[t] - (c0 + c1);
-    totals[b0] = ex;
-    totals[b1] = ex + c0;
-    if (t == 0) *task_counter = 0;
-}
-
-// Pass 3: every string takes its record slot from its tile's shared-memory copy of the bases.
-__global__ void __launch_bounds__(K1_BUCKET_THREADS)
-k1_scatter_kernel(const uint64_t *__restrict__ offsets, uint64_t n, const uint32_t *__restrict__ tile_bases,
-                  const uint32_t *__restrict__ bucket_base, K1Rec *__restrict__ recs) {
-    __shared__ uint32_t cnt[K1_BUCKETS];
-    const uint64_t ntiles = (n + K1_TILE - 1) / K1_TILE;
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint32_t *row = tile_bases + tile * K1_BUCKETS;
-        for (uint32_t i = threadIdx.x; i < K1_BUCKETS; i += blockDim.x) cnt[i] = row[i] + bucket_base[i];
-        __syncthreads();
-        const uint64_t lo = tile * K1_TILE, hi = (lo + K1_TILE < n) ? lo + K1_TILE : n;
-        for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-            const uint64_t b = offsets[i];
-            const uint32_t len = clamp_len(offsets[i + 1] - b);
-            const uint32_t slot = atomicAdd(&cnt[len_bucket(len)], 1u);
+#pragma unroll
+        for (int k = 0; k < K1_SORT_PER_THREAD; k++) {
+            if (bkt[k] == 0xffffffffu) continue;
+            const uint32_t slot = atomicAdd(&cnt[bkt[k]], 1u);
             K1Rec r;
-            r.start = b;
-            r.len = len;
-            r.idx = uint32_t(i);
-            recs[slot] = r;
+            r.start = beg[k];
+            r.len = len[k];
+            r.idx = uint32_t(lo + uint32_t(k) * K1_SORT_THREADS + t);
+            recs[lo + slot] = r;
         }
         __syncthreads();
     }
@@ -236,19 +255,73 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     return v;
 }
 
+// Quad stride (four bytes per lookup, DESIGN.md "K1").  x = word - lo4 maps the window's
+// letters to 0..3 in every byte; any other byte leaves a bit under 0xFC in its own or a lower
+// byte position and raises `bad`.  x * (1 + 2^10 + 2^20 + 2^30) gathers the four 2-bit codes
+// into bits 24..31 (partial products land in distinct 2-bit slots, nothing carries), so the
+// lookup address is q*256 + (prod >> 24): per word 3 instructions off the dependent chain and
+// IMAD + LDS.U8 on it.
+struct NoQuad {
+    static constexpr bool on = false;
+};
+struct QuadStep {
+    static constexpr bool on = true;
+    const uint8_t *Q;   // shared-memory table Q[q][code]
+    uint32_t neg_lo4;   // -(window base replicated into the four bytes)
+    __device__ __forceinline__ uint32_t word(uint32_t q, uint32_t w, uint32_t &bad) const {
+        const uint32_t x = w + neg_lo4;
+        bad |= x;
+        const uint32_t code = (x * 0x40100401u) >> 24;
+        uint32_t idx;
+        asm("mad.lo.u32 %0, %1, 256, %2;" : "=r"(idx) : "r"(q), "r"(code));
+        return Q[idx];
+    }
+    template <bool REV>
+    __device__ __forceinline__ uint32_t vec(uint32_t q, const uint32_t (&w)[4], uint32_t &bad) const {
+        uint32_t b = 0;
+#ifdef RXM_K1_PROBE  // tuning builds only: the staging path without the lookups
+        bad = 0;
+        return q ^ ((w[0] ^ w[1] ^ w[2] ^ w[3]) & 1u);
+#endif
+        if (!REV) {
+            q = word(q, w[0], b);
+            q = word(q, w[1], b);
+            q = word(q, w[2], b);
+            q = word(q, w[3], b);
+        } else {
+            q = word(q, w[3], b);
+            q = word(q, w[2], b);
+            q = word(q, w[1], b);
+            q = word(q, w[0], b);
+        }
+        bad = b & 0xfcfcfcfcu;
+        return q;
+    }
+};
+
 template <bool REV>
 __device__ __forceinline__ uint32_t vec_byte(const uint32_t (&w)[4], int k) {  // k-th byte in READING order
     const int mb = REV ? 15 - k : k;
     return __byte_perm(w[mb >> 2], 0, 0x4440 + (mb & 3));
 }
 
+// A lane's chunk grid is anchored at the K1_ANCHOR-aligned block that holds the first byte it
+// reads, so every CH-byte chunk is a whole number of 32-byte sectors (with 16-byte anchors half
+// of the strings straddle three sectors per 64-byte chunk: 1.6x the bytes over the L2 -> SM
+// crossbar, measured).  The pad in front (< K1_ANCHOR bytes) is skipped by the boundary path.
+#ifndef RXM_K1_ANCHOR
+#define RXM_K1_ANCHOR 32
+#endif
+constexpr uint32_t K1_ANCHOR = RXM_K1_ANCHOR;
+static_assert(K1_ANCHOR == 16 || K1_ANCHOR == 32 || K1_ANCHOR == 64, "anchor alignment");
+
 // CH = bytes per lane per stage, STAGES = ring depth, NS = strings walked by one lane at the
 // same time (independent lookup chains: the LDS -> IMAD -> LDS chain of one string is ~34
 // cycles per byte, so two interleaved chains double what a resident warp can issue).
 // Lane stride CH+16 keeps the per-lane LDS.128 and the cooperative 16-byte cp.async writes
 // bank-conflict free.
-template <bool REV, class Step, int CH, int STAGES, int NS>
-__device__ __forceinline__ void k1_scan_body(const Step st, const uint8_t *__restrict__ chars,
+template <bool REV, class Step, int CH, int STAGES, int NS, class Quad = NoQuad>
+__device__ __forceinline__ void k1_scan_body(const Step st, const Quad qd, const uint8_t *__restrict__ chars,
                                              const K1Rec *__restrict__ recs, uint64_t n,
                                              uint8_t *__restrict__ out, const uint8_t *accept,
                                              uint32_t start_state, uint32_t *__restrict__ task_counter,
@@ -264,13 +337,18 @@ __device__ __forceinline__ void k1_scan_body(const Step st, const uint8_t *__res
     const uint32_t part = lane % LPT;       // which 16-byte piece of the chunk this lane copies
     const uint32_t tsub = lane / LPT;       // which of the TPI targets
     const uint32_t my_ring = ring_base + lane * LS;
+    const uint32_t ntiles = uint32_t((n + K1_TILE_STRINGS - 1) / K1_TILE_STRINGS);
 
     for (;;) {
         uint32_t task = 0;
         if (lane == 0) task = atomicAdd(task_counter, 1u);
         task = __shfl_sync(0xffffffffu, task, 0);
-        const uint64_t first = uint64_t(task) * (32u * NS);
-        if (first >= n) break;
+        // task -> (group of 32*NS records, tile): group g of every tile comes before group g+1
+        const uint32_t grp = task / ntiles, tile = task - grp * ntiles;
+        if (grp >= K1_TILE_STRINGS / (32u * NS)) break;
+        const uint64_t first = uint64_t(tile) * K1_TILE_STRINGS + grp * (32u * NS);
+        const uint64_t tile_end = min(n, uint64_t(tile + 1u) * K1_TILE_STRINGS);
+        if (first >= tile_end) continue;
 
         // A lane's "stream" for string s: 16-byte vectors covering [p, p+len), anchored at the
         // aligned vector that holds the first byte read (forward: the string's first byte;
@@ -286,24 +364,24 @@ __device__ __forceinline__ void k1_scan_body(const Step st, const uint8_t *__res
             rec.start = 0;
             rec.len = 0;
             rec.idx = 0xffffffffu;
-            if (first + uint32_t(s) * 32u + lane < n) rec = recs[first + uint32_t(s) * 32u + lane];
+            if (first + uint32_t(s) * 32u + lane < tile_end) rec = recs[first + uint32_t(s) * 32u + lane];
             idx[s] = rec.idx;
             q[s] = start_state;
             const uint8_t *p = chars + rec.start;
             const uint32_t len = rec.len;
             const uint8_t *anchor;  // forward: address of vector 0; reversed: END of vector 0
             if (!REV) {
-                h[s] = uint32_t(reinterpret_cast<uintptr_t>(p)) & 15u;
+                h[s] = uint32_t(reinterpret_cast<uintptr_t>(p)) & (K1_ANCHOR - 1u);
                 anchor = p - h[s];
             } else {
                 const uint8_t *e = p + len;
-                h[s] = (16u - (uint32_t(reinterpret_cast<uintptr_t>(e)) & 15u)) & 15u;
+                h[s] = (K1_ANCHOR - (uint32_t(reinterpret_cast<uintptr_t>(e)) & (K1_ANCHOR - 1u))) & (K1_ANCHOR - 1u);
                 anchor = e + h[s];
             }
             nbytes[s] = len ? h[s] + len : 0u;  // stream length incl. front pad
             const uint32_t nvec = (nbytes[s] + 15u) >> 4;
             // vectors [vlo, vhi) are complete (no pad, no tail) in EVERY stream of the warp
-            vlo = max(vlo, __reduce_max_sync(0xffffffffu, h[s] ? 1u : 0u));
+            vlo = max(vlo, __reduce_max_sync(0xffffffffu, (h[s] + 15u) >> 4));
             vhi = min(vhi, __reduce_min_sync(0xffffffffu, nbytes[s] >> 4));
             nvmax = max(nvmax, __reduce_max_sync(0xffffffffu, nvec));
             // sources / limits of the target lanes this lane copies for (round-invariant)
@@ -356,10 +434,24 @@ __device__ __forceinline__ void k1_scan_body(const Step st, const uint8_t *__res
                         w[s][2] = v.z;
                         w[s][3] = v.w;
                     }
+                    if constexpr (Quad::on) {
 #pragma unroll
-                    for (int k = 0; k < 16; k++) {
+                        for (int s = 0; s < NS; s++) {
+                            uint32_t bad = 0;
+                            const uint32_t qf = qd.template vec<REV>(q[s], w[s], bad);
+                            if (bad) {  // a byte outside the quad window: this vector goes byte by byte
 #pragma unroll
-                        for (int s = 0; s < NS; s++) q[s] = st(q[s], vec_byte<REV>(w[s], k));
+                                for (int k = 0; k < 16; k++) q[s] = st(q[s], vec_byte<REV>(w[s], k));
+                            } else {
+                                q[s] = qf;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 16; k++) {
+#pragma unroll
+                            for (int s = 0; s < NS; s++) q[s] = st(q[s], vec_byte<REV>(w[s], k));
+                        }
                     }
                 }
             } else {
@@ -420,8 +512,32 @@ k1_dfa_direct_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict_
     __syncthreads();
     const uint32_t ring0 = uint32_t(__cvta_generic_to_shared(ring));
     const DirectStep<L> st{s_table};
-    k1_scan_body<REV, DirectStep<L>, CH, STAGES, NS>(st, chars, recs, n, out, s_accept, start, task_counter,
+    k1_scan_body<REV, DirectStep<L>, CH, STAGES, NS>(st, NoQuad(), chars, recs, n, out, s_accept, start, task_counter,
                                                      ring0 + (threadIdx.x >> 5) * (STAGES * NS * 32 * (CH + 16)));
+}
+
+// Quad-stride variant: g_table = T[256][SP] followed by Q[SP][256].
+template <bool REV, int L, int CH, int STAGES, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k1_dfa_quad_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict__ recs, uint64_t n,
+                   uint8_t *__restrict__ out, const uint8_t *__restrict__ g_table,
+                   const uint8_t *__restrict__ g_accept, uint32_t start, uint32_t quad_lo,
+                   uint32_t *__restrict__ task_counter) {
+    constexpr uint32_t TB = 256u << L;
+    __shared__ __align__(16) uint8_t s_table[2 * TB];  // T then Q; static: offsets fold into the LDS
+    __shared__ __align__(16) uint8_t s_accept[256];
+    extern __shared__ __align__(128) uint8_t ring[];
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(g_table);
+    uint4 *d4 = reinterpret_cast<uint4 *>(s_table);
+    for (uint32_t i = threadIdx.x; i < 2 * TB / 16; i += blockDim.x) d4[i] = s4[i];
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_accept[i] = g_accept[i];
+    __syncthreads();
+    const uint32_t ring0 = uint32_t(__cvta_generic_to_shared(ring));
+    const DirectStep<L> st{s_table};
+    const QuadStep qd{s_table + TB, 0u - quad_lo * 0x01010101u};
+    k1_scan_body<REV, DirectStep<L>, CH, STAGES, 1, QuadStep>(
+        st, qd, chars, recs, n, out, s_accept, start, task_counter,
+        ring0 + (threadIdx.x >> 5) * (STAGES * 32 * (CH + 16)));
 }
 
 template <bool REV, int CH, int STAGES>
@@ -439,7 +555,7 @@ k1_dfa_classed_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict
     const uint32_t sbase = uint32_t(__cvta_generic_to_shared(smem));
     const uint32_t ring0 = (sbase + table_bytes + accept_bytes + 127u) & ~127u;
     const ClassedStep st{smem, reinterpret_cast<const uint16_t *>(smem + 256), n_states};
-    k1_scan_body<REV, ClassedStep, CH, STAGES, 1>(st, chars, recs, n, out, smem + table_bytes, start, task_counter,
+    k1_scan_body<REV, ClassedStep, CH, STAGES, 1>(st, NoQuad(), chars, recs, n, out, smem + table_bytes, start, task_counter,
                                                   ring0 + (threadIdx.x >> 5) * (STAGES * 32 * (CH + 16)));
 }
 
@@ -455,7 +571,7 @@ inline int k1_variant() {
     if (v < 0) {
         const char *e = getenv("RXM_K1_VARIANT");
         v = e ? atoi(e) : 0;
-        if (v < 0 || v > 4) v = 0;
+        if (v < 0 || v > 7) v = 0;
     }
     return v;
 }
@@ -495,8 +611,48 @@ int launch_direct(const K1Tables &kt, const K1Launch &a) {
     }
 }
 
+template <bool REV, int L, int CH, int STAGES, int WARPS>
+int launch_quad_w(const K1Tables &kt, const K1Launch &a) {
+    const size_t smem = size_t(WARPS) * STAGES * 32 * (CH + 16);
+    auto kern = k1_dfa_quad_kernel<REV, L, CH, STAGES, WARPS>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+        return RXM_ERR_CUDA;
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, WARPS * 32, smem) != cudaSuccess || nb <= 0)
+        return RXM_ERR_CUDA;
+    const uint64_t tasks = (a.n + 31) / 32;
+    uint64_t blocks = uint64_t(a.sm_count) * nb;
+    const uint64_t need = (tasks + WARPS - 1) / WARPS;
+    if (blocks > need) blocks = need;
+    kern<<<unsigned(blocks), WARPS * 32, smem, a.stream>>>(a.d_chars, a.d_recs, a.n, a.d_out, a.d_table, a.d_accept,
+                                                          kt.start, kt.quad_lo, a.d_task_counter);
+    return RXM_OK;
+}
+
+template <bool REV, int L>
+int launch_quad(const K1Tables &kt, const K1Launch &a) {
+    switch (k1_variant()) {  // tuning: CTA width / ring geometry
+        case 1: return launch_quad_w<REV, L, 64, 2, 16>(kt, a);
+        case 2: return launch_quad_w<REV, L, 64, 3, 10>(kt, a);
+        case 3: return launch_quad_w<REV, L, 128, 2, 11>(kt, a);
+        case 4: return launch_quad_w<REV, L, 128, 2, 8>(kt, a);
+        case 5: return launch_quad_w<REV, L, 256, 2, 6>(kt, a);
+        case 6: return launch_quad_w<REV, L, 128, 3, 7>(kt, a);
+        case 7: return launch_quad_w<REV, L, 64, 4, 10>(kt, a);
+        default: return launch_quad_w<REV, L, 64, 2, 8>(kt, a);
+    }
+}
+
 template <bool REV>
 int launch_direct_l(const K1Tables &kt, const K1Launch &a) {
+    if (kt.quad) {
+        switch (kt.log2sp) {
+            case 4: return launch_quad<REV, 4>(kt, a);
+            case 5: return launch_quad<REV, 5>(kt, a);
+            case 6: return launch_quad<REV, 6>(kt, a);
+            default: return RXM_ERR_INVALID;
+        }
+    }
     switch (kt.log2sp) {
         case 4: return launch_direct<REV, 4>(kt, a);
         case 5: return launch_direct<REV, 5>(kt, a);
@@ -528,21 +684,17 @@ int launch_classed(const K1Tables &kt, const K1Launch &a) {
 
 int k1_launch(const K1Tables &kt, const K1Launch &a, int *launched) {
     *launched = 0;
-    // workspace: recs | tile_counts[ntiles][K1_BUCKETS] | task counter
     const uint64_t ntiles = (a.n + K1_TILE - 1) / K1_TILE;
     uint64_t blocks = ntiles;
-    const uint64_t cap = uint64_t(a.sm_count) * 8;
+    const uint64_t cap = uint64_t(a.sm_count) * 2;
     if (blocks > cap) blocks = cap;
-    k1_hist_kernel<<<unsigned(blocks), K1_BUCKET_THREADS, 0, a.stream>>>(a.d_offsets, a.n, a.d_hist, a.d_overflow);
-    uint32_t *totals = a.d_task_counter + 32;  // [K1_BUCKETS] after the task counter
-    k1_colscan_kernel<<<K1_BUCKETS / 128, 128, 0, a.stream>>>(a.d_hist, uint32_t(ntiles), totals);
-    k1_cursor_kernel<<<1, 1024, 0, a.stream>>>(totals, a.d_task_counter);
-    k1_scatter_kernel<<<unsigned(blocks), K1_BUCKET_THREADS, 0, a.stream>>>(a.d_offsets, a.n, a.d_hist, totals, a.d_recs);
-    *launched = 4;
+    k1_tilesort_kernel<<<unsigned(blocks), K1_SORT_THREADS, 0, a.stream>>>(a.d_offsets, a.n, a.d_recs, a.d_task_counter,
+                                                                          a.d_overflow);
+    *launched = 1;
     int st;
     if (kt.mode == K1_DIRECT) st = kt.reversed ? launch_direct_l<true>(kt, a) : launch_direct_l<false>(kt, a);
     else st = kt.reversed ? launch_classed<true>(kt, a) : launch_classed<false>(kt, a);
-    if (st == RXM_OK) *launched = 5;
+    if (st == RXM_OK) *launched = 2;
     return st;
 }
 

@@ -29,19 +29,21 @@ struct K1Tables {
     uint32_t reversed;
     uint32_t table_bytes;  // bytes of the device table blob (copied to shared memory)
     uint32_t accept_bytes;
+    uint32_t quad;         // K1_DIRECT with SP <= 64: the quad table Q[SP][256] follows T in the blob
+    uint32_t quad_lo;      // lowest byte value of the quad table's 4-letter window
 };
 
 int k1_build_tables(const DfaPlan &p, K1Tables &kt, std::vector<uint8_t> &table,
                     std::vector<uint8_t> &accept, std::string *err);
 
-// One record per string, written by the bucket pass in descending length-bucket order.
+// One record per string, written by the tile sort: descending length bucket within each tile.
 struct __align__(16) K1Rec {
     unsigned long long start;  // byte offset into chars
     uint32_t len;
     uint32_t idx;              // original string index (where the result bit goes)
 };
 constexpr uint32_t K1_BUCKETS = 2048;
-constexpr uint32_t K1_TILE_STRINGS = 4096;  // strings per bucket-pass tile
+constexpr uint32_t K1_TILE_STRINGS = 4096;  // strings per tile of the sort
 
 struct K1Launch {
     const uint8_t *d_table;
@@ -51,7 +53,6 @@ struct K1Launch {
     uint64_t n;
     uint8_t *d_out;
     K1Rec *d_recs;               // [n]        workspace
-    uint32_t *d_hist;            // [ntiles][K1_BUCKETS] workspace (per-tile counts, then bases)
     uint32_t *d_task_counter;    // [1]        workspace
     unsigned long long *d_overflow;
     int sm_count;

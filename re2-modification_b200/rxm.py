@@ -14,7 +14,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librxm.so")
+LIB_PATH = os.environ.get("RXM_LIB") or os.path.join(_HERE, "librxm.so")  # RXM_LIB: tuning builds
 
 RXM_OK = 0
 RXM_ERR_INVALID = 1
@@ -52,7 +52,7 @@ class RxmPlanInfo(C.Structure):
         ("engine", C.c_uint32), ("dfa_states", C.c_uint32), ("dfa_classes", C.c_uint32),
         ("exact_step_differs", C.c_uint32), ("n_states", C.c_uint32), ("n_edges", C.c_uint32),
         ("n_cells", C.c_uint32), ("reversed", C.c_uint32), ("sm_count", C.c_uint32),
-        ("reserved", C.c_uint32 * 7),
+        ("dfa_stride", C.c_uint32), ("reserved", C.c_uint32 * 6),
     ]
 
 

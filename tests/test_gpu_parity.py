@@ -198,6 +198,50 @@ def test_k1_every_length_and_alignment(name):
     m.close()
 
 
+@pytest.mark.parametrize("name", ["nfa_config2", "nfa_quirk", "nfa_abb", "nfa_dots", "nfa_third"])
+def test_k1_quad_stride_and_bytes_outside_the_window(name, monkeypatch):
+    """The four-bytes-per-lookup interior (dfa_stride 4) against the oracle and against the
+    one-byte scan (RXM_K1_NOQUAD=1), on long strings that stay alive and carry bytes outside
+    the 4-letter window -- singly, in every position of a 16-byte vector, and in runs."""
+    t, _, _ = load_case(name)
+    rng = np.random.default_rng(5)
+    ab = np.frombuffer(b"ab", dtype=np.uint8)
+    strings = []
+    for L in (64, 200, 1000, 3000):
+        for _ in range(40):
+            strings.append(bytes(rng.choice(ab, size=L)))
+    base = (b"aaba" + b"a" * 200 + b"bb" * 30 + b"aa" + b"abb") * 3
+    strings.append(base)
+    for junk in (b"c", b"d", b"`", b"z", b"\x00", b"\xff", b"A", b"1"):
+        for pos in range(20, 20 + 33):
+            s = bytearray(base)
+            s[pos] = junk[0]
+            strings.append(bytes(s))
+        s = bytearray(base)
+        s[100:140] = junk * 40
+        strings.append(bytes(s))
+    for _ in range(200):  # mostly-window strings with a few outsiders
+        s = bytearray(rng.choice(ab, size=int(rng.integers(100, 600))).tobytes())
+        for p in rng.integers(0, len(s), size=3):
+            s[p] = int(rng.choice(np.frombuffer(b"abcd.`z", dtype=np.uint8)))
+        strings.append(bytes(s))
+    chars, off = H.make_batch(strings)
+    want = H.oracle_bits(t, chars, off)
+    m = rxm.Matcher(t, 0)
+    stride = m.plan().dfa_stride
+    got = m.match_host(chars, off)
+    m.close()
+    monkeypatch.setenv("RXM_K1_NOQUAD", "1")
+    m1 = rxm.Matcher(t, 0)
+    assert m1.plan().dfa_stride == 1
+    got1 = m1.match_host(chars, off)
+    m1.close()
+    assert np.array_equal(got1, want)
+    assert np.array_equal(got, want), (stride, int((got != want).sum()))
+    if name == "nfa_config2":
+        assert stride == 4
+
+
 def test_k1_large_batch_properties():
     """BASELINE-sized property checks (no oracle at this size): the result vector is a
     pure function of each string -- a permuted batch gives the permuted bits, and a batch
