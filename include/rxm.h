@@ -146,6 +146,23 @@ int rxm_free(rxm_handle h);
 int rxm_match_batch(rxm_handle h, const uint8_t *chars, const uint64_t *offsets, uint64_t n,
                     uint8_t *out_bits, void *stream);
 
+/*
+ * The same for RAW TEXT: `text[0 .. nbytes)` is split on the device into the tokens
+ * `cin >> text` would deliver (matchers/match.cpp:22-23: runs of space, \t, \n, \v,
+ * \f, \r separate tokens) and the tokens before the first token `exit`
+ * (match.cpp:24; all of them if there is none) are matched in order:
+ * out_bits[k] = 0/1 for token k, *n_tokens = how many there were, *saw_exit (may
+ * be NULL) = 1 if the sentinel was met.  `text` and
+ * `out_bits` are both host or both device pointers; `out_cap` is the room in
+ * out_bits.  If there are more tokens than `out_cap` nothing is matched, *n_tokens is
+ * set and the call returns RXM_ERR_INVALID -- call again with that much room.
+ * nbytes must be below 4 GiB (cut larger inputs at whitespace).  The call synchronises
+ * `stream` once (the token count comes back to the host); with device pointers the
+ * matching itself is then asynchronous on `stream` as in rxm_match_batch.
+ */
+int rxm_match_text(rxm_handle h, const uint8_t *text, uint64_t nbytes, uint8_t *out_bits,
+                   uint64_t out_cap, uint64_t *n_tokens, int *saw_exit, void *stream);
+
 /* Number of kernels of this library launched through `h` so far. */
 int rxm_launch_count(rxm_handle h, uint64_t *launches);
 

@@ -13,11 +13,13 @@
 //   diploma_rxm -match [flags] -batch IN.rxmb OUT.bits [-regex R]   file batch route
 //       IN:  "RXMBATCH" | u64 n | u64 total | u64 offsets[n+1] | u8 chars[total]
 //       OUT: n bytes, 0/1
-//   extra: -device D (default 0), -chunk N (tokens per device batch, default 1<<20)
+//   extra: -device D (default 0), -chunk N (bytes of input per device batch, default 256 MiB)
 //
-// Differences from the reference that are deliberate: results are printed when a
-// batch is flushed (at `exit`, EOF, or every -chunk tokens) instead of after each
-// token; EOF ends the loop (the reference spins forever, match.cpp:23-31).
+// The tokens are found ON THE DEVICE (rxm_match_text): stdin is read as raw bytes and
+// shipped as it is.  Differences from the reference that are deliberate: results are
+// printed when a piece is flushed (at `exit`, end of input, every -chunk bytes, or per
+// line on a terminal) instead of after each token; end of input ends the loop (the
+// reference spins forever, match.cpp:23-31).
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -27,22 +29,36 @@
 #include <string>
 #include <vector>
 
+// read(2) / isatty(3) under private names: <unistd.h> cannot be included next to the reference's
+// edge.h, whose global `enum MemoryAction { open, close }` (edge.h:29-32) collides with close(2).
+extern "C" long rxm_posix_read(int, void *, unsigned long) __asm__("read");
+extern "C" int rxm_posix_isatty(int) __asm__("isatty");
+
 #include "regex/regex.h"  // reference header (-I<reference root>)
 
 #include "rxm_flatten.hpp"
 
-static int flush_batch(rxm_handle h, std::vector<uint8_t> &chars, std::vector<uint64_t> &off) {
-    const uint64_t n = off.size() - 1;
-    if (n == 0) return RXM_OK;
-    std::vector<uint8_t> bits(n);
-    const int st = rxm_match_batch(h, chars.data(), off.data(), n, bits.data(), nullptr);
+// Matches the tokens of text[0..len) on the device (tokenised there too) and prints one
+// `0`/`1` line per token (match.cpp:29).  *done <- the `exit` sentinel was met (match.cpp:24).
+static int match_piece(rxm_handle h, const uint8_t *text, size_t len, bool *done) {
+    std::vector<uint8_t> bits((len + 1) / 2 + 1);
+    uint64_t n = 0;
+    int saw_exit = 0;
+    const int st = rxm_match_text(h, text, len, bits.data(), bits.size(), &n, &saw_exit, nullptr);
     if (st != RXM_OK) return st;
-    for (uint64_t i = 0; i < n; i++) std::cout << int(bits[i]) << "\n";  // match.cpp:29
+    std::string outbuf;
+    outbuf.reserve(size_t(n) * 2);
+    for (uint64_t i = 0; i < n; i++) {
+        outbuf.push_back(bits[i] ? '1' : '0');
+        outbuf.push_back('\n');
+    }
+    std::cout << outbuf;
     std::cout.flush();
-    chars.clear();
-    off.assign(1, 0);
+    *done = saw_exit != 0;
     return RXM_OK;
 }
+
+static inline bool is_ws(uint8_t c) { return c == ' ' || (c >= 9 && c <= 13); }  // what `cin >>` skips
 
 int main(int argc, char **argv) {
     if (argc < 2 || std::strcmp(argv[1], "-match") != 0) {
@@ -55,7 +71,7 @@ int main(int argc, char **argv) {
     std::string regex;
     bool have_regex = false;
     int device = 0;
-    uint64_t chunk = uint64_t(1) << 20;
+    uint64_t chunk = uint64_t(256) << 20;
     // main.cpp:19-40
     if (argc > 2 && std::strcmp(argv[2], "-all") == 0) bnf = reverse = ssnf = true;
     for (int i = 2; i < argc; i++) {
@@ -68,7 +84,32 @@ int main(int argc, char **argv) {
         else if (a == "-device" && i + 1 < argc) device = std::atoi(argv[++i]);
         else if (a == "-chunk" && i + 1 < argc) chunk = std::strtoull(argv[++i], nullptr, 10);
     }
-    if (!have_regex && !(std::cin >> regex)) return 2;  // main.cpp:42-43
+    // stdin is read with read(2) so that nothing is buffered away from the token loop below
+    std::vector<uint8_t> buf;
+    size_t pos = 0;  // first unconsumed byte of buf
+    bool eof = false;
+    auto fill = [&]() {  // one read(2); false at end of input
+        const size_t old = buf.size(), want = size_t(8) << 20;
+        buf.resize(old + want);
+        const long got = rxm_posix_read(0, buf.data() + old, want);
+        buf.resize(old + (got > 0 ? size_t(got) : 0));
+        if (got <= 0) eof = true;
+        return got > 0;
+    };
+    if (!have_regex) {  // main.cpp:42-43: cin >> regex
+        for (;;) {
+            while (pos < buf.size() && is_ws(buf[pos])) pos++;
+            size_t e = pos;
+            while (e < buf.size() && !is_ws(buf[e])) e++;
+            if (e > pos && (e < buf.size() || eof)) {
+                regex.assign(reinterpret_cast<const char *>(buf.data()) + pos, e - pos);
+                pos = e;
+                break;
+            }
+            if (eof) return 2;
+            fill();
+        }
+    }
 
     Regexp *re = Regexp::parse_regexp(regex);                        // match.cpp:12
     bool is_mfa = false;
@@ -120,16 +161,47 @@ int main(int argc, char **argv) {
         return 0;
     }
 
-    std::vector<uint8_t> chars;
-    std::vector<uint64_t> off(1, 0);
-    std::string text;
-    while (std::cin >> text) {  // match.cpp:22-31
-        if (text == "exit") break;
-        chars.insert(chars.end(), text.begin(), text.end());
-        off.push_back(chars.size());
-        if (off.size() - 1 >= chunk && (st = flush_batch(h, chars, off)) != RXM_OK) break;
+    // match.cpp:22-31.  The raw bytes go to the device as they are; pieces are cut at
+    // whitespace so that no token is split.  A piece is flushed when `chunk_bytes` have
+    // gathered, at end of input, or -- on a terminal -- when a line is complete.
+    const bool tty = rxm_posix_isatty(0) != 0;
+    const size_t chunk_bytes = size_t(chunk) < (size_t(1) << 16) ? (size_t(1) << 16)
+                             : (size_t(chunk) > (size_t(3) << 30) ? (size_t(3) << 30) : size_t(chunk));
+    bool done = false;
+    while (!done) {
+        const bool line = tty && buf.size() > pos && buf.back() == '\n';
+        if (!eof && !line && buf.size() - pos < chunk_bytes) {
+            fill();
+            continue;
+        }
+        size_t end = buf.size();
+        if (!eof) {  // keep the (possibly incomplete) last token for the next piece
+            while (end > pos && !is_ws(buf[end - 1])) end--;
+            if (end == pos) {  // one token longer than everything read so far
+                fill();
+                continue;
+            }
+        }
+        if (end - pos > (size_t(3) << 30)) {  // rxm_match_text takes < 4 GiB: cut at whitespace
+            end = pos + (size_t(3) << 30);
+            while (end > pos && !is_ws(buf[end - 1])) end--;
+            if (end == pos) {
+                std::fprintf(stderr, "diploma_rxm: a token of more than 3 GiB\n");
+                return 3;
+            }
+        }
+        if (end > pos) st = match_piece(h, buf.data() + pos, end - pos, &done);
+        if (st != RXM_OK) break;
+        pos = end;
+        if (pos == buf.size()) {
+            buf.clear();
+            pos = 0;
+        } else if (pos > (size_t(64) << 20)) {
+            buf.erase(buf.begin(), buf.begin() + pos);
+            pos = 0;
+        }
+        if (eof && pos == buf.size()) break;
     }
-    if (st == RXM_OK) st = flush_batch(h, chars, off);
     if (st != RXM_OK) {
         std::fprintf(stderr, "diploma_rxm: match: %s (%s)\n", rxm_strerror(st), rxm_last_cuda_error());
         return 3;

@@ -79,6 +79,13 @@ struct rxm_matcher {
     size_t cap_recs = 0;
     uint32_t *d_k1_counter = nullptr;    // scan kernel's task counter
 
+    // tokeniser workspace (rxm_match_text)
+    uint64_t *d_tok_begin = nullptr, *d_tok_end = nullptr;
+    size_t cap_tok = 0;
+    uint64_t *d_tok_status = nullptr;
+    size_t cap_tok_status = 0;
+    uint32_t *d_tok_ticket = nullptr;          // [1] ticket, then 2 x u64 result (16-byte aligned)
+
     unsigned long long *d_overflow = nullptr;  // strings that hit a kernel limit
     uint64_t launches = 0;
     uint64_t last_overflow = 0;
@@ -217,6 +224,10 @@ extern "C" int rxm_free(rxm_handle h) {
     cudaFree(h->d_overflow);
     cudaFree(h->d_recs);
     cudaFree(h->d_k1_counter);
+    cudaFree(h->d_tok_begin);
+    cudaFree(h->d_tok_end);
+    cudaFree(h->d_tok_status);
+    cudaFree(h->d_tok_ticket);
     delete h;
     return RXM_OK;
 }
@@ -238,7 +249,7 @@ extern "C" int rxm_overflow_count(rxm_handle h, uint64_t *count) {
 }
 
 // total_chars: offsets[n] - offsets[0] if the caller knows it, else ~0ull
-static int launch_on_device(rxm_matcher *m, const uint8_t *d_chars, const uint64_t *d_offsets,
+static int launch_on_device(rxm_matcher *m, const uint8_t *d_chars, rxm::Spans spans,
                             uint64_t n, uint8_t *d_out, cudaStream_t stream, uint64_t total_chars) {
     CU(cudaMemsetAsync(m->d_overflow, 0, sizeof(unsigned long long), stream));
     if (n == 0) return RXM_OK;
@@ -255,7 +266,7 @@ static int launch_on_device(rxm_matcher *m, const uint8_t *d_chars, const uint64
             m->cap_recs = want;
         }
         if (!m->d_k1_counter) CU(cudaMalloc(reinterpret_cast<void **>(&m->d_k1_counter), 64 * sizeof(uint32_t)));
-        rxm::K1Launch a{m->d_k1_table, m->d_k1_accept, d_chars, d_offsets, n, d_out, m->d_recs,
+        rxm::K1Launch a{m->d_k1_table, m->d_k1_accept, d_chars, spans, n, d_out, m->d_recs,
                         m->d_k1_counter, m->d_overflow, m->sm_count, stream};
         st = rxm::k1_launch(m->k1, a, &launched);
     } else if (m->info.engine == RXM_ENGINE_K3_WARP) {
@@ -270,19 +281,19 @@ static int launch_on_device(rxm_matcher *m, const uint8_t *d_chars, const uint64
         if (tile < 32 && !m->k3_tile_forced) {
             if (total_chars == ~0ull) {
                 uint64_t ends[1] = {0};
-                CU(cudaMemcpyAsync(ends, d_offsets + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+                CU(cudaMemcpyAsync(ends, spans.end + (n - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
                 CU(cudaStreamSynchronize(stream));
                 total_chars = ends[0];
             }
             if (total_chars / n > 4096) tile = 32;
         }
         st = rxm::k3_launch(v, gp, uint32_t(m->prog.items.size()), uint32_t(m->prog.begin.size()),
-                            m->tables.n_cells, tile, d_chars, d_offsets, n, d_out, m->d_overflow, m->d_overflow + 1,
+                            m->tables.n_cells, tile, d_chars, spans, n, d_out, m->d_overflow, m->d_overflow + 1,
                             m->sm_count, stream, &launched);
     } else {
         rxm::MfaView v{m->d_edge_begin, m->d_edges, m->tables.n_states(), m->tables.start,
                        m->tables.finish, m->tables.reversed};
-        st = rxm::k2_launch(v, m->tables.n_cells, m->tables.n_edges(), d_chars, d_offsets, n, d_out,
+        st = rxm::k2_launch(v, m->tables.n_cells, m->tables.n_edges(), d_chars, spans, n, d_out,
                             m->d_overflow, m->d_overflow + 1, m->sm_count, stream, &launched);
     }
     m->launches += uint64_t(launched);
@@ -303,7 +314,7 @@ extern "C" int rxm_match_batch(rxm_handle h, const uint8_t *chars, const uint64_
     const bool dev_out = is_device_ptr(out_bits);
     const bool dev_chars = chars ? is_device_ptr(chars) : dev_off;
     if (dev_off && dev_out && dev_chars)
-        return launch_on_device(m, chars, offsets, n, out_bits, stream, ~0ull);
+        return launch_on_device(m, chars, rxm::csr_spans(offsets), n, out_bits, stream, ~0ull);
     if (dev_off || dev_out || (chars && dev_chars)) return RXM_ERR_INVALID;  // all host or all device
 
     // host buffers: stage through the handle's workspace
@@ -333,10 +344,98 @@ extern "C" int rxm_match_batch(rxm_handle h, const uint8_t *chars, const uint64_
     }
     if (total) CU(cudaMemcpyAsync(m->d_chars, chars, total, cudaMemcpyHostToDevice, stream));
     CU(cudaMemcpyAsync(m->d_offsets, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
-    int st = launch_on_device(m, m->d_chars, m->d_offsets, n, m->d_bits, stream, total);
+    int st = launch_on_device(m, m->d_chars, rxm::csr_spans(m->d_offsets), n, m->d_bits, stream, total);
     if (st != RXM_OK) return st;
     unsigned long long ovf = 0;
     if (n) CU(cudaMemcpyAsync(out_bits, m->d_bits, n, cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpyAsync(&ovf, m->d_overflow, sizeof ovf, cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    m->last_overflow = ovf;
+    return ovf ? RXM_ERR_OVERFLOW : RXM_OK;
+}
+
+// Raw text in, bits out: the tokenisation of match.cpp:22-24 (`cin >> text` until "exit")
+// runs on the device (rxm_tok.cu), its spans feed the same kernels as rxm_match_batch.
+extern "C" int rxm_match_text(rxm_handle h, const uint8_t *text, uint64_t nbytes, uint8_t *out_bits,
+                              uint64_t out_cap, uint64_t *n_tokens, int *saw_exit, void *stream_) {
+    if (!h || !n_tokens || (nbytes && !text) || (out_cap && !out_bits)) return RXM_ERR_INVALID;
+    *n_tokens = 0;
+    if (saw_exit) *saw_exit = 0;
+    rxm_matcher *m = h;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CU(cudaSetDevice(m->device));
+    const bool dev_text = nbytes ? is_device_ptr(text) : is_device_ptr(out_bits);
+    const bool dev_out = out_cap ? is_device_ptr(out_bits) : dev_text;
+    if (dev_text != dev_out) return RXM_ERR_INVALID;  // all host or all device
+    if (nbytes >= (1ull << 32) - 64) return RXM_ERR_UNSUPPORTED;  // feed larger inputs in pieces cut at whitespace
+
+    const uint8_t *d_text = text;
+    if (!dev_text) {  // stage the text (and later the bits) through the handle's workspace
+        if (nbytes + 64 > m->cap_chars) {
+            cudaFree(m->d_chars);
+            m->d_chars = nullptr;
+            m->cap_chars = 0;
+            const size_t want = size_t(nbytes + 64 + (nbytes >> 3));
+            CU(cudaMalloc(reinterpret_cast<void **>(&m->d_chars), want));
+            m->cap_chars = want;
+        }
+        if (nbytes) CU(cudaMemcpyAsync(m->d_chars, text, nbytes, cudaMemcpyHostToDevice, stream));
+        d_text = m->d_chars;
+    }
+    if (!d_text) d_text = reinterpret_cast<const uint8_t *>(m->d_overflow);  // empty text: any valid address
+    const uint64_t cap = out_cap ? out_cap : 1;
+    if (cap > m->cap_tok) {
+        cudaFree(m->d_tok_begin);
+        cudaFree(m->d_tok_end);
+        m->d_tok_begin = m->d_tok_end = nullptr;
+        m->cap_tok = 0;
+        const size_t want = size_t(cap + (cap >> 3) + 16);
+        CU(cudaMalloc(reinterpret_cast<void **>(&m->d_tok_begin), want * sizeof(uint64_t)));
+        CU(cudaMalloc(reinterpret_cast<void **>(&m->d_tok_end), want * sizeof(uint64_t)));
+        m->cap_tok = want;
+    }
+    const uint64_t words = rxm::tok_status_words(nbytes);
+    if (words > m->cap_tok_status) {
+        cudaFree(m->d_tok_status);
+        m->d_tok_status = nullptr;
+        m->cap_tok_status = 0;
+        const size_t want = size_t(words + (words >> 2) + 16);
+        CU(cudaMalloc(reinterpret_cast<void **>(&m->d_tok_status), want * sizeof(uint64_t)));
+        m->cap_tok_status = want;
+    }
+    if (!m->d_tok_ticket) CU(cudaMalloc(reinterpret_cast<void **>(&m->d_tok_ticket), 64));
+    rxm::TokWork w{m->d_tok_status, m->cap_tok_status, m->d_tok_ticket,
+                   reinterpret_cast<unsigned long long *>(m->d_tok_ticket + 4)};
+    int launched = 0;
+    int st = rxm::tok_launch(d_text, nbytes, m->d_tok_begin, m->d_tok_end, out_cap, w, m->sm_count, stream, &launched);
+    m->launches += uint64_t(launched);
+    if (st != RXM_OK) return st;
+    unsigned long long res[2] = {0, 0};
+    CU(cudaMemcpyAsync(res, w.d_result, sizeof res, cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    const uint64_t n = res[1] < res[0] ? res[1] : res[0];  // tokens before the first "exit"
+    *n_tokens = n;
+    if (saw_exit) *saw_exit = res[1] < res[0] ? 1 : 0;
+    if (n > out_cap) return RXM_ERR_INVALID;  // *n_tokens says how many bits the caller must provide
+    if (n == 0) return RXM_OK;
+
+    const rxm::Spans spans{m->d_tok_begin, m->d_tok_end};
+    if (dev_text) return launch_on_device(m, d_text, spans, n, out_bits, stream, nbytes);
+    if (n > m->cap_n) {
+        cudaFree(m->d_offsets);
+        cudaFree(m->d_bits);
+        m->d_offsets = nullptr;
+        m->d_bits = nullptr;
+        m->cap_n = 0;
+        const size_t want = size_t(n + 1 + (n >> 3));
+        CU(cudaMalloc(reinterpret_cast<void **>(&m->d_offsets), want * sizeof(uint64_t)));
+        CU(cudaMalloc(reinterpret_cast<void **>(&m->d_bits), want));
+        m->cap_n = want;
+    }
+    st = launch_on_device(m, d_text, spans, n, m->d_bits, stream, nbytes);
+    if (st != RXM_OK) return st;
+    unsigned long long ovf = 0;
+    CU(cudaMemcpyAsync(out_bits, m->d_bits, n, cudaMemcpyDeviceToHost, stream));
     CU(cudaMemcpyAsync(&ovf, m->d_overflow, sizeof ovf, cudaMemcpyDeviceToHost, stream));
     CU(cudaStreamSynchronize(stream));
     m->last_overflow = ovf;

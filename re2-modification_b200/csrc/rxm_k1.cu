@@ -116,7 +116,7 @@ constexpr int K1_TILE = int(K1_TILE_STRINGS);
 constexpr int K1_SORT_THREADS = 1024;
 constexpr int K1_SORT_PER_THREAD = K1_TILE / K1_SORT_THREADS;
 __global__ void __launch_bounds__(K1_SORT_THREADS)
-k1_tilesort_kernel(const uint64_t *__restrict__ offsets, uint64_t n, K1Rec *__restrict__ recs,
+k1_tilesort_kernel(const Spans sp, uint64_t n, K1Rec *__restrict__ recs,
                    uint32_t *__restrict__ task_counter, unsigned long long *__restrict__ overflow) {
     static_assert(K1_BUCKETS == 2 * K1_SORT_THREADS, "two buckets per thread in the prefix pass");
     __shared__ uint32_t cnt[K1_BUCKETS];
@@ -136,8 +136,8 @@ k1_tilesort_kernel(const uint64_t *__restrict__ offsets, uint64_t n, K1Rec *__re
             const uint64_t i = lo + uint32_t(k) * K1_SORT_THREADS + t;
             bkt[k] = 0xffffffffu;
             if (i < n) {
-                beg[k] = offsets[i];
-                const uint64_t l = offsets[i + 1] - beg[k];
+                beg[k] = sp.begin[i];
+                const uint64_t l = sp.end[i] - beg[k];
                 if (l >= 0x7fffffffull) atomicAdd(overflow, 1ull);
                 len[k] = clamp_len(l);
                 bkt[k] = len_bucket(len[k]);
@@ -688,7 +688,7 @@ int k1_launch(const K1Tables &kt, const K1Launch &a, int *launched) {
     uint64_t blocks = ntiles;
     const uint64_t cap = uint64_t(a.sm_count) * 2;
     if (blocks > cap) blocks = cap;
-    k1_tilesort_kernel<<<unsigned(blocks), K1_SORT_THREADS, 0, a.stream>>>(a.d_offsets, a.n, a.d_recs, a.d_task_counter,
+    k1_tilesort_kernel<<<unsigned(blocks), K1_SORT_THREADS, 0, a.stream>>>(a.spans, a.n, a.d_recs, a.d_task_counter,
                                                                           a.d_overflow);
     *launched = 1;
     int st;

@@ -31,7 +31,7 @@ constexpr int K2_THREADS = 128;
 template <int NC, int CAP, int DMAX, bool LOCAL>
 __global__ void __launch_bounds__(K2_THREADS)
 k2_mfa_thread_kernel(MfaView gv, uint32_t n_edges, const uint8_t *__restrict__ chars,
-                     const uint64_t *__restrict__ offsets, uint64_t n, uint8_t *__restrict__ out,
+                     const Spans sp, uint64_t n, uint8_t *__restrict__ out,
                      unsigned long long *__restrict__ overflow, unsigned long long *__restrict__ next_string,
                      uint32_t threads_used) {
     typedef K2Geom<NC, CAP, DMAX> G;
@@ -54,7 +54,7 @@ k2_mfa_thread_kernel(MfaView gv, uint32_t n_edges, const uint8_t *__restrict__ c
     for (;;) {
         const uint64_t i = atomicAdd(next_string, 1ull);
         if (i >= n) break;
-        const uint64_t b = offsets[i], e = offsets[i + 1];
+        const uint64_t b = sp.begin[i], e = sp.end[i];
         int r;
         if (e - b >= 0x7fffffffull) {
             r = 2;
@@ -71,7 +71,7 @@ k2_mfa_thread_kernel(MfaView gv, uint32_t n_edges, const uint8_t *__restrict__ c
 }
 
 template <int NC, int CAP, int DMAX>
-int launch_k2(const MfaView &v, uint32_t n_edges, const uint8_t *d_chars, const uint64_t *d_offsets,
+int launch_k2(const MfaView &v, uint32_t n_edges, const uint8_t *d_chars, Spans spans,
               uint64_t n, uint8_t *d_out, unsigned long long *d_overflow, unsigned long long *d_next,
               int sm_count, cudaStream_t stream) {
     typedef K2Geom<NC, CAP, DMAX> G;
@@ -96,7 +96,7 @@ int launch_k2(const MfaView &v, uint32_t n_edges, const uint8_t *d_chars, const 
     const uint64_t need = (n + threads - 1) / threads;
     if (blocks > need) blocks = need;
     if (cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), stream) != cudaSuccess) return RXM_ERR_CUDA;
-    kern<<<unsigned(blocks), K2_THREADS, smem, stream>>>(v, n_edges, d_chars, d_offsets, n, d_out, d_overflow,
+    kern<<<unsigned(blocks), K2_THREADS, smem, stream>>>(v, n_edges, d_chars, spans, n, d_out, d_overflow,
                                                         d_next, threads);
     return RXM_OK;
 }
@@ -104,13 +104,13 @@ int launch_k2(const MfaView &v, uint32_t n_edges, const uint8_t *d_chars, const 
 }  // namespace
 
 int k2_launch(const MfaView &v, uint32_t n_cells, uint32_t n_edges, const uint8_t *d_chars,
-              const uint64_t *d_offsets, uint64_t n, uint8_t *d_out, unsigned long long *d_overflow,
+              Spans spans, uint64_t n, uint8_t *d_out, unsigned long long *d_overflow,
               unsigned long long *d_next, int sm_count, cudaStream_t stream, int *launched) {
     *launched = 0;
     bool rxm_dispatch_ok = true;
     int st = RXM_OK;
 #define CALL(NC, CAP, DMAX) \
-    st = launch_k2<NC, CAP, DMAX>(v, n_edges, d_chars, d_offsets, n, d_out, d_overflow, d_next, sm_count, stream)
+    st = launch_k2<NC, CAP, DMAX>(v, n_edges, d_chars, spans, n, d_out, d_overflow, d_next, sm_count, stream)
     RXM_MFA_DISPATCH(n_cells, v.n_states, CALL);
 #undef CALL
     if (!rxm_dispatch_ok) return RXM_ERR_UNSUPPORTED;

@@ -14,6 +14,14 @@
 
 namespace rxm {
 
+// Where the strings of a batch are: string i = chars[begin[i] .. end[i]).  A CSR offsets array
+// is {offsets, offsets + 1}; the device tokeniser (rxm_tok.cu) fills two separate arrays.
+struct Spans {
+    const uint64_t *begin;
+    const uint64_t *end;
+};
+inline Spans csr_spans(const uint64_t *offsets) { return Spans{offsets, offsets + 1}; }
+
 // ---- K1: determinised memory-free automaton ------------------------------------------
 enum : uint32_t {
     K1_DIRECT = 0,   // T[byte][SP] u8, SP = 2^log2sp >= n_states, one shared-memory lookup per byte
@@ -49,7 +57,7 @@ struct K1Launch {
     const uint8_t *d_table;
     const uint8_t *d_accept;
     const uint8_t *d_chars;
-    const uint64_t *d_offsets;
+    Spans spans;
     uint64_t n;
     uint8_t *d_out;
     K1Rec *d_recs;               // [n]        workspace
@@ -63,15 +71,30 @@ int k1_launch(const K1Tables &kt, const K1Launch &a, int *launched);
 
 // ---- K2: MFA, one thread per string ------------------------------------------------------
 int k2_launch(const MfaView &dev_view, uint32_t n_cells, uint32_t n_edges, const uint8_t *d_chars,
-              const uint64_t *d_offsets, uint64_t n, uint8_t *d_out, unsigned long long *d_overflow,
+              Spans spans, uint64_t n, uint8_t *d_out, unsigned long long *d_overflow,
               unsigned long long *d_next /* work counter */, int sm_count, cudaStream_t stream,
               int *launched);
 
 // ---- K3: MFA, one warp per string, over host-compiled edge programs --------------------------
 int k3_launch(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n_keys, uint32_t n_cells,
-              uint32_t tile /* lanes per string: 8, 16 or 32 */, const uint8_t *d_chars, const uint64_t *d_offsets, uint64_t n, uint8_t *d_out,
+              uint32_t tile /* lanes per string: 8, 16 or 32 */, const uint8_t *d_chars, Spans spans, uint64_t n, uint8_t *d_out,
               unsigned long long *d_overflow, unsigned long long *d_next, int sm_count, cudaStream_t stream,
               int *launched);
+
+// ---- tokeniser: whitespace-delimited text -> spans (rxm_tok.cu) ------------------------------
+// Same token boundaries as `cin >> text` (matchers/match.cpp:22-23): whitespace is
+// space, \t, \n, \v, \f, \r.  Writes begin/end of the first `cap` tokens and, into
+// d_result[0..1], the number of tokens found and the index of the first token equal to
+// "exit" (the sentinel of match.cpp:24; the token count if there is none).
+struct TokWork {
+    uint64_t *d_status;      // [blocks] look-back words
+    uint64_t status_cap;     // in words
+    uint32_t *d_ticket;      // [1]
+    unsigned long long *d_result;  // [2]
+};
+uint64_t tok_status_words(uint64_t nbytes);
+int tok_launch(const uint8_t *d_text, uint64_t nbytes, uint64_t *d_begin, uint64_t *d_end, uint64_t cap,
+               const TokWork &w, int sm_count, cudaStream_t stream, int *launched);
 
 }  // namespace rxm
 #endif

@@ -31,7 +31,7 @@ ENGINE_NAMES = {1: "K1_DFA", 2: "K1_BITSET", 3: "K2_THREAD", 4: "K3_WARP"}
 # every symbol include/rxm.h declares (tests check that the library exports them all)
 ABI_SYMBOLS = [
     "rxm_tables_format", "rxm_tables_parse", "rxm_tables_release", "rxm_tables_validate",
-    "rxm_tables_upload", "rxm_plan_query", "rxm_free", "rxm_match_batch",
+    "rxm_tables_upload", "rxm_plan_query", "rxm_free", "rxm_match_batch", "rxm_match_text",
     "rxm_launch_count", "rxm_overflow_count", "rxm_strerror", "rxm_last_cuda_error",
 ]
 
@@ -92,6 +92,9 @@ def lib() -> C.CDLL:
         L.rxm_match_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                                       C.c_void_p]
         L.rxm_match_batch.restype = C.c_int
+        L.rxm_match_text.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+                                     C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.c_void_p]
+        L.rxm_match_text.restype = C.c_int
         L.rxm_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.rxm_launch_count.restype = C.c_int
         L.rxm_overflow_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
@@ -157,6 +160,7 @@ class Matcher:
         self.tables = tables
         self.device = device
         self._h = C.c_void_p()
+        self.saw_exit = C.c_int(0)  # set by the last match_text_* call
         st = lib().rxm_tables_upload(tables.ptr, device, C.byref(self._h))
         if st != RXM_OK:
             raise RxmError(st, "rxm_tables_upload: " + lib().rxm_last_cuda_error().decode())
@@ -186,6 +190,32 @@ class Matcher:
         st = lib().rxm_match_batch(self._h, chars_ptr, offsets_ptr, n, out_ptr, stream)
         if st != RXM_OK:
             raise RxmError(st, "rxm_match_batch: " + lib().rxm_last_cuda_error().decode())
+
+    def match_text_host(self, text: bytes, cap: Optional[int] = None) -> np.ndarray:
+        """Raw whitespace-delimited text in (host), bits of the tokens before `exit` out:
+        rxm_match_text (tokenised on the device)."""
+        buf = np.frombuffer(text, dtype=np.uint8) if len(text) else np.zeros(0, dtype=np.uint8)
+        cap = (len(text) + 1) // 2 if cap is None else cap
+        out = np.empty(max(cap, 1), dtype=np.uint8)
+        n = C.c_uint64(0)
+        st = lib().rxm_match_text(self._h, buf.ctypes.data if buf.size else None, buf.size,
+                                  out.ctypes.data, cap, C.byref(n), C.byref(self.saw_exit), None)
+        if st != RXM_OK:
+            e = RxmError(st, "rxm_match_text: " + lib().rxm_last_cuda_error().decode())
+            e.n_tokens = n.value
+            raise e
+        return out[:n.value].copy()
+
+    def match_text_ptrs(self, text_ptr: int, nbytes: int, out_ptr: int, cap: int, stream: int = 0) -> int:
+        """Raw pointers (both device or both host); returns the number of tokens matched."""
+        n = C.c_uint64(0)
+        st = lib().rxm_match_text(self._h, text_ptr, nbytes, out_ptr, cap, C.byref(n),
+                                  C.byref(self.saw_exit), stream)
+        if st != RXM_OK:
+            e = RxmError(st, "rxm_match_text: " + lib().rxm_last_cuda_error().decode())
+            e.n_tokens = n.value
+            raise e
+        return n.value
 
     def launch_count(self) -> int:
         v = C.c_uint64(0)

@@ -52,6 +52,7 @@ def test_strerror_and_null_arguments():
     L = rxm.lib()
     assert L.rxm_tables_validate(None) == rxm.RXM_ERR_INVALID
     assert L.rxm_match_batch(None, None, None, 0, None, None) == rxm.RXM_ERR_INVALID
+    assert L.rxm_match_text(None, None, 0, None, 0, None, None, None) == rxm.RXM_ERR_INVALID
     assert L.rxm_free(None) == rxm.RXM_OK
 
 

@@ -53,3 +53,29 @@ def test_match_driver_batch_route():
                            capture_output=True, cwd=td, timeout=300)
         assert r.returncode == 0, r.stderr.decode()[-400:]
         assert np.array_equal(np.fromfile(fout, dtype=np.uint8), bits)
+
+
+@pytest.mark.skipif(not os.path.exists(DRIVER), reason="diploma_rxm not built")
+def test_match_driver_pieces_eof_and_tokens_after_exit():
+    """Raw-text route: several tokens per line, input cut into 64 KB pieces at whitespace
+    (a token longer than a piece included), end of input without `exit`, and tokens after
+    `exit` ignored (match.cpp:24)."""
+    m = BY_NAME["nfa_config2"]
+    t, _, _ = load_case("nfa_config2")
+    rng = np.random.default_rng(2)
+    ab = np.frombuffer(b"ab", dtype=np.uint8)
+    toks = [bytes(rng.choice(ab, size=int(L))) for L in rng.integers(1, 3000, size=400)]
+    toks.insert(100, b"aaba" + b"a" * 200_000)  # longer than a piece
+    chars, off = H.make_batch(toks)
+    want = [int(x) for x in H.oracle_bits(t, chars, off)]
+    body = b""
+    for i, tk in enumerate(toks):
+        body += tk + (b" " if i % 3 else b"\n")
+    with tempfile.TemporaryDirectory() as td:
+        for tail, flags in ((b"", []), (b"exit\nab aaba\n", []), (b"", ["-chunk", "65536"]),
+                            (b"exit aaba", ["-chunk", "65536"])):
+            r = subprocess.run([DRIVER, "-match", *flags], input=m["regex"].encode() + b"\n" + body + tail,
+                               capture_output=True, cwd=td, timeout=300)
+            assert r.returncode == 0, r.stderr.decode()[-400:]
+            got = [int(ln) for ln in r.stdout.decode().splitlines() if ln in ("0", "1")]
+            assert got == want, (tail, flags, len(got), len(want))

@@ -272,3 +272,102 @@ def test_k1_large_batch_properties():
     want = H.oracle_bits(t, chars[:int(off_h[-1])].cpu().numpy(), off_h)
     assert np.array_equal(out[:k].cpu().numpy(), want)
     m.close()
+
+
+# ---- rxm_match_text: tokenisation on the device (match.cpp:22-24) -----------------------------
+def _ref_tokens(text: bytes):
+    """`cin >> text` until the token "exit": bytes.split() splits on the same six bytes."""
+    toks = text.split()
+    if b"exit" in toks:
+        toks = toks[:toks.index(b"exit")]
+    return toks
+
+
+def _check_text(m, t, text: bytes):
+    toks = _ref_tokens(text)
+    got = m.match_text_host(text)
+    assert len(got) == len(toks), (len(got), len(toks))
+    assert m.saw_exit.value == (1 if b"exit" in text.split() else 0)
+    if toks:
+        chars, off = H.make_batch(toks)
+        assert np.array_equal(got, H.oracle_bits(t, chars, off))
+
+
+@pytest.mark.parametrize("name", ["nfa_config2", "ex05_fwd", "ex02_rev"])
+def test_match_text_equals_cin_tokenisation(name):
+    t, strings, bits = load_case(name)
+    m = rxm.Matcher(t, 0)
+    rng = np.random.default_rng(11)
+    seps = [b" ", b"\n", b"\t", b"\r\n", b"\v", b"\f", b"  \n\n ", b"\t \r"]
+    # the golden strings, with every kind of separator, no trailing separator
+    all_strings = strings
+    strings = [s for s in strings if s and s != b"exit" and not any(c in s for c in b" \t\n\v\f\r")]
+    keep = set(strings)
+    text = b"".join(s + seps[int(rng.integers(len(seps)))] for s in strings[:-1]) + strings[-1]
+    got = m.match_text_host(text)
+    assert np.array_equal(got, bits[[i for i, s in enumerate(all_strings) if s in keep]])
+    _check_text(m, t, text)
+    # leading / trailing whitespace, exit in the middle, exit-like tokens that are not the sentinel
+    _check_text(m, t, b"  \n" + text + b" \n")
+    _check_text(m, t, b"aaba exits aexit ex it exit aaba aaba")
+    _check_text(m, t, b"exit aaba")
+    _check_text(m, t, b"aaba\nexit")
+    _check_text(m, t, b"aaba\nexit\n")
+    for blank in (b"", b" ", b"\n\n\n", b" \t\r\n\v\f"):
+        assert m.match_text_host(blank).shape == (0,)
+    # bytes that are NOT whitespace for `cin >>`: NUL, 0x1c-0x1f, 0x85, 0xa0
+    _check_text(m, t, b"aa\x00ba ab\x1cab \x85 \xa0aaba a\x0eb")
+    m.close()
+
+
+def test_match_text_tokens_across_piece_boundaries():
+    """Tokens that straddle the tokeniser's 64-byte thread pieces and 16 KB block pieces, runs of
+    one-letter tokens (the densest case), and a token that ends on the very last byte."""
+    t, _, _ = load_case("nfa_config2")
+    m = rxm.Matcher(t, 0)
+    rng = np.random.default_rng(3)
+    ab = np.frombuffer(b"ab", dtype=np.uint8)
+    parts = []
+    for L in list(range(1, 130)) + [16383, 16384, 16385, 40000, 63, 64, 65] + [1] * 300:
+        parts.append(bytes(rng.choice(ab, size=L)))
+    for sep in (b" ", b"\n", b"  "):
+        text = sep.join(parts)
+        _check_text(m, t, text)
+        _check_text(m, t, text + sep)
+    # one-letter tokens only: 2 bytes per token
+    _check_text(m, t, b"a b " * 20000)
+    # a long walk inside the language, then many of them
+    alive = [b"aaba" + b"a" * int(k) for k in rng.integers(0, 3000, size=400)]
+    _check_text(m, t, b"\n".join(alive))
+    m.close()
+
+
+def test_match_text_device_pointers_alignment_and_capacity():
+    import torch
+    t, _, _ = load_case("nfa_config2")
+    m = rxm.Matcher(t, 0)
+    toks = [b"aaba", b"ab", b"bbaaba", b"aabaa", b"b" * 100, b"aababbaa"] * 50
+    text = b"\n".join(toks) + b"\n"
+    chars, off = H.make_batch(toks)
+    want = H.oracle_bits(t, chars, off)
+    for shift in (0, 1, 5, 15):
+        d = torch.cat([torch.full((shift,), ord("a"), dtype=torch.uint8),
+                       torch.frombuffer(bytearray(text), dtype=torch.uint8)]).cuda()
+        out = torch.full((len(toks) + 3,), 9, dtype=torch.uint8, device="cuda")
+        n = m.match_text_ptrs(d.data_ptr() + shift, len(text), out.data_ptr(), out.numel(),
+                              torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert n == len(toks)
+        assert np.array_equal(out[:n].cpu().numpy(), want), shift
+        assert out[n:].eq(9).all()
+    # too little room: nothing is matched, the count comes back
+    with pytest.raises(rxm.RxmError) as e:
+        m.match_text_host(text, cap=10)
+    assert e.value.status == rxm.RXM_ERR_INVALID and e.value.n_tokens == len(toks)
+    # mixed host / device pointers
+    d = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
+    host_out = np.empty(len(toks), dtype=np.uint8)
+    with pytest.raises(rxm.RxmError) as e:
+        m.match_text_ptrs(d.data_ptr(), len(text), host_out.ctypes.data, len(toks))
+    assert e.value.status == rxm.RXM_ERR_INVALID
+    m.close()
