@@ -515,6 +515,57 @@ def main():
         }
         del u_chars, u_off
 
+    # ---- raw-text route (config 2): tokenise on the device, then match ------------------------
+    if wl == "config2":
+        nt = min(n, 250_000)
+        t_off = jobs[0]["offsets"][:nt + 1]
+        t_bytes = int(t_off[-1])
+        lens = (t_off[1:] - t_off[:-1])
+        text = torch.full((t_bytes + nt,), 10, dtype=torch.uint8, device=dev)  # '\n' after every string
+        idx = torch.arange(t_bytes, device=dev, dtype=torch.int64)
+        idx += torch.repeat_interleave(torch.arange(nt, device=dev, dtype=torch.int64), lens)
+        text[idx] = jobs[0]["chars"][:t_bytes]
+        del idx
+        t_out = torch.empty(nt, dtype=torch.uint8, device=dev)
+        for _ in range(3):
+            got_n = m.match_text_ptrs(text.data_ptr(), text.numel(), t_out.data_ptr(), nt, stream)
+        torch.cuda.synchronize()
+        t_ref = torch.empty(nt, dtype=torch.uint8, device=dev)
+        m.match_ptrs(jobs[0]["chars"].data_ptr(), jobs[0]["offsets"].data_ptr(), nt, t_ref.data_ptr(), stream)
+        torch.cuda.synchronize()
+        if got_n != nt or not torch.equal(t_out, t_ref):
+            raise SystemExit("bench.py: raw-text route disagrees with the offsets route")
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            m.match_text_ptrs(text.data_ptr(), text.numel(), t_out.data_ptr(), nt, stream)
+        e1.record()
+        barrier()
+        t_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        h_text = torch.empty(text.numel(), dtype=torch.uint8, pin_memory=True)
+        h_text.copy_(text)
+        h_tout = torch.empty(nt, dtype=torch.uint8, pin_memory=True)
+        torch.cuda.synchronize()
+        m.match_text_ptrs(h_text.data_ptr(), h_text.numel(), h_tout.data_ptr(), nt, stream)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            m.match_text_ptrs(h_text.data_ptr(), h_text.numel(), h_tout.data_ptr(), nt, stream)
+        th_s = (time.perf_counter() - t0) / e2e_steps
+        if not torch.equal(h_tout, t_out.cpu()):
+            raise SystemExit("bench.py: raw-text host route disagrees with the device route")
+        extra["text_route"] = {
+            "note": "rxm_match_text: newline-separated raw text, tokenised on the device "
+                    "(match.cpp:22-24 semantics), then the same kernels; includes one stream "
+                    "synchronisation per call (token count to the host)",
+            "strings": nt, "text_bytes": int(text.numel()),
+            "device_ms_per_step": t_ms, "device_strings_per_sec": nt / (t_ms / 1e3),
+            "device_input_gb_s": text.numel() / (t_ms / 1e3) / 1e9,
+            "host_ms_per_step": th_s * 1e3, "host_strings_per_sec": nt / th_s,
+            "host_input_gb_s": text.numel() / th_s / 1e9,
+        }
+        del text, h_text
+
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -537,6 +588,7 @@ def main():
             "config": {"workload": desc, "strings_per_gpu": n, "bytes_per_gpu": total_bytes,
                        "mean_len": total_bytes / n, "match_fraction": match_frac,
                        "engine": "+".join(sorted({rxm.ENGINE_NAMES.get(j["matcher"].plan().engine, "?") for j in jobs})),
+                       "dfa_stride": int(jobs[0]["matcher"].plan().dfa_stride),
                        "jobs_per_step": len(jobs),
                        "l2": "inputs (%.2f GB per GPU) are larger than the 126 MB L2" % (total_bytes / 1e9),
                        "sharding": "by string index, one rank per GPU, no data-path collective"},

@@ -185,10 +185,13 @@ k1_tilesort_kernel(const Spans sp, uint64_t n, K1Rec *__restrict__ recs,
 }
 
 // ---- scan kernel -----------------------------------------------------------------------
+// 16-byte asynchronous copy, L1 bypassed; the L2::256B hint makes L2 fetch the whole 256-byte
+// block on first touch, so DRAM sees 256-byte bursts per string instead of 64-byte ones
+// (measured: 0.443 -> 0.418 ms per config-2 step; L2::128B changes nothing, .ca doubles the time).
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gsrc, bool pred) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t"
-        "@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}\n" ::"r"(smem_dst),
+        "@p cp.async.cg.shared.global.L2::256B [%0], [%1], 16;\n\t}\n" ::"r"(smem_dst),
         "l"(gsrc), "r"(int(pred))
         : "memory");
 }
