@@ -54,6 +54,7 @@ struct rxm_matcher {
     rxm::K1Tables k1{};
     uint8_t *d_k1_table = nullptr;   // direct: [256][SP] u8 ; classed: see rxm_kernels.cuh
     uint8_t *d_k1_accept = nullptr;
+    uint32_t *d_k1b_edges = nullptr;  // K1B: packed edges (d_edge_begin holds the row starts)
 
     // K2: MFA tables
     uint16_t *d_edge_begin = nullptr;
@@ -140,7 +141,26 @@ extern "C" int rxm_tables_upload(const rxm_tables *host_tables, int device, rxm_
     };
 
     if (t.kind == RXM_KIND_NFA) {
-        st = rxm::plan_dfa(t, m->dfa, &err);
+        const char *nfa_force = getenv("RXM_NFA_ENGINE");  // "bitset": tuning and tests
+        const bool force_bitset = nfa_force && std::strcmp(nfa_force, "bitset") == 0;
+        st = force_bitset ? RXM_ERR_UNSUPPORTED : rxm::plan_dfa(t, m->dfa, &err);
+        if (st == RXM_ERR_UNSUPPORTED) {
+            // too many active sets for a table (or forced): simulate the set itself (K1B)
+            std::string berr;
+            if (rxm::check_nfa_bitset(t, &berr) != RXM_OK) {
+                if (err.empty() || force_bitset) err = berr;
+                else err += "; bit-set engine: " + berr;
+                return fail(RXM_ERR_UNSUPPORTED);
+            }
+            err.clear();
+            std::vector<uint16_t> eb;
+            std::vector<uint32_t> ed;
+            rxm::k1b_build_tables(t, eb, ed);
+            if ((st = upload_vec(eb, &m->d_edge_begin)) != RXM_OK) return fail(st);
+            if ((st = upload_vec(ed, &m->d_k1b_edges)) != RXM_OK) return fail(st);
+            m->info.engine = RXM_ENGINE_K1_BITSET;
+            goto planned;
+        }
         if (st != RXM_OK) return fail(st);
         std::vector<uint8_t> table, accept;
         st = rxm::k1_build_tables(m->dfa, m->k1, table, accept, &err);
@@ -194,6 +214,7 @@ extern "C" int rxm_tables_upload(const rxm_tables *host_tables, int device, rxm_
             return fail(RXM_ERR_UNSUPPORTED);
         }
     }
+planned:
     // [0] strings that hit a kernel limit, [1] K2/K3 work counter
     if (cudaMalloc(reinterpret_cast<void **>(&m->d_overflow), 2 * sizeof(unsigned long long)) != cudaSuccess)
         return fail(cuda_fail(cudaGetLastError(), "cudaMalloc overflow counter"));
@@ -213,6 +234,7 @@ extern "C" int rxm_free(rxm_handle h) {
     cudaSetDevice(h->device);
     cudaFree(h->d_k1_table);
     cudaFree(h->d_k1_accept);
+    cudaFree(h->d_k1b_edges);
     cudaFree(h->d_edge_begin);
     cudaFree(h->d_edges);
     cudaFree(h->d_items);
@@ -269,6 +291,10 @@ static int launch_on_device(rxm_matcher *m, const uint8_t *d_chars, rxm::Spans s
         rxm::K1Launch a{m->d_k1_table, m->d_k1_accept, d_chars, spans, n, d_out, m->d_recs,
                         m->d_k1_counter, m->d_overflow, m->sm_count, stream};
         st = rxm::k1_launch(m->k1, a, &launched);
+    } else if (m->info.engine == RXM_ENGINE_K1_BITSET) {
+        st = rxm::k1b_launch(m->d_edge_begin, m->d_k1b_edges, m->tables.n_states(), m->tables.n_edges(),
+                             m->tables.start, m->tables.finish, m->tables.reversed, d_chars, spans, n, d_out,
+                             m->d_overflow, m->d_overflow + 1, m->sm_count, stream, &launched);
     } else if (m->info.engine == RXM_ENGINE_K3_WARP) {
         rxm::MfaView v{m->d_edge_begin, m->d_edges, m->tables.n_states(), m->tables.start,
                        m->tables.finish, m->tables.reversed};

@@ -1,0 +1,94 @@
+// K1B -- memory-free automaton as a bit set, sm_100a.
+// Replaces Automata::match (automata.cpp:177-210) for automata whose determinisation under the
+// reference's exact step is too large for K1's table (rxm_plan.cpp: kMaxDfaStates).  One thread
+// per string; the active set std::set<Node*> is a 128-bit mask (bit = address rank, so ascending
+// bits == set order, automata.cpp:122), `visited` and the next set are masks too, and
+// Automata::evaluateState's recursion through epsilon edges (automata.cpp:108-110) is an explicit
+// stack of (node, next edge).  The step is the reference's, quirk included: an edge -- letter
+// edges too -- whose target was already evaluated in this step is skipped (automata.cpp:104-107),
+// and a node is marked evaluated only after its edge loop (automata.cpp:116).
+// Bound: instruction issue (a handful of edge visits per input byte); this is the fallback
+// engine, the table scan K1 is the fast one.
+#include "rxm_kernels.cuh"
+#include "rxm_nfa_core.cuh"
+
+namespace rxm {
+
+namespace {
+
+constexpr int K1B_THREADS = 128;
+static_assert(kNfaBitsDepth == int(kBitsetMaxDepth), "planner limit == kernel stack");
+
+__global__ void __launch_bounds__(K1B_THREADS)
+k1b_bitset_kernel(const uint16_t *__restrict__ g_eb, const uint32_t *__restrict__ g_ed, uint32_t n_states,
+                  uint32_t n_edges, uint32_t start, uint32_t finish, uint32_t reversed,
+                  const uint8_t *__restrict__ chars, const Spans sp, uint64_t n, uint8_t *__restrict__ out,
+                  unsigned long long *__restrict__ overflow, unsigned long long *__restrict__ next_string) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t *ed = reinterpret_cast<uint32_t *>(smem);
+    uint16_t *eb = reinterpret_cast<uint16_t *>(smem + size_t(n_edges) * 4);
+    for (uint32_t i = threadIdx.x; i < n_edges; i += blockDim.x) ed[i] = g_ed[i];
+    for (uint32_t i = threadIdx.x; i <= n_states; i += blockDim.x) eb[i] = g_eb[i];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(next_string, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint64_t i = base + lane;
+        if (i >= n) continue;
+        const uint64_t b = sp.begin[i], e = sp.end[i];
+        bool ok = e - b < 0x7fffffffull;
+        Bits128 S{0, 0}, N;
+        S.set(start);  // automata.cpp:178-179
+        const uint8_t *s = chars + b;
+        const uint32_t len = ok ? uint32_t(e - b) : 0u;
+        for (uint32_t k = 0; k < len && ok; k++) {  // :181-200
+            const int letter = reversed ? s[len - 1u - k] : s[k];
+            ok = nfa_bits_step(eb, ed, finish, S, letter, N);
+            S = N;
+            if (S.empty()) break;  // :186-188
+        }
+        if (ok) ok = nfa_bits_step(eb, ed, finish, S, -1, N);  // :201-202
+        if (!ok) {
+            atomicAdd(overflow, 1ull);
+            out[i] = 0;
+        } else {
+            out[i] = N.test(finish) ? 1 : 0;  // :204-209
+        }
+    }
+}
+
+}  // namespace
+
+void k1b_build_tables(const rxm_tables &t, std::vector<uint16_t> &eb, std::vector<uint32_t> &ed) {
+    eb.resize(t.n_states + 1);
+    ed.resize(t.n_edges);
+    for (uint32_t q = 0; q <= t.n_states; q++) eb[q] = uint16_t(t.edge_begin[q]);
+    for (uint32_t e = 0; e < t.n_edges; e++) ed[e] = nfa_pack_edge(t.edge_kind[e], t.edge_sym[e], t.edge_to[e]);
+}
+
+int k1b_launch(const uint16_t *d_eb, const uint32_t *d_ed, uint32_t n_states, uint32_t n_edges, uint32_t start,
+               uint32_t finish, uint32_t reversed, const uint8_t *d_chars, Spans spans, uint64_t n, uint8_t *d_out,
+               unsigned long long *d_overflow, unsigned long long *d_next, int sm_count, cudaStream_t stream,
+               int *launched) {
+    *launched = 0;
+    const size_t smem = ((size_t(n_edges) * 4 + (size_t(n_states) + 1) * 2) + 15) & ~size_t(15);
+    if (smem > 96 * 1024) return RXM_ERR_UNSUPPORTED;
+    if (cudaFuncSetAttribute(k1b_bitset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+        return RXM_ERR_CUDA;
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k1b_bitset_kernel, K1B_THREADS, smem) != cudaSuccess || nb <= 0)
+        return RXM_ERR_CUDA;
+    uint64_t blocks = uint64_t(sm_count) * nb;
+    const uint64_t need = (n + K1B_THREADS - 1) / K1B_THREADS;
+    if (blocks > need) blocks = need;
+    if (cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), stream) != cudaSuccess) return RXM_ERR_CUDA;
+    k1b_bitset_kernel<<<unsigned(blocks), K1B_THREADS, smem, stream>>>(d_eb, d_ed, n_states, n_edges, start, finish, reversed,
+                                                                       d_chars, spans, n, d_out, d_overflow, d_next);
+    *launched = 1;
+    return RXM_OK;
+}
+
+}  // namespace rxm

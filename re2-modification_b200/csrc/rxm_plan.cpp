@@ -277,6 +277,40 @@ int compile_programs(const rxm_tables &t, MfaProgram &out, std::string *err) {
     return RXM_OK;
 }
 
+int check_nfa_bitset(const rxm_tables &t, std::string *err) {
+    if (t.n_states > kBitsetMaxStates) {
+        if (err) *err = "memory-free automaton with more than " + std::to_string(kBitsetMaxStates) + " states";
+        return RXM_ERR_UNSUPPORTED;
+    }
+    // longest chain of epsilon edges (Automata::evaluateState recursion depth, automata.cpp:108-110)
+    std::vector<int> depth(t.n_states, -1);  // -1 unknown, -2 in progress
+    bool cyc = false;
+    std::function<int(uint32_t)> dfs = [&](uint32_t q) -> int {
+        if (depth[q] == -2) {
+            cyc = true;
+            return 0;
+        }
+        if (depth[q] >= 0) return depth[q];
+        depth[q] = -2;
+        int d = 0;
+        for (uint32_t e = t.edge_begin[q]; e < t.edge_begin[q + 1] && !cyc; e++)
+            if (t.edge_kind[e] == RXM_EDGE_EPS) d = std::max(d, 1 + dfs(t.edge_to[e]));
+        depth[q] = d;
+        return d;
+    };
+    int longest = 0;
+    for (uint32_t q = 0; q < t.n_states && !cyc; q++) longest = std::max(longest, dfs(q));
+    if (cyc) {
+        if (err) *err = "epsilon cycle: the reference's evaluateState recurses without bound";
+        return RXM_ERR_UNSUPPORTED;
+    }
+    if (uint32_t(longest) + 1 > kBitsetMaxDepth) {
+        if (err) *err = "epsilon chain longer than " + std::to_string(kBitsetMaxDepth) + " edges";
+        return RXM_ERR_UNSUPPORTED;
+    }
+    return RXM_OK;
+}
+
 int check_mfa(const rxm_tables &t, std::string *err) {
     // epsilon-only cycles make MFA::evaluateState (mfa.cpp:143-147) recurse forever
     std::vector<uint8_t> color(t.n_states, 0);

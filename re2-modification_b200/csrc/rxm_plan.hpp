@@ -62,6 +62,14 @@ struct MfaProgram {
 // RXM_OK, or RXM_ERR_UNSUPPORTED (more than kProgMaxCells cells, program too large).
 int compile_programs(const rxm_tables &t, MfaProgram &out, std::string *err);
 
+// Memory-free automaton simulated as a bit set ("K1_BITSET", rxm_k1b.cu): used when the exact-
+// step determinisation above exceeds kMaxDfaStates.  Limits: kBitsetMaxStates states, no
+// epsilon cycle (the reference overflows its stack there), epsilon chains of at most
+// kBitsetMaxDepth edges (the kernel's explicit recursion stack).
+constexpr uint32_t kBitsetMaxStates = 128;
+constexpr uint32_t kBitsetMaxDepth = 48;
+int check_nfa_bitset(const rxm_tables &t, std::string *err);
+
 // Static checks for an MFA table (epsilon cycles, sizes).  RXM_OK or RXM_ERR_UNSUPPORTED.
 int check_mfa(const rxm_tables &t, std::string *err);
 

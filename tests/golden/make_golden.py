@@ -44,6 +44,10 @@ NFA_EXPRESSIONS = [
     ("abba", "(ab|ba)*", ["abba", "abab", "aba"]),
     ("third", "(a|b)*a(a|b)(a|b)", ["abb", "aaa", "bab"]),
     ("lit", "abcabc", ["abcabc", "abcab", "abcabcc"]),
+    # an `a`, twelve letters, a `b`: 2^14 active sets in either reading direction -> beyond the
+    # table engine's limit, runs on the bit-set engine (K1B); Thompson branch, 77 nodes
+    ("blowup", "(a|b)*a" + "(a|b)" * 12 + "b(a|b)*",
+     ["a" + "a" * 12 + "b", "b" * 30, "ab" * 20, "a" * 13 + "b", "a" * 12 + "b", "ba" + "b" * 12 + "ba"]),
 ]
 
 
@@ -174,20 +178,32 @@ def write_case(name: str, regex: str, flags: list[str], strings: list[bytes]) ->
 
 
 def main():
+    only = set(sys.argv[1:])  # optional: case names to (re)generate; the others keep their files
     if not H.have_reference():
         raise SystemExit("needs oracle/_ref (make -C oracle) and bin/rxm_compile "
                          "(make -C re2-modification_b200 front)")
     os.makedirs(CASES_DIR, exist_ok=True)
     manifest = []
+    old = {}
+    if only and os.path.exists(os.path.join(HERE, "manifest.json")):
+        old = {m["name"]: m for m in json.load(open(os.path.join(HERE, "manifest.json")))}
     for i in range(1, 18):
         regex = open(f"{REF}/test/example_{i}/regexp.txt").readline().strip()
         for flags in ([], ["-reverse"]):
             rng = random.Random(1000 * i + len(flags))
             name = f"ex{i:02d}" + ("_rev" if flags else "_fwd")
+            if only and name not in only:
+                if name in old:
+                    manifest.append(old[name])
+                continue
             m = write_case(name, regex, flags, strings_for_example(i, regex, rng))
             manifest.append(m)
             print(m)
     for name, regex, extra in NFA_EXPRESSIONS:
+        if only and "nfa_" + name not in only:
+            if "nfa_" + name in old:
+                manifest.append(old["nfa_" + name])
+            continue
         strings = strings_for_nfa(regex, random.Random(len(name) * 7919)) + [x.encode() for x in extra]
         m = write_case("nfa_" + name, regex, [], strings)
         manifest.append(m)

@@ -9,6 +9,7 @@
 #include "../../include/rxm.h"
 #include "../../re2-modification_b200/csrc/rxm_mfa_core.cuh"
 #include "../../re2-modification_b200/csrc/rxm_mfa_dispatch.hpp"
+#include "../../re2-modification_b200/csrc/rxm_nfa_core.cuh"
 #include "../../re2-modification_b200/csrc/rxm_plan.hpp"
 
 static uint64_t g_steps_run = 0, g_steps_skipped = 0;
@@ -107,6 +108,35 @@ extern "C" int hostsim_dfa_batch(const rxm_tables *t, const uint8_t *chars, cons
             q = p.trans[size_t(p.byte_class[b]) * p.n_states + q];
         }
         out[i] = p.accept[q];
+    }
+    return 0;
+}
+
+// The K1B step (rxm_nfa_core.cuh) on the host: returns 0, the planner's status if the bit-set
+// engine's static checks reject the table, or 2 if a string overflowed the recursion stack.
+extern "C" int hostsim_nfa_bits_batch(const rxm_tables *t, const uint8_t *chars, const uint64_t *off,
+                                      uint64_t n, uint8_t *out) {
+    std::string err;
+    int st = rxm::check_nfa_bitset(*t, &err);
+    if (st != RXM_OK) return st;
+    std::vector<uint16_t> eb(t->n_states + 1);
+    std::vector<uint32_t> ed(t->n_edges);
+    for (uint32_t q = 0; q <= t->n_states; q++) eb[q] = uint16_t(t->edge_begin[q]);
+    for (uint32_t e = 0; e < t->n_edges; e++) ed[e] = rxm::nfa_pack_edge(t->edge_kind[e], t->edge_sym[e], t->edge_to[e]);
+    for (uint64_t i = 0; i < n; i++) {
+        const uint8_t *s = chars + off[i];
+        const uint32_t len = uint32_t(off[i + 1] - off[i]);
+        rxm::Bits128 S{0, 0}, N{0, 0};
+        S.set(t->start);
+        bool ok = true;
+        for (uint32_t k = 0; k < len && ok; k++) {
+            ok = rxm::nfa_bits_step(eb.data(), ed.data(), t->finish, S, t->reversed ? s[len - 1 - k] : s[k], N);
+            S = N;
+            if (S.empty()) break;
+        }
+        if (ok) ok = rxm::nfa_bits_step(eb.data(), ed.data(), t->finish, S, -1, N);
+        if (!ok) return 2;
+        out[i] = N.test(t->finish) ? 1 : 0;
     }
     return 0;
 }

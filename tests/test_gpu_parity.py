@@ -242,6 +242,41 @@ def test_k1_quad_stride_and_bytes_outside_the_window(name, monkeypatch):
         assert stride == 4
 
 
+@pytest.mark.parametrize("name", [n for n in CASE_NAMES if BY_NAME[n]["kind"] == "nfa"])
+def test_bitset_engine_on_every_memory_free_fixture(name, monkeypatch):
+    """K1B (the active set as a 128-bit mask, the reference's exact step per letter): forced on
+    every memory-free fixture, golden bits + random batches against the oracle; forward,
+    right-to-left, Thompson, the visited quirk."""
+    monkeypatch.setenv("RXM_NFA_ENGINE", "bitset")
+    t, strings, bits = load_case(name)
+    m = rxm.Matcher(t, 0)
+    assert rxm.ENGINE_NAMES[m.plan().engine] == "K1_BITSET"
+    chars, off = H.make_batch(strings)
+    assert np.array_equal(m.match_host(chars, off), bits)
+    rng = np.random.default_rng(17)
+    for (n, lo, hi, alpha) in ((3000, 0, 40, b"ab"), (500, 1, 300, b"ab"), (300, 1, 60, b"abcd.")):
+        chars, off = _random_batch(rng, n, lo, hi, alpha)
+        assert np.array_equal(m.match_host(chars, off), H.oracle_bits(t, chars, off))
+    assert m.overflow_count() == 0
+    m.close()
+
+
+def test_planner_hands_large_determinisations_to_the_bitset_engine():
+    """nfa_blowup has 2^14 reachable active sets: no table, K1B instead of RXM_ERR_UNSUPPORTED;
+    long strings that stay alive, raw-text route included."""
+    t, strings, bits = load_case("nfa_blowup")
+    m = rxm.Matcher(t, 0)
+    assert rxm.ENGINE_NAMES[m.plan().engine] == "K1_BITSET"
+    rng = np.random.default_rng(4)
+    ab = np.frombuffer(b"ab", dtype=np.uint8)
+    long_strings = [bytes(rng.choice(ab, size=int(L))) for L in rng.integers(1000, 6000, size=64)]
+    chars, off = H.make_batch(long_strings)
+    want = H.oracle_bits(t, chars, off)
+    assert np.array_equal(m.match_host(chars, off), want)
+    assert np.array_equal(m.match_text_host(b"\n".join(long_strings)), want)
+    m.close()
+
+
 def test_k1_large_batch_properties():
     """BASELINE-sized property checks (no oracle at this size): the result vector is a
     pure function of each string -- a permuted batch gives the permuted bits, and a batch
