@@ -83,9 +83,9 @@ struct rxm_matcher {
     // tokeniser workspace (rxm_match_text)
     uint64_t *d_tok_begin = nullptr, *d_tok_end = nullptr;
     size_t cap_tok = 0;
-    uint64_t *d_tok_status = nullptr;
-    size_t cap_tok_status = 0;
-    uint32_t *d_tok_ticket = nullptr;          // [1] ticket, then 2 x u64 result (16-byte aligned)
+    uint64_t *d_tok_masks = nullptr, *d_tok_counts = nullptr;
+    size_t cap_tok_blocks = 0;
+    unsigned long long *d_tok_result = nullptr;  // [2] token count, index of the first `exit`
 
     unsigned long long *d_overflow = nullptr;  // strings that hit a kernel limit
     uint64_t launches = 0;
@@ -248,8 +248,9 @@ extern "C" int rxm_free(rxm_handle h) {
     cudaFree(h->d_k1_counter);
     cudaFree(h->d_tok_begin);
     cudaFree(h->d_tok_end);
-    cudaFree(h->d_tok_status);
-    cudaFree(h->d_tok_ticket);
+    cudaFree(h->d_tok_masks);
+    cudaFree(h->d_tok_counts);
+    cudaFree(h->d_tok_result);
     delete h;
     return RXM_OK;
 }
@@ -420,18 +421,19 @@ extern "C" int rxm_match_text(rxm_handle h, const uint8_t *text, uint64_t nbytes
         CU(cudaMalloc(reinterpret_cast<void **>(&m->d_tok_end), want * sizeof(uint64_t)));
         m->cap_tok = want;
     }
-    const uint64_t words = rxm::tok_status_words(nbytes);
-    if (words > m->cap_tok_status) {
-        cudaFree(m->d_tok_status);
-        m->d_tok_status = nullptr;
-        m->cap_tok_status = 0;
-        const size_t want = size_t(words + (words >> 2) + 16);
-        CU(cudaMalloc(reinterpret_cast<void **>(&m->d_tok_status), want * sizeof(uint64_t)));
-        m->cap_tok_status = want;
+    const uint64_t blocks = rxm::tok_blocks(nbytes);
+    if (blocks > m->cap_tok_blocks) {
+        cudaFree(m->d_tok_masks);
+        cudaFree(m->d_tok_counts);
+        m->d_tok_masks = m->d_tok_counts = nullptr;
+        m->cap_tok_blocks = 0;
+        const size_t want = size_t(blocks + (blocks >> 2) + 16);
+        CU(cudaMalloc(reinterpret_cast<void **>(&m->d_tok_masks), want * 256 * sizeof(uint64_t)));
+        CU(cudaMalloc(reinterpret_cast<void **>(&m->d_tok_counts), want * sizeof(uint64_t)));
+        m->cap_tok_blocks = want;
     }
-    if (!m->d_tok_ticket) CU(cudaMalloc(reinterpret_cast<void **>(&m->d_tok_ticket), 64));
-    rxm::TokWork w{m->d_tok_status, m->cap_tok_status, m->d_tok_ticket,
-                   reinterpret_cast<unsigned long long *>(m->d_tok_ticket + 4)};
+    if (!m->d_tok_result) CU(cudaMalloc(reinterpret_cast<void **>(&m->d_tok_result), 64));
+    rxm::TokWork w{m->d_tok_masks, m->d_tok_counts, m->cap_tok_blocks, m->d_tok_result};
     int launched = 0;
     int st = rxm::tok_launch(d_text, nbytes, m->d_tok_begin, m->d_tok_end, out_cap, w, m->sm_count, stream, &launched);
     m->launches += uint64_t(launched);

@@ -229,7 +229,7 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
                         const uint32_t pkey = (q << gp.n_cells) | exists_mask_n<NC>(fl);
                         pb = s_begin[pkey];
                         if (pb == 0xffffffffu) ovf = true;  // a (node, cells) pair the host analysis missed
-                        else pc = s_count[pkey];
+                        else pc = s_count[pkey] & kProgCountMask;
                     }
                 }
                 const uint32_t bal = (__ballot_sync(FULL, lv) >> tshift) & ((TILE == 32) ? 0xffffffffu : ((1u << TILE) - 1u));
@@ -256,6 +256,7 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
             __syncwarp(FULL);
             const uint32_t ch = (i < n32) ? uint32_t(v.reversed ? s[n32 - 1u - i] : s[i]) : 0u;
             const uint32_t digit_bit = (i < n32 && ch >= '1' && ch <= '9') ? (1u << (ch - '1')) : 0u;
+            bool next_near = false;  // the new set holds a configuration that is active (or dead) at step i+1
             // ---- B. expand: one item per lane per pass ----
             for (uint32_t t0 = 0; t0 < T; t0 += TILE) {
                 const uint32_t tt = t0 + lane;
@@ -347,6 +348,7 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
                 // claim the target slot: smallest order key wins
                 uint64_t k64 = 0;
                 if (have) {
+                    if (cand.first < i + 2u) next_near = true;  // its node will hold a configuration with first <= i+1
                     k64 = k3_key(cand.first, cand.flags, cand.born);
                     atomicMin(reinterpret_cast<unsigned long long *>(&KN[cand.node]), (unsigned long long)k64);
                 }
@@ -364,10 +366,38 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
             }
             cur ^= 1u;  // states = new_states (:212)
             __syncwarp(FULL);
+            bool jumped = false;
             if (ovf || i == n32) finished = true;
+            // ---- C0. every configuration of the new set waits (first >= i + 2) and is reproduced
+            //          unchanged by a step (kProgStable): the steps up to the first activation /
+            //          reversed-mode pruning are the identity and are not run at all ----
+            else if (i + 2 < n32 && !__any_sync(FULL, next_near)) {
+                bool stable = true, any = false;
+                uint32_t ev = n32;
+                for (uint32_t q = lane; q < SP; q += TILE) {
+                    const uint64_t ka = keys[cur * SP + q];
+                    if (ka == K3_EMPTY) continue;
+                    any = true;
+                    const uint32_t fa = uint32_t(ka >> 36), sa = cur * SP + q, fla = flg[sa];
+                    const uint32_t pkey = (q << gp.n_cells) | exists_mask_n<NC>(fla);
+                    if (fa < i + 2 || fa == n32 || s_begin[pkey] == 0xffffffffu || !(s_count[pkey] & kProgStable)) stable = false;
+                    if (fa < ev) ev = fa;
+                    if (v.reversed) {
+                        const uint32_t need = k3_need<NC>(fla, lnn + sa * NC);  // fresh: not yet tested against mfa.cpp:141
+                        const uint32_t ps = need > n32 ? 0u : n32 - need + 1u;
+                        if (ps < ev) ev = ps;
+                    }
+                }
+                stable = __all_sync(FULL, stable) && __any_sync(FULL, any);
+                ev = __reduce_min_sync(FULL, ev);
+                if (stable && ev > i + 1) {
+                    i = ev - 1;  // the increment below makes the next step ev
+                    jumped = true;
+                }
+            }
             // ---- C. fast-forward over idle steps (see MfaSim::run); only after a step in which
             //         no configuration was active ----
-            else if (!any_active && i + 1 < n32) {
+            if (!finished && !jumped && !any_active && i + 1 < n32) {
                 bool same = true;
                 uint32_t ev = n32;
                 for (uint32_t q = lane; q < SP; q += TILE) {

@@ -94,12 +94,12 @@ int k3_launch(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n
 // d_result[0..1], the number of tokens found and the index of the first token equal to
 // "exit" (the sentinel of match.cpp:24; the token count if there is none).
 struct TokWork {
-    uint64_t *d_status;      // [blocks] look-back words
-    uint64_t status_cap;     // in words
-    uint32_t *d_ticket;      // [1]
+    uint64_t *d_masks;       // [blocks * 256] one whitespace bit per input position
+    uint64_t *d_counts;      // [blocks] per-block (starts << 32 | ends), then their exclusive prefix
+    uint64_t blocks_cap;     // capacity of both, in blocks
     unsigned long long *d_result;  // [2]
 };
-uint64_t tok_status_words(uint64_t nbytes);
+uint64_t tok_blocks(uint64_t nbytes);  // 16 KB pieces a text of nbytes needs
 int tok_launch(const uint8_t *d_text, uint64_t nbytes, uint64_t *d_begin, uint64_t *d_end, uint64_t cap,
                const TokWork &w, int sm_count, cudaStream_t stream, int *launched);
 

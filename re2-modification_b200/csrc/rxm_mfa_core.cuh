@@ -459,6 +459,14 @@ RXM_UNROLL
 // Hence (0 for (a)) or 1 + (ENTER? 1:0) << 19 | source node << 12 | item index orders exactly
 // like the reference's allocation order wherever that order is consulted, and the sources
 // of a step can be expanded in ANY order (K3 expands them all at once).
+// ProgView::count[key] carries the item count in its low bits and this flag: a WAITING
+// configuration (first > step) with this (node, cells) key is reproduced unchanged by a step --
+// its program re-inserts it (the root ENTER has a leaf, mfa.cpp:195-197) and no epsilon /
+// absent-cell path below it reaches another node that has a leaf.  When every configuration of a
+// set is such, the steps up to the next event are the identity and need not be run at all.
+constexpr uint32_t kProgStable = 1u << 30;
+constexpr uint32_t kProgCountMask = kProgStable - 1u;
+
 RXM_HD uint32_t prog_stamp(bool is_enter, uint32_t src_node, uint32_t item) {
     return 1u + ((is_enter ? 1u : 0u) << 19) + (src_node << 12) + item;
 }
@@ -509,7 +517,7 @@ RXM_UNROLL
             overflow = true;
             return;
         }
-        const uint32_t cntp = pv.count[key];
+        const uint32_t cntp = pv.count[key] & kProgCountMask;
         const bool active = (i != n && i == root.first);
         const bool waiting = (i != n && i < root.first);
         const uint32_t ch = active ? rd.at(i) : 0u;
@@ -597,7 +605,35 @@ RXM_UNROLL
             const cfg_t *now = buf[nb ^ 1u];
             const cfg_t *prev = buf[nb];
             const uint32_t m = cnt[nb ^ 1u];
-            if (m == 0 || m != cnt[nb] || i + 1 >= n) continue;
+            if (m == 0 || i + 1 >= n) continue;
+            {   // every configuration waiting and stable (kProgStable): the coming steps are the
+                // identity until the first activation / reversed-mode pruning -- skip them unrun
+                bool stable = true;
+                uint32_t evs = n;
+                for (uint32_t j = 0; j < m && stable; j++) {
+                    const cfg_t &c = now[j];
+                    if (c.first < i + 2 || c.first == n) stable = false;
+                    const uint32_t key = (c.node << pv.n_cells) | (exists_mask(c.flags) & ((1u << pv.n_cells) - 1u));
+                    if (pv.begin[key] == 0xffffffffu || !(pv.count[key] & kProgStable)) stable = false;
+                    if (c.first < evs) evs = c.first;
+                    if (t.reversed) {
+                        uint32_t need = 0;
+RXM_UNROLL
+                        for (int k = 0; k < NC; k++) {
+                            const uint32_t fl = (c.flags >> (3 * k)) & 7u;
+                            if ((fl & 1u) && ((fl & 2u) || !(fl & 4u))) need += c.len[k];
+                        }
+                        const uint32_t ps = need > n ? 0u : n - need + 1;  // fresh configurations: not yet tested against mfa.cpp:141
+                        if (ps < evs) evs = ps;
+                    }
+                }
+                if (stable && evs > i + 1) {
+                    steps_skipped += evs - 1 - i;
+                    i = evs - 1;
+                    continue;
+                }
+            }
+            if (m != cnt[nb]) continue;
             uint32_t ev = n;
             bool idle = true;
             for (uint32_t j = 0; j < m && idle; j++) {

@@ -269,6 +269,10 @@ int compile_programs(const rxm_tables &t, MfaProgram &out, std::string *err) {
         }
         out.count[key] = uint32_t(out.items.size() - g.root_start);
         out.max_count = std::max(out.max_count, out.count[key]);
+        bool stable = (out.items[g.root_start].a & 4u) != 0;  // the root call has a leaf: re-inserted while waiting
+        for (size_t x = g.root_start + 1; x < out.items.size() && stable; x++)
+            if (!(out.items[x].a & 1u) && (out.items[x].a & 4u)) stable = false;  // a deeper call with a leaf
+        if (stable) out.count[key] |= kProgStable;
         for (const auto &f : g.found) {
             const size_t k2 = (size_t(f.first) << t.n_cells) | (f.second & (nm - 1));
             if (out.begin[k2] == 0xffffffffu) work.push_back(f);

@@ -6,12 +6,16 @@
 // text goes to HBM as it is and this pass finds the tokens there: ONE read of the text, 16
 // bytes written per token.  Bound: HBM.
 //
-// One pass, chained scan: a block takes the next 16 KB piece (atomic ticket, so earlier
-// pieces are always running), every thread classifies its 64 bytes into a 64-bit whitespace
-// mask (byte-parallel range tests, no per-byte loop), derives the token-start and token-end
-// bits from the mask and the previous position, the block publishes its (starts, ends) counts
-// in one 64-bit status word and looks back for its prefix (decoupled look-back, warp-wide),
-// and the threads write begin[rank] / end[rank] straight from their mask registers.
+// Three kernels, no inter-block dependency (a one-pass chained scan was measured first: with
+// ~1200 resident 16 KB pieces the decoupled look-back window never closes and 7 of 8 warps sit at
+// the barrier -- 1.9 TB/s; ncu: barrier stall 22.8 per issue):
+//   tok_classify  one coalesced read of the text; every 16-byte vector becomes a 16-bit
+//                 whitespace mask (byte-parallel range tests, no per-byte loop); the block
+//                 writes its masks (1 bit per input byte) and its (token starts, token ends) counts
+//   tok_offsets   exclusive scan of the per-block counts (one block; 8 bytes per 16 KB of text)
+//   tok_emit      reads the MASKS only (1/8 of the text), recomputes start / end bits and writes
+//                 begin[rank] / end[rank]
+// HBM traffic: text x 1.25 + 16 bytes per token.
 #include "rxm_kernels.cuh"
 
 namespace rxm {
@@ -21,10 +25,6 @@ namespace {
 constexpr int TOK_THREADS = 256;
 constexpr int TOK_BPT = 64;  // bytes per thread
 constexpr uint64_t TOK_BLOCK_BYTES = uint64_t(TOK_THREADS) * TOK_BPT;
-
-// status word: flag:2 | starts:31 | ends:31
-constexpr uint64_t TOK_AGG = 1ull << 62, TOK_INC = 2ull << 62, TOK_FLAGS = 3ull << 62;
-__device__ __forceinline__ uint64_t tok_pack(uint64_t flag, uint64_t s, uint64_t e) { return flag | (s << 31) | e; }
 
 // bit 7 of every byte of the result: that byte of x is C-locale whitespace (9..13 or 32)
 __device__ __forceinline__ uint32_t ws_bits(uint32_t x) {
@@ -38,66 +38,17 @@ __device__ __forceinline__ uint32_t ws_bits(uint32_t x) {
 // the four bit-7 flags of a word gathered into bits 0..3
 __device__ __forceinline__ uint32_t gather4(uint32_t b7) { return (((b7 >> 7) * 0x00204081u) >> 21) & 0xfu; }
 
-__device__ __forceinline__ uint64_t ld_status(const uint64_t *p) {
-    uint64_t v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ void st_status(uint64_t *p, uint64_t v) {
-    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-// text0 = text rounded down to 16 bytes, pad = text - text0 (positions < pad are virtual
-// whitespace); n0 = pad + nbytes.  Position n0 is virtual whitespace too, so that a token that
-// runs to the last byte still gets its end.
-__global__ void __launch_bounds__(TOK_THREADS)
-tok_scan_kernel(const uint8_t *__restrict__ text0, uint32_t pad, uint64_t n0, uint64_t *__restrict__ begin,
-                uint64_t *__restrict__ end, uint64_t cap, uint64_t *__restrict__ status,
-                uint32_t *__restrict__ ticket, unsigned long long *__restrict__ result, uint32_t nblocks) {
-    __shared__ uint32_t s_bid;
-    __shared__ uint32_t s_warp[TOK_THREADS / 32];
-    __shared__ uint64_t s_prefix;
-    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
-    if (t == 0) s_bid = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint32_t bid = s_bid;
-    if (bid >= nblocks) return;
-    const uint64_t base = uint64_t(bid) * TOK_BLOCK_BYTES + uint64_t(t) * TOK_BPT;
-
-    // ---- classify: 64-bit whitespace mask of positions base .. base+63 ----
-    uint64_t m = ~0ull;
-    if (base < n0) {
-        m = 0;
-        const uint4 *src = reinterpret_cast<const uint4 *>(text0 + base);
-#pragma unroll
-        for (int k = 0; k < TOK_BPT / 16; k++) {
-            uint32_t nib = 0xffffu;
-            if (base + uint64_t(k) * 16 < n0) {  // the last vector may run past n0 inside its 16-byte block
-                const uint4 v = __ldg(src + k);
-                nib = gather4(ws_bits(v.x)) | (gather4(ws_bits(v.y)) << 4) | (gather4(ws_bits(v.z)) << 8) |
-                      (gather4(ws_bits(v.w)) << 12);
-            }
-            m |= uint64_t(nib) << (16 * k);
-        }
-        if (base < pad) m |= (pad - base >= 64) ? ~0ull : ((1ull << (pad - base)) - 1ull);
-        if (n0 - base < 64) m |= ~0ull << (n0 - base);
-    }
-    // whitespace flag of position base-1: the previous thread's top bit
-    uint32_t prev = uint32_t(__shfl_up_sync(0xffffffffu, uint32_t(m >> 63), 1));
-    if (lane == 0) {
-        prev = 1u;
-        if (base != 0 && base - 1 < n0 && base - 1 >= pad) {
-            const uint32_t b = text0[base - 1];
-            prev = (b == 32u || (b - 9u) <= 4u) ? 1u : 0u;
-        }
-    }
+// (starts, ends) of one thread's 64 positions from its whitespace mask and the flag of the position before
+__device__ __forceinline__ void tok_edges(uint64_t m, uint32_t prev, uint64_t &starts, uint64_t &ends) {
     const uint64_t pm = (m << 1) | prev;
-    const uint64_t starts = ~m & pm;  // token begins here
-    const uint64_t ends = m & ~pm;    // token ended just before here (exclusive end)
-    const uint32_t cs = uint32_t(__popcll(starts)), ce = uint32_t(__popcll(ends));
+    starts = ~m & pm;  // a token begins here
+    ends = m & ~pm;    // a token ended just before here (exclusive end)
+}
 
-    // ---- block scan of (cs, ce), packed 16:16 (a block holds < 2^14 of either) ----
-    uint32_t inc = (cs << 16) | ce;
+// block-wide exclusive scan of a packed (starts << 16 | ends) count; returns the block total in *total
+__device__ __forceinline__ uint32_t tok_block_scan(uint32_t mine, uint32_t *s_warp, uint32_t *total) {
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    uint32_t inc = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
@@ -112,47 +63,114 @@ tok_scan_kernel(const uint8_t *__restrict__ text0, uint32_t pad, uint64_t n0, ui
         if (w < int(warp)) woff += x;
         btot += x;
     }
-    const uint32_t ex = inc - ((cs << 16) | ce) + woff;  // exclusive, inside the block
+    *total = btot;
+    return inc - mine + woff;
+}
 
-    // ---- chained scan over blocks: publish the aggregate, look back for the prefix ----
-    if (warp == 0) {
-        const uint64_t bs = btot >> 16, be = btot & 0xffffu;
-        if (lane == 0) st_status(status + bid, tok_pack(bid == 0 ? TOK_INC : TOK_AGG, bs, be));
-        uint64_t ps = 0, pe = 0;
-        if (bid != 0) {
-            int64_t j = int64_t(bid) - 1;
-            for (;;) {
-                const int64_t mine = j - int64_t(lane);
-                uint64_t w = TOK_INC;  // blocks before the first: an empty inclusive prefix
-                if (mine >= 0) {
-                    do w = ld_status(status + mine);
-                    while ((w & TOK_FLAGS) == 0);
-                }
-                const uint32_t incl = __ballot_sync(0xffffffffu, (w & TOK_FLAGS) == TOK_INC);
-                const int stop = incl ? __ffs(int(incl)) - 1 : 32;  // nearest block with an inclusive prefix
-                uint64_t s = (int(lane) <= stop) ? ((w >> 31) & 0x7fffffffull) : 0ull;
-                uint64_t e = (int(lane) <= stop) ? (w & 0x7fffffffull) : 0ull;
+// text0 = text rounded down to 16 bytes, pad = text - text0 (positions < pad are virtual
+// whitespace); n0 = pad + nbytes.  Position n0 and everything after it is virtual whitespace
+// too, so that a token that runs to the last byte still gets its end.  masks[] holds one bit per
+// position (whitespace = 1) with those corrections applied.
+__global__ void __launch_bounds__(TOK_THREADS)
+tok_classify_kernel(const uint8_t *__restrict__ text0, uint32_t pad, uint64_t n0, uint64_t *__restrict__ masks,
+                    uint64_t *__restrict__ counts) {
+    __shared__ __align__(8) uint16_t s_mask[TOK_THREADS * TOK_BPT / 16];  // one 16-bit mask per 16-byte vector
+    __shared__ uint32_t s_warp[TOK_THREADS / 32];
+    const uint32_t t = threadIdx.x, lane = t & 31u, bid = blockIdx.x;
+    const uint64_t blk0 = uint64_t(bid) * TOK_BLOCK_BYTES, base = blk0 + uint64_t(t) * TOK_BPT;
+    uint32_t prev_blk = 1u;  // whitespace flag of the byte before the block
+    if (t == 0 && blk0 != 0 && blk0 - 1 < n0 && blk0 - 1 >= pad) {
+        const uint32_t pb = text0[blk0 - 1];
+        prev_blk = (pb == 32u || (pb - 9u) <= 4u) ? 1u : 0u;
+    }
+    {   // fully coalesced: thread t takes vectors t, t+256, ...
+        const uint4 *src = reinterpret_cast<const uint4 *>(text0 + blk0);
+        uint4 v[TOK_BPT / 16];
 #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) {
-                    s += __shfl_xor_sync(0xffffffffu, s, d);
-                    e += __shfl_xor_sync(0xffffffffu, e, d);
-                }
-                ps += s;
-                pe += e;
-                if (incl) break;
-                j -= 32;
-            }
-            if (lane == 0) st_status(status + bid, tok_pack(TOK_INC, ps + bs, pe + be));
+        for (int k = 0; k < TOK_BPT / 16; k++) {
+            const uint64_t vo = blk0 + (uint64_t(k) * TOK_THREADS + t) * 16;
+            v[k] = make_uint4(0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u);  // past the end: whitespace
+            if (vo < n0) v[k] = __ldg(src + k * TOK_THREADS + t);  // the last vector may run past n0 inside its 16-byte block
         }
-        if (lane == 0) {
-            s_prefix = (ps << 32) | pe;
-            if (bid == nblocks - 1) result[0] = ps + bs;  // tokens in the whole text
-        }
+#pragma unroll
+        for (int k = 0; k < TOK_BPT / 16; k++)
+            s_mask[k * TOK_THREADS + t] = uint16_t(gather4(ws_bits(v[k].x)) | (gather4(ws_bits(v[k].y)) << 4) |
+                                                   (gather4(ws_bits(v[k].z)) << 8) | (gather4(ws_bits(v[k].w)) << 12));
     }
     __syncthreads();
-    uint64_t rs = (s_prefix >> 32) + (ex >> 16), re = (s_prefix & 0xffffffffull) + (ex & 0xffffu);
+    uint64_t m = *reinterpret_cast<const uint64_t *>(&s_mask[4 * t]);  // this thread's 64 consecutive positions
+    if (base < pad) m |= (pad - base >= 64) ? ~0ull : ((1ull << (pad - base)) - 1ull);
+    if (base >= n0) m = ~0ull;
+    else if (n0 - base < 64) m |= ~0ull << (n0 - base);
+    masks[uint64_t(bid) * TOK_THREADS + t] = m;
+    uint32_t prev = uint32_t(__shfl_up_sync(0xffffffffu, uint32_t(m >> 63), 1));
+    if (lane == 0) {
+        prev = (t == 0) ? prev_blk : uint32_t(s_mask[4 * t - 1] >> 15);
+        if (t != 0 && (base - 1 < pad || base - 1 >= n0)) prev = 1u;  // s_mask lacks the corrections above
+    }
+    uint64_t starts, ends;
+    tok_edges(m, prev, starts, ends);
+    uint32_t btot;
+    tok_block_scan((uint32_t(__popcll(starts)) << 16) | uint32_t(__popcll(ends)), s_warp, &btot);
+    if (t == 0) counts[bid] = (uint64_t(btot >> 16) << 32) | (btot & 0xffffu);
+}
 
-    // ---- emit ----
+// counts[b] = (starts << 32 | ends) of block b  ->  exclusive prefix in place; result[0] = tokens in the text
+__global__ void __launch_bounds__(1024)
+tok_offsets_kernel(uint64_t *__restrict__ counts, uint32_t nblocks, unsigned long long *__restrict__ result) {
+    __shared__ uint64_t s_w[32];
+    __shared__ uint64_t s_carry;
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    if (t == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t b0 = 0; b0 < nblocks; b0 += 1024) {
+        const uint32_t b = b0 + t;
+        const uint64_t mine = b < nblocks ? counts[b] : 0ull;
+        uint64_t inc = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t u = __shfl_up_sync(0xffffffffu, inc, d);
+            if (int(lane) >= d) inc += u;
+        }
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint64_t w = s_w[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint64_t u = __shfl_up_sync(0xffffffffu, w, d);
+                if (int(lane) >= d) w += u;
+            }
+            s_w[lane] = w;
+        }
+        __syncthreads();
+        const uint64_t carry = s_carry;
+        const uint64_t ex = carry + inc - mine + (warp ? s_w[warp - 1] : 0ull);
+        if (b < nblocks) counts[b] = ex;
+        __syncthreads();
+        if (t == 1023) s_carry = carry + s_w[31];
+        __syncthreads();
+    }
+    if (t == 0) result[0] = s_carry >> 32;
+}
+
+__global__ void __launch_bounds__(TOK_THREADS)
+tok_emit_kernel(const uint64_t *__restrict__ masks, const uint64_t *__restrict__ bases, uint32_t pad,
+                uint64_t *__restrict__ begin, uint64_t *__restrict__ end, uint64_t cap) {
+    __shared__ uint32_t s_warp[TOK_THREADS / 32];
+    const uint32_t t = threadIdx.x, lane = t & 31u, bid = blockIdx.x;
+    const uint64_t widx = uint64_t(bid) * TOK_THREADS + t;
+    const uint64_t m = masks[widx];
+    uint32_t prev = uint32_t(__shfl_up_sync(0xffffffffu, uint32_t(m >> 63), 1));
+    if (lane == 0) prev = widx ? uint32_t(masks[widx - 1] >> 63) : 1u;
+    uint64_t starts, ends;
+    tok_edges(m, prev, starts, ends);
+    uint32_t btot;
+    const uint32_t ex = tok_block_scan((uint32_t(__popcll(starts)) << 16) | uint32_t(__popcll(ends)), s_warp, &btot);
+    if (btot == 0) return;
+    const uint64_t bb = bases[bid];
+    uint64_t rs = (bb >> 32) + (ex >> 16), re = (bb & 0xffffffffull) + (ex & 0xffffu);
+    const uint64_t base = widx * TOK_BPT;
     uint64_t b = starts;
     while (b) {
         const int k = __ffsll(static_cast<long long>(b)) - 1;
@@ -184,29 +202,27 @@ tok_exit_kernel(const uint8_t *__restrict__ text, const uint64_t *__restrict__ b
 
 }  // namespace
 
-uint64_t tok_status_words(uint64_t nbytes) { return (nbytes + 16 + TOK_BLOCK_BYTES) / TOK_BLOCK_BYTES + 1; }
+uint64_t tok_blocks(uint64_t nbytes) { return (nbytes + 16 + TOK_BLOCK_BYTES) / TOK_BLOCK_BYTES + 1; }
 
 int tok_launch(const uint8_t *d_text, uint64_t nbytes, uint64_t *d_begin, uint64_t *d_end, uint64_t cap,
                const TokWork &w, int sm_count, cudaStream_t stream, int *launched) {
     *launched = 0;
-    if (nbytes >= (1ull << 32) - 64) return RXM_ERR_UNSUPPORTED;  // counts are 31 bits per status word
+    if (nbytes >= (1ull << 32) - 64) return RXM_ERR_UNSUPPORTED;  // per-call counts are 32 bits
     const uint32_t pad = uint32_t(reinterpret_cast<uintptr_t>(d_text)) & 15u;
     const uint64_t n0 = nbytes + pad;
     const uint64_t nblocks = (n0 + 1 + TOK_BLOCK_BYTES - 1) / TOK_BLOCK_BYTES;  // position n0 included
-    if (nblocks > w.status_cap) return RXM_ERR_INVALID;
-    if (cudaMemsetAsync(w.d_status, 0, nblocks * sizeof(uint64_t), stream) != cudaSuccess) return RXM_ERR_CUDA;
-    if (cudaMemsetAsync(w.d_ticket, 0, sizeof(uint32_t), stream) != cudaSuccess) return RXM_ERR_CUDA;
-    if (cudaMemsetAsync(w.d_result, 0, sizeof(unsigned long long), stream) != cudaSuccess) return RXM_ERR_CUDA;
+    if (nblocks > w.blocks_cap) return RXM_ERR_INVALID;
     if (cudaMemsetAsync(w.d_result + 1, 0xff, sizeof(unsigned long long), stream) != cudaSuccess) return RXM_ERR_CUDA;
-    tok_scan_kernel<<<unsigned(nblocks), TOK_THREADS, 0, stream>>>(d_text - pad, pad, n0, d_begin, d_end, cap, w.d_status,
-                                                                  w.d_ticket, w.d_result, uint32_t(nblocks));
-    *launched = 1;
+    tok_classify_kernel<<<unsigned(nblocks), TOK_THREADS, 0, stream>>>(d_text - pad, pad, n0, w.d_masks, w.d_counts);
+    tok_offsets_kernel<<<1, 1024, 0, stream>>>(w.d_counts, uint32_t(nblocks), w.d_result);
+    tok_emit_kernel<<<unsigned(nblocks), TOK_THREADS, 0, stream>>>(w.d_masks, w.d_counts, pad, d_begin, d_end, cap);
+    *launched = 3;
     uint64_t eb = (cap + 255) / 256;
     const uint64_t ecap = uint64_t(sm_count) * 8;
     if (eb > ecap) eb = ecap;
     if (eb == 0) eb = 1;
     tok_exit_kernel<<<unsigned(eb), 256, 0, stream>>>(d_text, d_begin, d_end, cap, w.d_result);
-    *launched = 2;
+    *launched = 4;
     return RXM_OK;
 }
 
