@@ -119,7 +119,10 @@ __device__ __forceinline__ uint32_t k3_need(uint32_t flags, const uint32_t *len)
 // TILE lanes cooperate on one string (TILE = 32: the whole warp; 16 / 8: two / four strings
 // per warp when the edge programs are short -- the items of a step fit one pass anyway).
 template <int NC, int TILE>
-__global__ void __launch_bounds__(K3_WARPS * 32)
+// Several strings per warp (TILE < 32): throughput work, issue-bound -- 5 blocks per SM (48
+// registers, a few spilled words) measured 17 % faster than 3 blocks at 73 registers.  TILE == 32
+// is chosen for long strings, where the single longest string bounds the batch: full registers.
+__global__ void __launch_bounds__(K3_WARPS * 32, TILE == 32 ? 1 : 5)
 k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, uint32_t items_in_smem,
                    const uint8_t *__restrict__ chars, const Spans sp, uint64_t n,
                    uint8_t *__restrict__ out, unsigned long long *__restrict__ overflow,
