@@ -13,6 +13,7 @@
 //   diploma_rxm -match [flags] -batch IN.rxmb OUT.bits [-regex R]   file batch route
 //       IN:  "RXMBATCH" | u64 n | u64 total | u64 offsets[n+1] | u8 chars[total]
 //       OUT: n bytes, 0/1
+//   diploma_rxm -match N [-maxlen L]                                 benchmark route (example_runner.cpp)
 //   extra: -device D (default 0), -chunk N (bytes of input per device batch, default 256 MiB)
 //
 // The tokens are found ON THE DEVICE (rxm_match_text): stdin is read as raw bytes and
@@ -20,6 +21,7 @@
 // printed when a piece is flushed (at `exit`, end of input, every -chunk bytes, or per
 // line on a terminal) instead of after each token; end of input ends the loop (the
 // reference spins forever, match.cpp:23-31).
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -58,6 +60,137 @@ static int match_piece(rxm_handle h, const uint8_t *text, size_t len, bool *done
     return RXM_OK;
 }
 
+// ---- `-match N`: the reference's benchmark route (matchers/example_runner.cpp:84-151) -------------
+// Same inputs (test/example_N/regexp.txt, pump.txt relative to the working directory), same three
+// automata (plain / bnf / reverse, all with -ssnf: example_runner.cpp:109-111), same CUMULATIVE
+// attack strings (:123 appends to `prefix`), same stop rule (a measurement >= 0.5 s ends that
+// automaton's series, :76-81) and the same `len seconds` lines in diploma_results.txt,
+// diploma_bnf_results.txt and diploma_reverse_results.txt -- but each string is matched by the
+// device kernels (one rxm_match_batch of one string, host buffers, wall clock around the call).
+static std::string pumped_string(int n, const std::vector<std::string> &pump_v) {  // example_runner.cpp:15-29
+    const int pump_count = int(pump_v.size()) / 2 + 1;
+    const int del_count = int(pump_v.size()) - pump_count;
+    const int tmp_len = int(pump_v[0].length());
+    std::string res = pump_v[0];
+    while (int(res.length()) + tmp_len < (n - del_count) / pump_count) res += pump_v[0];
+    std::string out;
+    for (int i = 0; i < del_count; i++) out += res + pump_v[1];
+    out += res;
+    return out;
+}
+
+static std::vector<std::string> split_commas(const std::string &str) {  // example_runner.cpp:31-44
+    std::vector<std::string> parts;
+    size_t start = 0;
+    for (size_t i = 0; i <= str.size(); i++)
+        if (i == str.size() || str[i] == ',') {
+            parts.push_back(str.substr(start, i - start));
+            start = i + 1;
+        }
+    return parts;
+}
+
+static bool read_line(FILE *f, std::string &out) {
+    out.clear();
+    int c;
+    bool any = false;
+    while ((c = std::fgetc(f)) != EOF) {
+        any = true;
+        if (c == '\n') break;
+        out.push_back(char(c));
+    }
+    return any;
+}
+
+static int run_configuration_examples_gpu(const std::string &number, int device, size_t max_len) {
+    const std::string dir = "test/example_" + number + "/";
+    FILE *regex_file = std::fopen((dir + "regexp.txt").c_str(), "r");
+    FILE *pump_file = std::fopen((dir + "pump.txt").c_str(), "r");
+    if (!regex_file || !pump_file) {
+        std::fprintf(stderr, "diploma_rxm: cannot open %sregexp.txt / pump.txt\n", dir.c_str());
+        return 2;
+    }
+    std::string pump_s, suffix, prefix, regexp_str;
+    read_line(pump_file, pump_s);
+    read_line(pump_file, suffix);
+    read_line(pump_file, prefix);
+    read_line(regex_file, regexp_str);
+    std::fclose(regex_file);
+    std::fclose(pump_file);
+    const std::vector<std::string> pump = split_commas(pump_s);
+    std::cout << regexp_str << std::endl;  // :105
+
+    std::string parse_copy = regexp_str;   // parse_regexp consumes its argument (parser.cpp:68)
+    Regexp *regexp = Regexp::parse_regexp(parse_copy);
+    regexp->is_backref_correct();
+    const bool flags[3][3] = {{false, false, true}, {false, true, true}, {true, true, true}};  // reverse, bnf, ssnf (:109-111)
+    const char *names[3] = {"diploma_results.txt", "diploma_bnf_results.txt", "diploma_reverse_results.txt"};
+    rxm_handle h[3] = {nullptr, nullptr, nullptr};
+    FILE *out[3] = {nullptr, nullptr, nullptr};
+    for (int a = 0; a < 3; a++) {
+        bool is_mfa = true;
+        Automata *automata = regexp->compile(is_mfa, flags[a][0], flags[a][1], flags[a][2]);
+        std::cout.flush();
+        rxm::HostTables host;
+        std::string err;
+        int st = rxm::flatten(automata, is_mfa, host, &err);
+        if (st != RXM_OK) {
+            std::fprintf(stderr, "diploma_rxm: flatten: %s (%s)\n", rxm_strerror(st), err.c_str());
+            return 3;
+        }
+        const rxm_tables t = host.view();
+        st = rxm_tables_upload(&t, device, &h[a]);
+        if (st != RXM_OK) {
+            std::fprintf(stderr, "diploma_rxm: upload: %s (%s)\n", rxm_strerror(st), rxm_last_cuda_error());
+            return 3;
+        }
+        out[a] = std::fopen((dir + names[a]).c_str(), "w");
+        if (!out[a]) return 2;
+    }
+    {   // first use pays for context and workspace set-up: not part of any measurement
+        const uint8_t w[1] = {'a'};
+        const uint64_t off[2] = {0, 1};
+        uint8_t bit;
+        for (int a = 0; a < 3; a++) rxm_match_batch(h[a], w, off, 1, &bit, nullptr);
+    }
+    bool timeouted[3] = {false, false, false};
+    int count = 0;
+    long long pump_size = 500;
+    size_t len = prefix.length() + size_t(pump_size) + suffix.length();
+    int rc = 0;
+    while ((!timeouted[0] || !timeouted[1] || !timeouted[2]) && len < max_len) {  // :120
+        if (pump_size > (1ll << 30)) break;
+        prefix.append(pumped_string(int(pump_size), pump)).append(suffix);  // :123 -- cumulative
+        const std::string &input_str = prefix;
+        len = input_str.length();
+        pump_size += pump_size;
+        for (int a = 0; a < 3; a++) {
+            if (timeouted[a]) continue;
+            const uint64_t off[2] = {0, uint64_t(len)};
+            uint8_t bit = 0;
+            const auto t0 = std::chrono::steady_clock::now();
+            const int st = rxm_match_batch(h[a], reinterpret_cast<const uint8_t *>(input_str.data()), off, 1, &bit, nullptr);
+            const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (st != RXM_OK) {
+                std::fprintf(stderr, "diploma_rxm: %s, length %zu: %s (%s)\n", names[a], len, rxm_strerror(st),
+                             rxm_last_cuda_error());
+                timeouted[a] = true;
+                if (st != RXM_ERR_OVERFLOW) rc = 3;
+                continue;
+            }
+            if (seconds >= 0.5) timeouted[a] = true;                                  // :78-79
+            if (seconds < 1) std::fprintf(out[a], "%zu %g\n", len, seconds);           // :80-81
+            if (a == 2) count++;                                                       // :140
+        }
+        if (count % 10 == 0) pump_size *= 2;  // :143-144
+    }
+    for (int a = 0; a < 3; a++) {
+        std::fclose(out[a]);
+        rxm_free(h[a]);
+    }
+    return rc;
+}
+
 static inline bool is_ws(uint8_t c) { return c == ' ' || (c >= 9 && c <= 13); }  // what `cin >>` skips
 
 int main(int argc, char **argv) {
@@ -65,6 +198,15 @@ int main(int argc, char **argv) {
         std::fprintf(stderr, "usage: diploma_rxm -match [-all|-bnf|-reverse|-ssnf] "
                              "[-batch IN OUT] [-regex R] [-device D] [-chunk N]\n");
         return 2;
+    }
+    if (argc > 2 && argv[2][0] >= '0' && argv[2][0] <= '9') {  // main.cpp:11-13: -match N
+        int device = 0;
+        size_t max_len = size_t(1) << 24;
+        for (int i = 3; i + 1 < argc; i++) {
+            if (std::strcmp(argv[i], "-device") == 0) device = std::atoi(argv[i + 1]);
+            if (std::strcmp(argv[i], "-maxlen") == 0) max_len = std::strtoull(argv[i + 1], nullptr, 10);
+        }
+        return run_configuration_examples_gpu(argv[2], device, max_len);
     }
     bool bnf = false, reverse = false, ssnf = false;
     const char *batch_in = nullptr, *batch_out = nullptr;

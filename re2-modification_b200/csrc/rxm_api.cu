@@ -429,7 +429,7 @@ extern "C" int rxm_match_text(rxm_handle h, const uint8_t *text, uint64_t nbytes
         m->cap_tok_blocks = 0;
         const size_t want = size_t(blocks + (blocks >> 2) + 16);
         CU(cudaMalloc(reinterpret_cast<void **>(&m->d_tok_masks), want * 256 * sizeof(uint64_t)));
-        CU(cudaMalloc(reinterpret_cast<void **>(&m->d_tok_counts), want * sizeof(uint64_t)));
+        CU(cudaMalloc(reinterpret_cast<void **>(&m->d_tok_counts), want * 9 * sizeof(uint64_t)));
         m->cap_tok_blocks = want;
     }
     if (!m->d_tok_result) CU(cudaMalloc(reinterpret_cast<void **>(&m->d_tok_result), 64));

@@ -95,7 +95,8 @@ int k3_launch(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n
 // "exit" (the sentinel of match.cpp:24; the token count if there is none).
 struct TokWork {
     uint64_t *d_masks;       // [blocks * 256] one whitespace bit per input position
-    uint64_t *d_counts;      // [blocks] per-block (starts << 32 | ends), then their exclusive prefix
+    uint64_t *d_counts;      // [blocks_cap] per 16 KB block (starts << 32 | ends), then their exclusive prefix;
+                             // followed by [blocks_cap * 8]: each 2 KB warp piece's offset inside its block
     uint64_t blocks_cap;     // capacity of both, in blocks
     unsigned long long *d_result;  // [2]
 };

@@ -185,16 +185,21 @@ def example5_strings(n, lo, hi, seed, device, corrupt_frac=0.5, kmax=64):
     return chars, offsets
 
 
+def pumped_string(nn, pump):
+    """matchers/example_runner.cpp:15-29 (== matcher.py:26-38)."""
+    pump_count = len(pump) // 2 + 1
+    del_count = len(pump) - pump_count
+    res = pump[0]
+    while len(res) + len(pump[0]) < (nn - del_count) // pump_count:
+        res += pump[0]
+    return res if len(pump) == 1 else (res + pump[1]) * del_count + res
+
+
 def attack_strings(pump, suffix, prefix, sizes):
     """Attack strings of matchers/example_runner.cpp:15-29 / matcher.py:26-38
     (non-cumulative), with and without the failing suffix.  -> list[bytes]"""
     def pumped(nn):
-        pump_count = len(pump) // 2 + 1
-        del_count = len(pump) - pump_count
-        res = pump[0]
-        while len(res) + len(pump[0]) < (nn - del_count) // pump_count:
-            res += pump[0]
-        return res if len(pump) == 1 else (res + pump[1]) * del_count + res
+        return pumped_string(nn, pump)
     out = []
     for s in sizes:
         p = pumped(s)

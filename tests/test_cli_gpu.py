@@ -79,3 +79,42 @@ def test_match_driver_pieces_eof_and_tokens_after_exit():
             assert r.returncode == 0, r.stderr.decode()[-400:]
             got = [int(ln) for ln in r.stdout.decode().splitlines() if ln in ("0", "1")]
             assert got == want, (tail, flags, len(got), len(want))
+
+
+def _cumulative_lengths(pump, suffix, prefix, max_len):
+    """Lengths of example_runner.cpp:118-145's strings (prefix grows by pumped + suffix; pump_size
+    doubles each round and once more after every tenth)."""
+    W = H.load_workloads()
+    out, pump_size, count = [], 500, 0
+    cur = prefix
+    length = len(prefix) + pump_size + len(suffix)
+    while length < max_len:
+        cur = cur + W.pumped_string(pump_size, pump) + suffix
+        length = len(cur)
+        out.append(length)
+        pump_size += pump_size
+        count += 1
+        if count % 10 == 0:
+            pump_size *= 2
+    return out
+
+
+@pytest.mark.skipif(not os.path.exists(DRIVER), reason="diploma_rxm not built")
+def test_match_driver_benchmark_route():
+    """`-match N` (example_runner.cpp:84-151): three result files of `len seconds` lines over the
+    cumulative attack strings, here for example 5 (pump aa / suffix b / prefix aacaac)."""
+    m = BY_NAME["ex05_fwd"]
+    with tempfile.TemporaryDirectory() as td:
+        ex = os.path.join(td, "test", "example_5")
+        os.makedirs(ex)
+        open(os.path.join(ex, "regexp.txt"), "w").write(m["regex"] + "\n")
+        open(os.path.join(ex, "pump.txt"), "w").write("aa\nb\naacaac\n")
+        r = subprocess.run([DRIVER, "-match", "5", "-maxlen", "200000"], capture_output=True, cwd=td, timeout=600)
+        assert r.returncode == 0, r.stderr.decode()[-400:]
+        assert r.stdout.decode().splitlines()[0] == m["regex"]
+        want = _cumulative_lengths(["aa"], "b", "aacaac", 200000)
+        assert len(want) >= 5
+        for name in ("diploma_results.txt", "diploma_bnf_results.txt", "diploma_reverse_results.txt"):
+            rows = [ln.split() for ln in open(os.path.join(ex, name)).read().splitlines()]
+            assert [int(a) for a, _ in rows] == want[:len(rows)], name
+            assert len(rows) >= 3 and all(0 < float(b) < 1 for _, b in rows)
