@@ -406,3 +406,45 @@ def test_match_text_device_pointers_alignment_and_capacity():
         m.match_text_ptrs(d.data_ptr(), len(text), host_out.ctypes.data, len(toks))
     assert e.value.status == rxm.RXM_ERR_INVALID
     m.close()
+
+
+@pytest.mark.parametrize("engine", ["k3", "k2"])
+def test_mfa_large_batch_properties(engine):
+    """BASELINE-shaped MFA batch (config 3: example 5 on x c x c x^m strings of 64-4096; 200 k strings
+    for K3, 20 k for K2): the bits are a pure function of each string -- a permuted batch gives the
+    permuted bits, a split batch the same bits, the raw-text route the same bits -- and a sample
+    equals the oracle."""
+    import torch
+    t, _, _ = load_case("ex05_fwd")
+    W = H.load_workloads()
+    n = 200_000 if engine == "k3" else 20_000
+    chars, off = W.example5_strings(n, 64, 4096, 9, "cuda")
+    m = _matcher(t, engine)
+    s = torch.cuda.current_stream().cuda_stream
+    out = torch.empty(n, dtype=torch.uint8, device="cuda")
+    m.match_ptrs(chars.data_ptr(), off.data_ptr(), n, out.data_ptr(), s)
+    torch.cuda.synchronize()
+    assert m.overflow_count() == 0
+    frac = float(out.float().mean())
+    assert 0.3 < frac < 0.7
+    # split
+    h = n // 3
+    out2 = torch.empty(n, dtype=torch.uint8, device="cuda")
+    m.match_ptrs(chars.data_ptr(), off.data_ptr(), h, out2.data_ptr(), s)
+    m.match_ptrs(chars.data_ptr(), off[h:].contiguous().data_ptr(), n - h, out2.data_ptr() + h, s)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+    # permutation of a slice (gathered on the host: 5000 strings)
+    k = 5000
+    off_h = off[:k + 1].cpu().numpy().astype(np.uint64)
+    chars_h = chars[:int(off_h[-1])].cpu().numpy()
+    strings = [bytes(chars_h[int(off_h[i]):int(off_h[i + 1])]) for i in range(k)]
+    perm = np.random.default_rng(1).permutation(k)
+    pc, po = H.make_batch([strings[i] for i in perm])
+    got_p = m.match_host(pc, po)
+    base = out[:k].cpu().numpy()
+    assert np.array_equal(got_p, base[perm])
+    # oracle on the slice, and the raw-text route on the same strings
+    assert np.array_equal(base, H.oracle_bits(t, chars_h, off_h))
+    assert np.array_equal(m.match_text_host(b"\n".join(strings)), base)
+    m.close()
