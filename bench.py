@@ -254,7 +254,7 @@ def reference_arm(args, W, rxm):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
     return 0
 
 
@@ -313,6 +313,9 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+RESULT_OUT = sys.stdout
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -324,6 +327,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    # stdout carries exactly ONE JSON line: anything libraries print there (NCCL prints its version
+    # line to stdout at the first collective) is sent to stderr instead
+    global RESULT_OUT
+    sys.stdout.flush()
+    RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     rxm = _load("rxm", os.path.join(PKG, "rxm.py"))
     W = _load("workloads", os.path.join(PKG, "workloads.py"))
@@ -629,7 +638,7 @@ def main():
                 line["cpu_baseline"] = cpu_baseline(W, rxm, wl, tables, regex, flags)
             else:
                 line["cpu_baseline"] = cpu_baseline_jobs(jobs, wl)
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=RESULT_OUT, flush=True)
     M.close()
     if world > 1:
         dist.destroy_process_group()

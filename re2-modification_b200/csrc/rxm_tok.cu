@@ -196,6 +196,7 @@ tok_emit_kernel(const uint64_t *__restrict__ masks, const uint64_t *__restrict__
     carry = __shfl_sync(0xffffffffu, carry, 0);
 #pragma unroll
     for (int j = 0; j < TOKE_PIECES; j++) {
+        if (!carry && !__any_sync(0xffffffffu, m[j] != 0)) continue;  // 2 KB inside one token: no boundary
         const uint32_t top = uint32_t(m[j] >> 63);
         uint32_t prev = __shfl_up_sync(0xffffffffu, top, 1);
         if (lane == 0) prev = carry;
