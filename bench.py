@@ -417,10 +417,27 @@ def main():
                 j["matcher"].close()
     M = _AllMatchers()
 
+    # one matcher (handle) per job; handles may run concurrently (include/rxm.h), so a step with
+    # several jobs puts each on its own stream, forked from and joined back into the timed stream
+    job_streams = [torch.cuda.Stream(device=dev) for _ in jobs] if len(jobs) > 1 else []
+    fork_ev = torch.cuda.Event()
+    join_evs = [torch.cuda.Event() for _ in job_streams]
+
     def step_device():
-        for j in jobs:
+        if not job_streams:
+            j = jobs[0]
             j["matcher"].match_ptrs(j["chars"].data_ptr(), j["offsets"].data_ptr(), j["n"],
                                     j["out"].data_ptr(), stream)
+            return
+        cur = torch.cuda.current_stream()
+        fork_ev.record(cur)
+        for j, st, ev_j in zip(jobs, job_streams, join_evs):
+            st.wait_event(fork_ev)
+            j["matcher"].match_ptrs(j["chars"].data_ptr(), j["offsets"].data_ptr(), j["n"],
+                                    j["out"].data_ptr(), st.cuda_stream)
+            ev_j.record(st)
+        for ev_j in join_evs:
+            cur.wait_event(ev_j)
 
     # ---- kernel-resident timing (inputs already in HBM) ---------------------------------
     for _ in range(args.warmup):
@@ -616,6 +633,7 @@ def main():
                        "engine": "+".join(sorted({rxm.ENGINE_NAMES.get(j["matcher"].plan().engine, "?") for j in jobs})),
                        "dfa_stride": int(jobs[0]["matcher"].plan().dfa_stride),
                        "jobs_per_step": len(jobs),
+                       "job_streams": max(1, len(job_streams)),
                        "l2": ("L2 flushed between timed steps (512 MB written; inputs are %.2f GB per GPU)" if flush else
                               "inputs (%.2f GB per GPU) are larger than the 126 MB L2") % (total_bytes / 1e9),
                        "sharding": "by string index, one rank per GPU, no data-path collective"},
