@@ -276,7 +276,7 @@ static int launch_on_device(rxm_matcher *m, const uint8_t *d_chars, rxm::Spans s
                             uint64_t n, uint8_t *d_out, cudaStream_t stream, uint64_t total_chars) {
     CU(cudaMemsetAsync(m->d_overflow, 0, sizeof(unsigned long long), stream));
     if (n == 0) return RXM_OK;
-    int launched = 0;
+    int launched = 0, launched_extra = 0;
     int st;
     if (m->info.engine == RXM_ENGINE_K1_DFA) {
         if (n > 0xfffffff0ull) return RXM_ERR_UNSUPPORTED;  // record index is 32 bits
@@ -314,8 +314,26 @@ static int launch_on_device(rxm_matcher *m, const uint8_t *d_chars, rxm::Spans s
             }
             if (total_chars / n > 4096) tile = 32;
         }
+        // long strings first: the tile sort's records give the order (skipped for small batches)
+        const rxm::K1Rec *order = nullptr;
+        const char *lpt = getenv("RXM_K3_ORDER");  // "index": tuning
+        if (n >= 4 * rxm::K1_TILE_STRINGS && n <= 0xfffffff0ull && !(lpt && std::strcmp(lpt, "index") == 0)) {
+            if (n > m->cap_recs) {
+                cudaFree(m->d_recs);
+                m->d_recs = nullptr;
+                m->cap_recs = 0;
+                const size_t want = size_t(n + (n >> 3) + 32);
+                CU(cudaMalloc(reinterpret_cast<void **>(&m->d_recs), want * sizeof(rxm::K1Rec)));
+                m->cap_recs = want;
+            }
+            if (!m->d_k1_counter) CU(cudaMalloc(reinterpret_cast<void **>(&m->d_k1_counter), 64 * sizeof(uint32_t)));
+            st = rxm::k1_tilesort_launch(spans, n, m->d_recs, m->d_k1_counter, nullptr, m->sm_count, stream);
+            if (st != RXM_OK) return st;
+            launched_extra = 1;
+            order = m->d_recs;
+        }
         st = rxm::k3_launch(v, gp, uint32_t(m->prog.items.size()), uint32_t(m->prog.begin.size()),
-                            m->tables.n_cells, tile, d_chars, spans, n, d_out, m->d_overflow, m->d_overflow + 1,
+                            m->tables.n_cells, tile, d_chars, spans, order, n, d_out, m->d_overflow, m->d_overflow + 1,
                             m->sm_count, stream, &launched);
     } else {
         rxm::MfaView v{m->d_edge_begin, m->d_edges, m->tables.n_states(), m->tables.start,
@@ -323,7 +341,7 @@ static int launch_on_device(rxm_matcher *m, const uint8_t *d_chars, rxm::Spans s
         st = rxm::k2_launch(v, m->tables.n_cells, m->tables.n_edges(), d_chars, spans, n, d_out,
                             m->d_overflow, m->d_overflow + 1, m->sm_count, stream, &launched);
     }
-    m->launches += uint64_t(launched);
+    m->launches += uint64_t(launched + launched_extra);
     if (st != RXM_OK) return st;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");

@@ -117,7 +117,7 @@ constexpr int K1_SORT_THREADS = 1024;
 constexpr int K1_SORT_PER_THREAD = K1_TILE / K1_SORT_THREADS;
 __global__ void __launch_bounds__(K1_SORT_THREADS)
 k1_tilesort_kernel(const Spans sp, uint64_t n, K1Rec *__restrict__ recs,
-                   uint32_t *__restrict__ task_counter, unsigned long long *__restrict__ overflow) {
+                   uint32_t *__restrict__ task_counter, unsigned long long *__restrict__ overflow /* may be null */) {
     static_assert(K1_BUCKETS == 2 * K1_SORT_THREADS, "two buckets per thread in the prefix pass");
     __shared__ uint32_t cnt[K1_BUCKETS];
     __shared__ uint32_t wsum[K1_SORT_THREADS / 32];
@@ -138,7 +138,7 @@ k1_tilesort_kernel(const Spans sp, uint64_t n, K1Rec *__restrict__ recs,
             if (i < n) {
                 beg[k] = sp.begin[i];
                 const uint64_t l = sp.end[i] - beg[k];
-                if (l >= 0x7fffffffull) atomicAdd(overflow, 1ull);
+                if (l >= 0x7fffffffull && overflow) atomicAdd(overflow, 1ull);
                 len[k] = clamp_len(l);
                 bkt[k] = len_bucket(len[k]);
                 atomicAdd(&cnt[bkt[k]], 1u);
@@ -684,6 +684,17 @@ int launch_classed(const K1Tables &kt, const K1Launch &a) {
 }
 
 }  // namespace
+
+int k1_tilesort_launch(Spans spans, uint64_t n, K1Rec *d_recs, uint32_t *d_counter, unsigned long long *d_overflow,
+                       int sm_count, cudaStream_t stream) {
+    const uint64_t ntiles = (n + K1_TILE - 1) / K1_TILE;
+    uint64_t blocks = ntiles;
+    const uint64_t cap = uint64_t(sm_count) * 2;
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) return RXM_OK;
+    k1_tilesort_kernel<<<unsigned(blocks), K1_SORT_THREADS, 0, stream>>>(spans, n, d_recs, d_counter, d_overflow);
+    return RXM_OK;
+}
 
 int k1_launch(const K1Tables &kt, const K1Launch &a, int *launched) {
     *launched = 0;

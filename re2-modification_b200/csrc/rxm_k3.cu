@@ -124,7 +124,7 @@ template <int NC, int TILE>
 // is chosen for long strings, where the single longest string bounds the batch: full registers.
 __global__ void __launch_bounds__(K3_WARPS * 32, TILE == 32 ? 1 : 5)
 k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, uint32_t items_in_smem,
-                   const uint8_t *__restrict__ chars, const Spans sp, uint64_t n,
+                   const uint8_t *__restrict__ chars, const Spans sp, const K1Rec *__restrict__ recs, uint64_t n,
                    uint8_t *__restrict__ out, unsigned long long *__restrict__ overflow,
                    unsigned long long *__restrict__ next_string) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -175,7 +175,21 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
         if (!have_str && !exhausted) {
             if (lane == 0) si = atomicAdd(next_string, 1ull);
             si = __shfl_sync(FULL, si, 0, TILE);
-            if (si >= n) {
+            bool skip = false;
+            if (recs) {
+                // strings are handed out in the tile sort's order -- group g (32 records) of every tile
+                // of 4096 before group g+1 of any: the long strings of the whole batch go first, so
+                // the tail of the launch is made of short ones
+                const uint64_t ntiles = (n + K1_TILE_STRINGS - 1) / K1_TILE_STRINGS;
+                const uint64_t g = si / (ntiles * 32u), rem = si - g * (ntiles * 32u);
+                const uint64_t tl = rem >> 5, pos = tl * K1_TILE_STRINGS + g * 32u + (rem & 31u);
+                if (g >= K1_TILE_STRINGS / 32u) si = n;                              // all handed out
+                else if (pos >= min(n, (tl + 1u) * K1_TILE_STRINGS)) skip = true;    // the last tile is short
+                else si = recs[pos].idx;
+            }
+            if (skip) {
+                // nothing this round; the next iteration takes another ticket
+            } else if (si >= n) {
                 exhausted = true;
             } else {
                 const uint64_t sb = sp.begin[si], se = sp.end[si];
@@ -455,7 +469,7 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
 
 template <int NC, int TILE>
 int launch_k3(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n_keys, const uint8_t *d_chars,
-              Spans spans, uint64_t n, uint8_t *d_out, unsigned long long *d_overflow,
+              Spans spans, const K1Rec *d_recs, uint64_t n, uint8_t *d_out, unsigned long long *d_overflow,
               unsigned long long *d_next, int sm_count, cudaStream_t stream) {
     constexpr int TILES = K3_WARPS * 32 / TILE;  // strings in flight per block
     const uint32_t SP = (v.n_states + TILE - 1u) & ~uint32_t(TILE - 1);
@@ -475,30 +489,30 @@ int launch_k3(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n
     if (blocks > need) blocks = need;
     if (cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), stream) != cudaSuccess) return RXM_ERR_CUDA;
     kern<<<unsigned(blocks), K3_WARPS * 32, smem, stream>>>(v, gp, n_items, n_keys, in_smem ? 1u : 0u, d_chars,
-                                                           spans, n, d_out, d_overflow, d_next);
+                                                           spans, d_recs, n, d_out, d_overflow, d_next);
     return RXM_OK;
 }
 
 template <int NC>
 int launch_k3_tile(uint32_t tile, const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n_keys,
-                   const uint8_t *d_chars, Spans spans, uint64_t n, uint8_t *d_out,
+                   const uint8_t *d_chars, Spans spans, const K1Rec *d_recs, uint64_t n, uint8_t *d_out,
                    unsigned long long *d_overflow, unsigned long long *d_next, int sm_count, cudaStream_t stream) {
-    if (tile <= 8) return launch_k3<NC, 8>(v, gp, n_items, n_keys, d_chars, spans, n, d_out, d_overflow, d_next, sm_count, stream);
-    if (tile <= 16) return launch_k3<NC, 16>(v, gp, n_items, n_keys, d_chars, spans, n, d_out, d_overflow, d_next, sm_count, stream);
-    return launch_k3<NC, 32>(v, gp, n_items, n_keys, d_chars, spans, n, d_out, d_overflow, d_next, sm_count, stream);
+    if (tile <= 8) return launch_k3<NC, 8>(v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, stream);
+    if (tile <= 16) return launch_k3<NC, 16>(v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, stream);
+    return launch_k3<NC, 32>(v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, stream);
 }
 
 }  // namespace
 
 int k3_launch(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n_keys, uint32_t n_cells,
-              uint32_t tile, const uint8_t *d_chars, Spans spans, uint64_t n, uint8_t *d_out,
+              uint32_t tile, const uint8_t *d_chars, Spans spans, const K1Rec *d_recs, uint64_t n, uint8_t *d_out,
               unsigned long long *d_overflow, unsigned long long *d_next, int sm_count, cudaStream_t stream,
               int *launched) {
     *launched = 0;
     int st;
-    if (n_cells <= 1) st = launch_k3_tile<1>(tile, v, gp, n_items, n_keys, d_chars, spans, n, d_out, d_overflow, d_next, sm_count, stream);
-    else if (n_cells <= 2) st = launch_k3_tile<2>(tile, v, gp, n_items, n_keys, d_chars, spans, n, d_out, d_overflow, d_next, sm_count, stream);
-    else if (n_cells <= 4) st = launch_k3_tile<4>(tile, v, gp, n_items, n_keys, d_chars, spans, n, d_out, d_overflow, d_next, sm_count, stream);
+    if (n_cells <= 1) st = launch_k3_tile<1>(tile, v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, stream);
+    else if (n_cells <= 2) st = launch_k3_tile<2>(tile, v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, stream);
+    else if (n_cells <= 4) st = launch_k3_tile<4>(tile, v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, stream);
     else return RXM_ERR_UNSUPPORTED;
     if (st == RXM_OK) *launched = 1;
     return st;

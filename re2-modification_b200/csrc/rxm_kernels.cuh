@@ -68,6 +68,9 @@ struct K1Launch {
 };
 
 int k1_launch(const K1Tables &kt, const K1Launch &a, int *launched);
+// The tile sort alone (K3 uses its order to hand out the long strings first); d_overflow may be null.
+int k1_tilesort_launch(Spans spans, uint64_t n, K1Rec *d_recs, uint32_t *d_counter, unsigned long long *d_overflow,
+                       int sm_count, cudaStream_t stream);
 
 // ---- K1B: memory-free automaton as a bit set (fallback when the determinisation is too large) ----
 void k1b_build_tables(const rxm_tables &t, std::vector<uint16_t> &edge_begin, std::vector<uint32_t> &edges);
@@ -84,7 +87,8 @@ int k2_launch(const MfaView &dev_view, uint32_t n_cells, uint32_t n_edges, const
 
 // ---- K3: MFA, one warp per string, over host-compiled edge programs --------------------------
 int k3_launch(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n_keys, uint32_t n_cells,
-              uint32_t tile /* lanes per string: 8, 16 or 32 */, const uint8_t *d_chars, Spans spans, uint64_t n, uint8_t *d_out,
+              uint32_t tile /* lanes per string: 8, 16 or 32 */, const uint8_t *d_chars, Spans spans,
+              const K1Rec *d_recs /* tile-sorted order, or null: index order */, uint64_t n, uint8_t *d_out,
               unsigned long long *d_overflow, unsigned long long *d_next, int sm_count, cudaStream_t stream,
               int *launched);
 
