@@ -272,6 +272,29 @@ extern "C" int rxm_overflow_count(rxm_handle h, uint64_t *count) {
 }
 
 // total_chars: offsets[n] - offsets[0] if the caller knows it, else ~0ull
+// Tile-sorted order of a batch (long strings first, equal lengths together) for the engines that
+// hand strings out one by one; *order stays null for small batches (and with RXM_K3_ORDER=index).
+static int prepare_order(rxm_matcher *m, rxm::Spans spans, uint64_t n, cudaStream_t stream,
+                         const rxm::K1Rec **order, int *launched) {
+    *order = nullptr;
+    const char *lpt = getenv("RXM_K3_ORDER");  // "index": tuning
+    if (n < 4 * rxm::K1_TILE_STRINGS || n > 0xfffffff0ull || (lpt && std::strcmp(lpt, "index") == 0)) return RXM_OK;
+    if (n > m->cap_recs) {
+        cudaFree(m->d_recs);
+        m->d_recs = nullptr;
+        m->cap_recs = 0;
+        const size_t want = size_t(n + (n >> 3) + 32);
+        CU(cudaMalloc(reinterpret_cast<void **>(&m->d_recs), want * sizeof(rxm::K1Rec)));
+        m->cap_recs = want;
+    }
+    if (!m->d_k1_counter) CU(cudaMalloc(reinterpret_cast<void **>(&m->d_k1_counter), 64 * sizeof(uint32_t)));
+    const int st = rxm::k1_tilesort_launch(spans, n, m->d_recs, m->d_k1_counter, nullptr, m->sm_count, stream);
+    if (st != RXM_OK) return st;
+    *launched = 1;
+    *order = m->d_recs;
+    return RXM_OK;
+}
+
 static int launch_on_device(rxm_matcher *m, const uint8_t *d_chars, rxm::Spans spans,
                             uint64_t n, uint8_t *d_out, cudaStream_t stream, uint64_t total_chars) {
     CU(cudaMemsetAsync(m->d_overflow, 0, sizeof(unsigned long long), stream));
@@ -293,8 +316,10 @@ static int launch_on_device(rxm_matcher *m, const uint8_t *d_chars, rxm::Spans s
                         m->d_k1_counter, m->d_overflow, m->sm_count, stream};
         st = rxm::k1_launch(m->k1, a, &launched);
     } else if (m->info.engine == RXM_ENGINE_K1_BITSET) {
+        const rxm::K1Rec *order = nullptr;
+        if ((st = prepare_order(m, spans, n, stream, &order, &launched_extra)) != RXM_OK) return st;
         st = rxm::k1b_launch(m->d_edge_begin, m->d_k1b_edges, m->tables.n_states(), m->tables.n_edges(),
-                             m->tables.start, m->tables.finish, m->tables.reversed, d_chars, spans, n, d_out,
+                             m->tables.start, m->tables.finish, m->tables.reversed, d_chars, spans, order, n, d_out,
                              m->d_overflow, m->d_overflow + 1, m->sm_count, stream, &launched);
     } else if (m->info.engine == RXM_ENGINE_K3_WARP) {
         rxm::MfaView v{m->d_edge_begin, m->d_edges, m->tables.n_states(), m->tables.start,
@@ -314,24 +339,8 @@ static int launch_on_device(rxm_matcher *m, const uint8_t *d_chars, rxm::Spans s
             }
             if (total_chars / n > 4096) tile = 32;
         }
-        // long strings first: the tile sort's records give the order (skipped for small batches)
         const rxm::K1Rec *order = nullptr;
-        const char *lpt = getenv("RXM_K3_ORDER");  // "index": tuning
-        if (n >= 4 * rxm::K1_TILE_STRINGS && n <= 0xfffffff0ull && !(lpt && std::strcmp(lpt, "index") == 0)) {
-            if (n > m->cap_recs) {
-                cudaFree(m->d_recs);
-                m->d_recs = nullptr;
-                m->cap_recs = 0;
-                const size_t want = size_t(n + (n >> 3) + 32);
-                CU(cudaMalloc(reinterpret_cast<void **>(&m->d_recs), want * sizeof(rxm::K1Rec)));
-                m->cap_recs = want;
-            }
-            if (!m->d_k1_counter) CU(cudaMalloc(reinterpret_cast<void **>(&m->d_k1_counter), 64 * sizeof(uint32_t)));
-            st = rxm::k1_tilesort_launch(spans, n, m->d_recs, m->d_k1_counter, nullptr, m->sm_count, stream);
-            if (st != RXM_OK) return st;
-            launched_extra = 1;
-            order = m->d_recs;
-        }
+        if ((st = prepare_order(m, spans, n, stream, &order, &launched_extra)) != RXM_OK) return st;
         st = rxm::k3_launch(v, gp, uint32_t(m->prog.items.size()), uint32_t(m->prog.begin.size()),
                             m->tables.n_cells, tile, d_chars, spans, order, n, d_out, m->d_overflow, m->d_overflow + 1,
                             m->sm_count, stream, &launched);

@@ -22,7 +22,8 @@ static_assert(kNfaBitsDepth == int(kBitsetMaxDepth), "planner limit == kernel st
 __global__ void __launch_bounds__(K1B_THREADS)
 k1b_bitset_kernel(const uint16_t *__restrict__ g_eb, const uint32_t *__restrict__ g_ed, uint32_t n_states,
                   uint32_t n_edges, uint32_t start, uint32_t finish, uint32_t reversed,
-                  const uint8_t *__restrict__ chars, const Spans sp, uint64_t n, uint8_t *__restrict__ out,
+                  const uint8_t *__restrict__ chars, const Spans sp, const K1Rec *__restrict__ recs, uint64_t n,
+                  uint8_t *__restrict__ out,
                   unsigned long long *__restrict__ overflow, unsigned long long *__restrict__ next_string) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t *ed = reinterpret_cast<uint32_t *>(smem);
@@ -35,9 +36,20 @@ k1b_bitset_kernel(const uint16_t *__restrict__ g_eb, const uint32_t *__restrict_
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(next_string, 32ull);
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const uint64_t i = base + lane;
-        if (i >= n) continue;
+        uint64_t i = base + lane;
+        if (recs) {
+            // the tile sort's order (see rxm_k3.cu): 32 consecutive tickets are one group of one tile,
+            // i.e. 32 strings of nearly equal length -- the lanes of this warp finish together
+            const uint64_t ntiles = (n + K1_TILE_STRINGS - 1) / K1_TILE_STRINGS;
+            const uint64_t g = base / (ntiles * 32u), tl = (base - g * (ntiles * 32u)) >> 5;
+            if (g >= K1_TILE_STRINGS / 32u) break;
+            const uint64_t pos = tl * K1_TILE_STRINGS + g * 32u + lane;
+            if (pos >= min(n, (tl + 1u) * K1_TILE_STRINGS)) continue;
+            i = recs[pos].idx;
+        } else {
+            if (base >= n) break;
+            if (i >= n) continue;
+        }
         const uint64_t b = sp.begin[i], e = sp.end[i];
         bool ok = e - b < 0x7fffffffull;
         Bits128 S{0, 0}, N;
@@ -70,9 +82,9 @@ void k1b_build_tables(const rxm_tables &t, std::vector<uint16_t> &eb, std::vecto
 }
 
 int k1b_launch(const uint16_t *d_eb, const uint32_t *d_ed, uint32_t n_states, uint32_t n_edges, uint32_t start,
-               uint32_t finish, uint32_t reversed, const uint8_t *d_chars, Spans spans, uint64_t n, uint8_t *d_out,
-               unsigned long long *d_overflow, unsigned long long *d_next, int sm_count, cudaStream_t stream,
-               int *launched) {
+               uint32_t finish, uint32_t reversed, const uint8_t *d_chars, Spans spans, const K1Rec *d_recs, uint64_t n,
+               uint8_t *d_out, unsigned long long *d_overflow, unsigned long long *d_next, int sm_count,
+               cudaStream_t stream, int *launched) {
     *launched = 0;
     const size_t smem = ((size_t(n_edges) * 4 + (size_t(n_states) + 1) * 2) + 15) & ~size_t(15);
     if (smem > 96 * 1024) return RXM_ERR_UNSUPPORTED;
@@ -86,7 +98,7 @@ int k1b_launch(const uint16_t *d_eb, const uint32_t *d_ed, uint32_t n_states, ui
     if (blocks > need) blocks = need;
     if (cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), stream) != cudaSuccess) return RXM_ERR_CUDA;
     k1b_bitset_kernel<<<unsigned(blocks), K1B_THREADS, smem, stream>>>(d_eb, d_ed, n_states, n_edges, start, finish, reversed,
-                                                                       d_chars, spans, n, d_out, d_overflow, d_next);
+                                                                       d_chars, spans, d_recs, n, d_out, d_overflow, d_next);
     *launched = 1;
     return RXM_OK;
 }

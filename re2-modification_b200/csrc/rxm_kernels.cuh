@@ -75,7 +75,8 @@ int k1_tilesort_launch(Spans spans, uint64_t n, K1Rec *d_recs, uint32_t *d_count
 // ---- K1B: memory-free automaton as a bit set (fallback when the determinisation is too large) ----
 void k1b_build_tables(const rxm_tables &t, std::vector<uint16_t> &edge_begin, std::vector<uint32_t> &edges);
 int k1b_launch(const uint16_t *d_eb, const uint32_t *d_ed, uint32_t n_states, uint32_t n_edges, uint32_t start,
-               uint32_t finish, uint32_t reversed, const uint8_t *d_chars, Spans spans, uint64_t n, uint8_t *d_out,
+               uint32_t finish, uint32_t reversed, const uint8_t *d_chars, Spans spans,
+               const K1Rec *d_recs /* tile-sorted order, or null */, uint64_t n, uint8_t *d_out,
                unsigned long long *d_overflow, unsigned long long *d_next, int sm_count, cudaStream_t stream,
                int *launched);
 

@@ -274,6 +274,9 @@ def test_planner_hands_large_determinisations_to_the_bitset_engine():
     want = H.oracle_bits(t, chars, off)
     assert np.array_equal(m.match_host(chars, off), want)
     assert np.array_equal(m.match_text_host(b"\n".join(long_strings)), want)
+    # a batch large enough for the tile-sorted hand-out order (>= 4 tiles of 4096 strings)
+    chars, off = _random_batch(rng, 20000, 0, 200, b"ab")
+    assert np.array_equal(m.match_host(chars, off), H.oracle_bits(t, chars, off))
     m.close()
 
 
