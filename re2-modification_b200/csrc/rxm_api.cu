@@ -55,6 +55,9 @@ struct rxm_matcher {
     uint8_t *d_k1_table = nullptr;   // direct: [256][SP] u8 ; classed: see rxm_kernels.cuh
     uint8_t *d_k1_accept = nullptr;
     uint32_t *d_k1b_edges = nullptr;  // K1B: packed edges (d_edge_begin holds the row starts)
+    rxm::BitsetMasks bmasks;          // K1B: follow masks (bit-parallel step) when the table allows them
+    uint64_t *d_k1b_ls = nullptr;
+    uint8_t *d_k1b_class = nullptr;
 
     // K2: MFA tables
     uint16_t *d_edge_begin = nullptr;
@@ -158,6 +161,15 @@ extern "C" int rxm_tables_upload(const rxm_tables *host_tables, int device, rxm_
             rxm::k1b_build_tables(t, eb, ed);
             if ((st = upload_vec(eb, &m->d_edge_begin)) != RXM_OK) return fail(st);
             if ((st = upload_vec(ed, &m->d_k1b_edges)) != RXM_OK) return fail(st);
+            const char *walk = getenv("RXM_K1B_WALK");  // "1": force the edge-walking step (tests)
+            rxm::plan_bitset_masks(t, m->bmasks);
+            if (walk && walk[0] == '1') m->bmasks.ok = false;
+            if (m->bmasks.ok) {
+                std::vector<uint8_t> cls(m->bmasks.byte_class, m->bmasks.byte_class + 256);
+                if ((st = upload_vec(m->bmasks.ls, &m->d_k1b_ls)) != RXM_OK) return fail(st);
+                if ((st = upload_vec(cls, &m->d_k1b_class)) != RXM_OK) return fail(st);
+            }
+            m->info.dfa_classes = m->bmasks.ok ? m->bmasks.n_classes : 0;  // 0: the edge-walking step
             m->info.engine = RXM_ENGINE_K1_BITSET;
             goto planned;
         }
@@ -235,6 +247,8 @@ extern "C" int rxm_free(rxm_handle h) {
     cudaFree(h->d_k1_table);
     cudaFree(h->d_k1_accept);
     cudaFree(h->d_k1b_edges);
+    cudaFree(h->d_k1b_ls);
+    cudaFree(h->d_k1b_class);
     cudaFree(h->d_edge_begin);
     cudaFree(h->d_edges);
     cudaFree(h->d_items);
@@ -318,6 +332,12 @@ static int launch_on_device(rxm_matcher *m, const uint8_t *d_chars, rxm::Spans s
     } else if (m->info.engine == RXM_ENGINE_K1_BITSET) {
         const rxm::K1Rec *order = nullptr;
         if ((st = prepare_order(m, spans, n, stream, &order, &launched_extra)) != RXM_OK) return st;
+        if (m->bmasks.ok)
+            st = rxm::k1b_mask_launch(m->d_k1b_ls, m->d_k1b_class, m->tables.n_states(), m->bmasks.n_classes,
+                                      m->tables.start, m->bmasks.accept[0], m->bmasks.accept[1], m->tables.reversed,
+                                      d_chars, spans, order, n, d_out, m->d_overflow, m->d_overflow + 1, m->sm_count,
+                                      stream, &launched);
+        else
         st = rxm::k1b_launch(m->d_edge_begin, m->d_k1b_edges, m->tables.n_states(), m->tables.n_edges(),
                              m->tables.start, m->tables.finish, m->tables.reversed, d_chars, spans, order, n, d_out,
                              m->d_overflow, m->d_overflow + 1, m->sm_count, stream, &launched);

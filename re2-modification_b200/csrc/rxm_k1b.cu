@@ -72,7 +72,78 @@ k1b_bitset_kernel(const uint16_t *__restrict__ g_eb, const uint32_t *__restrict_
     }
 }
 
+// Bit-parallel form (rxm_plan.hpp: BitsetMasks): per input byte one class lookup and, per root of
+// the active set, two 64-bit follow-mask words from shared memory -- no edge walk, no stack.
+__global__ void __launch_bounds__(K1B_THREADS)
+k1b_mask_kernel(const uint64_t *__restrict__ g_ls, const uint8_t *__restrict__ g_class, uint32_t n_states,
+                uint32_t n_classes, uint32_t start, uint64_t acc_lo, uint64_t acc_hi, uint32_t reversed,
+                const uint8_t *__restrict__ chars, const Spans sp, const K1Rec *__restrict__ recs, uint64_t n,
+                uint8_t *__restrict__ out, unsigned long long *__restrict__ overflow,
+                unsigned long long *__restrict__ next_string) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint64_t *ls = reinterpret_cast<uint64_t *>(smem);
+    uint8_t *bc = smem + size_t(n_classes) * n_states * 16;
+    for (uint32_t i = threadIdx.x; i < n_classes * n_states * 2; i += blockDim.x) ls[i] = g_ls[i];
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) bc[i] = g_class[i];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(next_string, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        uint64_t i = base + lane;
+        if (recs) {  // the tile sort's order: 32 strings of nearly equal length per warp
+            const uint64_t ntiles = (n + K1_TILE_STRINGS - 1) / K1_TILE_STRINGS;
+            const uint64_t g = base / (ntiles * 32u), tl = (base - g * (ntiles * 32u)) >> 5;
+            if (g >= K1_TILE_STRINGS / 32u) break;
+            const uint64_t pos = tl * K1_TILE_STRINGS + g * 32u + lane;
+            if (pos >= min(n, (tl + 1u) * K1_TILE_STRINGS)) continue;
+            i = recs[pos].idx;
+        } else {
+            if (base >= n) break;
+            if (i >= n) continue;
+        }
+        const uint64_t b = sp.begin[i], e = sp.end[i];
+        if (e - b >= 0x7fffffffull) {
+            atomicAdd(overflow, 1ull);
+            out[i] = 0;
+            continue;
+        }
+        const uint8_t *s = chars + b;
+        const uint32_t len = uint32_t(e - b);
+        Bits128 S{0, 0};
+        S.set(start);  // automata.cpp:178-179
+        for (uint32_t k = 0; k < len && !S.empty(); k++) {  // :181-200, break on the empty set (:186-188)
+            const uint32_t byte = reversed ? s[len - 1u - k] : s[k];
+            S = nfa_mask_step(ls + size_t(bc[byte]) * n_states * 2, S);
+        }
+        out[i] = ((S.lo & acc_lo) | (S.hi & acc_hi)) ? 1 : 0;  // :201-209
+    }
+}
+
 }  // namespace
+
+int k1b_mask_launch(const uint64_t *d_ls, const uint8_t *d_class, uint32_t n_states, uint32_t n_classes, uint32_t start,
+                    uint64_t acc_lo, uint64_t acc_hi, uint32_t reversed, const uint8_t *d_chars, Spans spans,
+                    const K1Rec *d_recs, uint64_t n, uint8_t *d_out, unsigned long long *d_overflow,
+                    unsigned long long *d_next, int sm_count, cudaStream_t stream, int *launched) {
+    *launched = 0;
+    const size_t smem = size_t(n_classes) * n_states * 16 + 256;
+    if (smem > 96 * 1024) return RXM_ERR_UNSUPPORTED;
+    if (cudaFuncSetAttribute(k1b_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+        return RXM_ERR_CUDA;
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k1b_mask_kernel, K1B_THREADS, smem) != cudaSuccess || nb <= 0)
+        return RXM_ERR_CUDA;
+    uint64_t blocks = uint64_t(sm_count) * nb;
+    const uint64_t need = (n + K1B_THREADS - 1) / K1B_THREADS;
+    if (blocks > need) blocks = need;
+    if (cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), stream) != cudaSuccess) return RXM_ERR_CUDA;
+    k1b_mask_kernel<<<unsigned(blocks), K1B_THREADS, smem, stream>>>(d_ls, d_class, n_states, n_classes, start, acc_lo, acc_hi,
+                                                                     reversed, d_chars, spans, d_recs, n, d_out, d_overflow, d_next);
+    *launched = 1;
+    return RXM_OK;
+}
 
 void k1b_build_tables(const rxm_tables &t, std::vector<uint16_t> &eb, std::vector<uint32_t> &ed) {
     eb.resize(t.n_states + 1);

@@ -80,6 +80,11 @@ int k1b_launch(const uint16_t *d_eb, const uint32_t *d_ed, uint32_t n_states, ui
                unsigned long long *d_overflow, unsigned long long *d_next, int sm_count, cudaStream_t stream,
                int *launched);
 
+int k1b_mask_launch(const uint64_t *d_ls, const uint8_t *d_class, uint32_t n_states, uint32_t n_classes, uint32_t start,
+                    uint64_t acc_lo, uint64_t acc_hi, uint32_t reversed, const uint8_t *d_chars, Spans spans,
+                    const K1Rec *d_recs, uint64_t n, uint8_t *d_out, unsigned long long *d_overflow,
+                    unsigned long long *d_next, int sm_count, cudaStream_t stream, int *launched);
+
 // ---- K2: MFA, one thread per string ------------------------------------------------------
 int k2_launch(const MfaView &dev_view, uint32_t n_cells, uint32_t n_edges, const uint8_t *d_chars,
               Spans spans, uint64_t n, uint8_t *d_out, unsigned long long *d_overflow,

@@ -79,5 +79,27 @@ RXM_HD bool nfa_bits_step(const uint16_t *eb, const uint32_t *ed, uint32_t finis
     return true;
 }
 
+// The same step from follow masks (rxm_plan.hpp: BitsetMasks): ls = LS[class] = n_states x 2 words.
+RXM_HD Bits128 nfa_mask_step(const uint64_t *ls, Bits128 S) {
+    Bits128 N{0, 0};
+    uint64_t w = S.lo;
+    while (w) {  // roots 0..63: the filter is S.lo below r
+        const uint32_t r = nfa_ctz64(w);
+        const uint64_t below = S.lo & ((1ull << r) - 1ull);
+        w &= w - 1;
+        N.lo |= ls[2 * r] & ~below;
+        N.hi |= ls[2 * r + 1];
+    }
+    w = S.hi;
+    while (w) {  // roots 64..127: all of S.lo lies below
+        const uint32_t r = nfa_ctz64(w);
+        const uint64_t below = S.hi & ((1ull << r) - 1ull);
+        w &= w - 1;
+        N.lo |= ls[2 * (r + 64)] & ~S.lo;
+        N.hi |= ls[2 * (r + 64) + 1] & ~below;
+    }
+    return N;
+}
+
 }  // namespace rxm
 #endif

@@ -315,6 +315,61 @@ int check_nfa_bitset(const rxm_tables &t, std::string *err) {
     return RXM_OK;
 }
 
+void plan_bitset_masks(const rxm_tables &t, BitsetMasks &out) {
+    out = BitsetMasks();
+    if (t.n_states > kBitsetMaxStates) return;
+    std::vector<uint8_t> letter_target(t.n_states, 0), eps_target(t.n_states, 0);
+    for (uint32_t q = 0; q < t.n_states; q++)
+        for (uint32_t e = t.edge_begin[q]; e < t.edge_begin[q + 1]; e++) {
+            if (t.edge_kind[e] == RXM_EDGE_EPS) eps_target[t.edge_to[e]] = 1;
+            else if (t.edge_kind[e] == RXM_EDGE_LIT || t.edge_kind[e] == RXM_EDGE_ANY) letter_target[t.edge_to[e]] = 1;
+        }
+    for (uint32_t q = 0; q < t.n_states; q++)
+        if (letter_target[q] && eps_target[q]) return;  // such a node can be "visited" without being a root
+    // byte classes: one per distinct literal byte, class 0 for the rest
+    std::vector<int> rep{-1};
+    int cls_of[256];
+    std::fill(cls_of, cls_of + 256, 0);
+    for (uint32_t e = 0; e < t.n_edges; e++)
+        if (t.edge_kind[e] == RXM_EDGE_LIT && cls_of[t.edge_sym[e]] == 0) {
+            cls_of[t.edge_sym[e]] = int(rep.size());
+            rep.push_back(t.edge_sym[e]);
+        }
+    out.n_classes = uint32_t(rep.size());
+    for (int b = 0; b < 256; b++) out.byte_class[b] = uint8_t(cls_of[b]);
+    // epsilon closures (no epsilon cycle: check_nfa_bitset ran first)
+    std::vector<std::vector<uint32_t>> closure(t.n_states);
+    for (uint32_t r = 0; r < t.n_states; r++) {
+        std::vector<uint8_t> seen(t.n_states, 0);
+        std::vector<uint32_t> stack{r};
+        seen[r] = 1;
+        while (!stack.empty()) {
+            const uint32_t u = stack.back();
+            stack.pop_back();
+            closure[r].push_back(u);
+            for (uint32_t e = t.edge_begin[u]; e < t.edge_begin[u + 1]; e++)
+                if (t.edge_kind[e] == RXM_EDGE_EPS && !seen[t.edge_to[e]]) {
+                    seen[t.edge_to[e]] = 1;
+                    stack.push_back(t.edge_to[e]);
+                }
+        }
+    }
+    out.ls.assign(size_t(out.n_classes) * t.n_states * 2, 0);
+    for (uint32_t r = 0; r < t.n_states; r++)
+        for (uint32_t u : closure[r]) {
+            if (u == t.finish) out.accept[r >> 6] |= 1ull << (r & 63);
+            for (uint32_t e = t.edge_begin[u]; e < t.edge_begin[u + 1]; e++) {
+                const uint32_t to = t.edge_to[e];
+                for (uint32_t c = 0; c < out.n_classes; c++) {
+                    const bool fires = t.edge_kind[e] == RXM_EDGE_ANY ||
+                                       (t.edge_kind[e] == RXM_EDGE_LIT && c != 0 && int(t.edge_sym[e]) == rep[c]);
+                    if (fires) out.ls[(size_t(c) * t.n_states + r) * 2 + (to >> 6)] |= 1ull << (to & 63);
+                }
+            }
+        }
+    out.ok = true;
+}
+
 int check_mfa(const rxm_tables &t, std::string *err) {
     // epsilon-only cycles make MFA::evaluateState (mfa.cpp:143-147) recurse forever
     std::vector<uint8_t> color(t.n_states, 0);

@@ -70,6 +70,24 @@ constexpr uint32_t kBitsetMaxStates = 128;
 constexpr uint32_t kBitsetMaxDepth = 48;
 int check_nfa_bitset(const rxm_tables &t, std::string *err);
 
+// Follow masks for K1B's bit-parallel step.  When no letter-edge target has an incoming epsilon
+// edge (true for everything toGlushkov and toThomson build: a letter edge always leads to a fresh
+// node) the reference's step collapses to
+//     next = OR over r in S of  LS[class(letter)][r] & ~(S & bits_below(r))
+// with LS[c][r] = letter-c successors of r's epsilon closure: a node is only ever "visited" as a
+// completed ROOT of the walk (roots run in ascending order, automata.cpp:122), so the `visited`
+// test of automata.cpp:105-107 removes exactly the targets that sit in S below the current root,
+// and a node reached from two roots is evaluated under the smaller one, whose filter is the
+// weaker.  Acceptance (final pass, :100-102, :201-209): finish lies in the closure of some r in S.
+struct BitsetMasks {
+    bool ok = false;               // the structural condition holds; otherwise K1B walks the edges
+    uint32_t n_classes = 0;        // class 0: bytes no literal edge names (only `.` edges fire)
+    uint8_t byte_class[256] = {0};
+    std::vector<uint64_t> ls;      // [n_classes][n_states][2]
+    uint64_t accept[2] = {0, 0};   // r: finish in eclose(r)
+};
+void plan_bitset_masks(const rxm_tables &t, BitsetMasks &out);
+
 // Static checks for an MFA table (epsilon cycles, sizes).  RXM_OK or RXM_ERR_UNSUPPORTED.
 int check_mfa(const rxm_tables &t, std::string *err);
 

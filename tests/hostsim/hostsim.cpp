@@ -112,6 +112,31 @@ extern "C" int hostsim_dfa_batch(const rxm_tables *t, const uint8_t *chars, cons
     return 0;
 }
 
+// K1B's bit-parallel step from follow masks on the host.  Returns 0, 1 if the structural
+// condition for the masks does not hold for this table (the caller then expects the walk), or the
+// planner's status.
+extern "C" int hostsim_nfa_mask_batch(const rxm_tables *t, const uint8_t *chars, const uint64_t *off,
+                                      uint64_t n, uint8_t *out) {
+    std::string err;
+    int st = rxm::check_nfa_bitset(*t, &err);
+    if (st != RXM_OK) return st;
+    rxm::BitsetMasks bm;
+    rxm::plan_bitset_masks(*t, bm);
+    if (!bm.ok) return 1;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint8_t *s = chars + off[i];
+        const uint32_t len = uint32_t(off[i + 1] - off[i]);
+        rxm::Bits128 S{0, 0};
+        S.set(t->start);
+        for (uint32_t k = 0; k < len && !S.empty(); k++) {
+            const uint8_t b = t->reversed ? s[len - 1 - k] : s[k];
+            S = rxm::nfa_mask_step(bm.ls.data() + size_t(bm.byte_class[b]) * t->n_states * 2, S);
+        }
+        out[i] = ((S.lo & bm.accept[0]) | (S.hi & bm.accept[1])) ? 1 : 0;
+    }
+    return 0;
+}
+
 // The K1B step (rxm_nfa_core.cuh) on the host: returns 0, the planner's status if the bit-set
 // engine's static checks reject the table, or 2 if a string overflowed the recursion stack.
 extern "C" int hostsim_nfa_bits_batch(const rxm_tables *t, const uint8_t *chars, const uint64_t *off,

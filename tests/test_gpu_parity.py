@@ -242,15 +242,20 @@ def test_k1_quad_stride_and_bytes_outside_the_window(name, monkeypatch):
         assert stride == 4
 
 
+@pytest.mark.parametrize("mode", ["masks", "walk"])
 @pytest.mark.parametrize("name", [n for n in CASE_NAMES if BY_NAME[n]["kind"] == "nfa"])
-def test_bitset_engine_on_every_memory_free_fixture(name, monkeypatch):
-    """K1B (the active set as a 128-bit mask, the reference's exact step per letter): forced on
-    every memory-free fixture, golden bits + random batches against the oracle; forward,
-    right-to-left, Thompson, the visited quirk."""
+def test_bitset_engine_on_every_memory_free_fixture(name, mode, monkeypatch):
+    """K1B (the active set as a 128-bit mask, the reference's exact step per letter) in both of its
+    forms -- bit-parallel follow masks and the edge walk: forced on every memory-free fixture,
+    golden bits + random batches against the oracle; forward, right-to-left, Thompson, the
+    visited quirk."""
     monkeypatch.setenv("RXM_NFA_ENGINE", "bitset")
+    if mode == "walk":
+        monkeypatch.setenv("RXM_K1B_WALK", "1")
     t, strings, bits = load_case(name)
     m = rxm.Matcher(t, 0)
     assert rxm.ENGINE_NAMES[m.plan().engine] == "K1_BITSET"
+    assert (m.plan().dfa_classes > 0) == (mode == "masks")
     chars, off = H.make_batch(strings)
     assert np.array_equal(m.match_host(chars, off), bits)
     rng = np.random.default_rng(17)
