@@ -105,7 +105,8 @@ typedef struct rxm_matcher *rxm_handle;
 /* Which kernel family the host planner picked for a table. */
 enum {
     RXM_ENGINE_K1_DFA = 1,     /* memory-free automaton, determinised with the reference's exact step */
-    RXM_ENGINE_K1_BITSET = 2,  /* memory-free automaton, bit-parallel active-set kernel             */
+    RXM_ENGINE_K1_BITSET = 2,  /* memory-free automaton too large to determinise: the active set
+                                  itself on the device (follow masks, or an edge walk)             */
     RXM_ENGINE_K2_THREAD = 3,  /* MFA, one thread per string                                        */
     RXM_ENGINE_K3_WARP = 4     /* MFA, one warp per string (long strings / large automata)          */
 };
@@ -113,7 +114,8 @@ enum {
 typedef struct rxm_plan_info {
     uint32_t engine;        /* RXM_ENGINE_*                                        */
     uint32_t dfa_states;    /* K1_DFA: reachable active sets (incl. dead state)    */
-    uint32_t dfa_classes;   /* K1_DFA: byte classes                                */
+    uint32_t dfa_classes;   /* K1_DFA: byte classes; K1_BITSET: classes of the follow masks,
+                               0 when the edge-walking step is used                   */
     uint32_t exact_step_differs; /* memory-free: #(set,letter) pairs where the reference's
                                     `visited` step (automata.cpp:104-107) differs from the
                                     textbook step -- informational                   */

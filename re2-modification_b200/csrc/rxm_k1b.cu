@@ -1,14 +1,18 @@
 // K1B -- memory-free automaton as a bit set, sm_100a.
 // Replaces Automata::match (automata.cpp:177-210) for automata whose determinisation under the
 // reference's exact step is too large for K1's table (rxm_plan.cpp: kMaxDfaStates).  One thread
-// per string; the active set std::set<Node*> is a 128-bit mask (bit = address rank, so ascending
-// bits == set order, automata.cpp:122), `visited` and the next set are masks too, and
-// Automata::evaluateState's recursion through epsilon edges (automata.cpp:108-110) is an explicit
-// stack of (node, next edge).  The step is the reference's, quirk included: an edge -- letter
-// edges too -- whose target was already evaluated in this step is skipped (automata.cpp:104-107),
-// and a node is marked evaluated only after its edge loop (automata.cpp:116).
-// Bound: instruction issue (a handful of edge visits per input byte); this is the fallback
-// engine, the table scan K1 is the fast one.
+// per string; the active set std::set<Node*> is a 128-bit mask in registers (bit = address rank,
+// so ascending bits == set order, automata.cpp:122).  Two kernels:
+//   k1b_mask_kernel    bit-parallel: next = OR over r in S of LS[class][r] & ~(S & bits_below(r)),
+//                      follow masks LS in shared memory (rxm_plan.hpp: BitsetMasks explains why this
+//                      IS the reference's step, `visited` quirk included, when no letter-edge
+//                      target has an incoming epsilon edge)
+//   k1b_bitset_kernel  the general form: `visited` and the next set are masks too, and
+//                      Automata::evaluateState's recursion through epsilon edges
+//                      (automata.cpp:108-110) is an explicit stack of (node, next edge); an edge --
+//                      letter edges too -- whose target was already evaluated in this step is skipped
+//                      (automata.cpp:104-107), a node is marked evaluated only after its edge loop (:116)
+// Bound: instruction issue (per input byte ~25 instructions per member of the active set).
 #include "rxm_kernels.cuh"
 #include "rxm_nfa_core.cuh"
 
