@@ -314,6 +314,38 @@ class ClockSampler:
 
 
 RESULT_OUT = sys.stdout
+ORIG_AFFINITY = None
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank on the CPUs of the NUMA node its GPU hangs off (what `numactl` would do for a
+    one-process-per-GPU job): pinned host buffers are then allocated next to the GPU's PCIe root,
+    which is what the host-buffer (`e2e`) path pays for when several ranks copy at once.  Returns
+    the node or None; the original affinity is kept for the CPU-baseline leg."""
+    global ORIG_AFFINITY
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local_rank]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else local_rank
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bdf = bus.lower()[-12:]  # 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        ORIG_AFFINITY = os.sched_getaffinity(0)
+        cpus &= ORIG_AFFINITY
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
 
 
 def main():
@@ -347,6 +379,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    numa_node = bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -634,6 +667,7 @@ def main():
                        "dfa_stride": int(jobs[0]["matcher"].plan().dfa_stride),
                        "jobs_per_step": len(jobs),
                        "job_streams": max(1, len(job_streams)),
+                       "numa_node": numa_node,
                        "l2": ("L2 flushed between timed steps (512 MB written; inputs are %.2f GB per GPU)" if flush else
                               "inputs (%.2f GB per GPU) are larger than the 126 MB L2") % (total_bytes / 1e9),
                        "sharding": "by string index, one rank per GPU, no data-path collective"},
@@ -651,6 +685,8 @@ def main():
             "parity_checked": k_chk,
         }
         line.update(extra)
+        if ORIG_AFFINITY is not None:
+            os.sched_setaffinity(0, ORIG_AFFINITY)  # the CPU baseline uses every host core
         if world == 1 and not args.no_cpu_baseline:
             if wl in ("config2", "config3"):
                 line["cpu_baseline"] = cpu_baseline(W, rxm, wl, tables, regex, flags)
