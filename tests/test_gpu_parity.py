@@ -456,3 +456,29 @@ def test_mfa_large_batch_properties(engine):
     assert np.array_equal(base, H.oracle_bits(t, chars_h, off_h))
     assert np.array_equal(m.match_text_host(b"\n".join(strings)), base)
     m.close()
+
+
+@pytest.mark.parametrize("name", ["nfa_config2", "ex05_fwd", "ex02_rev", "nfa_blowup"])
+def test_sharded_1_2_4_8_ways_gives_the_identical_bit_vector(name):
+    """the batch cut into 1, 2, 4 and 8 byte-balanced contiguous shards
+    (re2-modification_b200/sharding.py -- what each rank of an N-GPU job owns), every shard matched
+    on its own with rebased offsets, concatenated: the same bits as the whole batch."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("sharding", os.path.join(H.PKG, "sharding.py"))
+    S = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(S)
+    t, strings, bits = load_case(name)
+    rng = np.random.default_rng(21)
+    extra = [bytes(rng.choice(np.frombuffer(b"aabbc", dtype=np.uint8), size=int(L))) for L in rng.integers(0, 400, size=3000)]
+    chars, off = H.make_batch(strings + extra)
+    m = rxm.Matcher(t, 0)
+    whole = m.match_host(chars, off)
+    assert np.array_equal(whole[:len(bits)], bits)
+    for world in (2, 4, 8):
+        bounds = S.shard_by_bytes(off, world)
+        parts = []
+        for r in range(world):
+            c, o = S.local_view(chars, off, bounds[r], bounds[r + 1])
+            parts.append(m.match_host(c, o))
+        assert np.array_equal(np.concatenate(parts), whole), world
+    m.close()

@@ -13,6 +13,8 @@ METRICS = [
     "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
     "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
     "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "smsp__sass_average_branch_targets_threads_uniform.pct", "smsp__branch_targets_threads_divergent",
+    "smsp__inst_executed_op_branch.sum",
     "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__warps_eligible.avg.per_cycle_active",
     "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
