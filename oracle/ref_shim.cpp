@@ -86,7 +86,11 @@ extern "C" void __real_free(void *);
 constexpr size_t SMALL_MAX = 256;
 static inline void *oracle_new(size_t n) {
     if (n <= SMALL_MAX) return arena_alloc(n);
-    void *p = malloc(n);
+    // zero-filled like the arena: the reference reads members it never initialises (`bool is_read`,
+    // `Regexp* reference_to`, regex/regex.h:85; first read at regex/bnf.cpp:49,63), and a Regexp is
+    // larger than SMALL_MAX -- with recycled malloc chunks bnf() then builds a different expression
+    // from one process to the next.  Zero is what a fresh heap gives the reference.
+    void *p = calloc(1, n);
     if (!p) abort();
     return p;
 }

@@ -64,7 +64,11 @@ void *bump(size_t n) {
 bool in_arena(const void *p) { return g_base && p >= g_base && p < g_base + kArenaBytes; }
 void *front_new(size_t n) {
     if (n <= kSmallMax) return bump(n);
-    void *p = malloc(n);
+    // zero-filled like the arena: the reference reads members it never initialises (`bool is_read`,
+    // `Regexp* reference_to`, regex/regex.h:85; first read at regex/bnf.cpp:49,63), and a Regexp is
+    // larger than kSmallMax -- with recycled malloc chunks bnf() then builds a different expression
+    // from one process to the next.  Zero is what a fresh heap gives the reference.
+    void *p = calloc(1, n);
     if (!p) abort();
     return p;
 }

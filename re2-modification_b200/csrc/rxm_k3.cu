@@ -497,9 +497,15 @@ template <int NC>
 int launch_k3_tile(uint32_t tile, const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n_keys,
                    const uint8_t *d_chars, Spans spans, const K1Rec *d_recs, uint64_t n, uint8_t *d_out,
                    unsigned long long *d_overflow, unsigned long long *d_next, int sm_count, cudaStream_t stream) {
-    if (tile <= 8) return launch_k3<NC, 8>(v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, stream);
-    if (tile <= 16) return launch_k3<NC, 16>(v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, stream);
-    return launch_k3<NC, 32>(v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, stream);
+    // the per-string state (two buffers of one slot per node) of all strings of a block must fit
+    // shared memory: automata with many nodes move to wider tiles (fewer strings per block)
+    int st = RXM_ERR_UNSUPPORTED;
+    if (tile <= 8) st = launch_k3<NC, 8>(v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, stream);
+    if (st == RXM_ERR_UNSUPPORTED && tile <= 16)
+        st = launch_k3<NC, 16>(v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, stream);
+    if (st == RXM_ERR_UNSUPPORTED)
+        st = launch_k3<NC, 32>(v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, stream);
+    return st;
 }
 
 }  // namespace

@@ -27,3 +27,16 @@ def load_case(name):
             bits.append(int(b))
             strings.append(b"" if s == "<empty>" else s.encode())
     return t, strings, np.array(bits, dtype=np.uint8)
+
+
+def load_fuzz_corpus(path=None):
+    """Random-expression fixtures (tests/golden/make_fuzz_corpus.py; bits from the reference's own code).
+    -> list of (regex, flags, kind, Tables, list[bytes], bits uint8[n])"""
+    out = []
+    with open(path or os.path.join(H.GOLDEN, "fuzz", "corpus.jsonl")) as f:
+        for line in f:
+            c = json.loads(line)
+            out.append((c["regex"], c["flags"], c["kind"], H.rxm.Tables(c["tables"]),
+                        [s.encode() for s in c["strings"]],
+                        np.frombuffer(c["bits"].encode(), dtype=np.uint8) - ord("0")))
+    return out

@@ -482,3 +482,34 @@ def test_sharded_1_2_4_8_ways_gives_the_identical_bit_vector(name):
             parts.append(m.match_host(c, o))
         assert np.array_equal(np.concatenate(parts), whole), world
     m.close()
+
+
+def test_random_expression_corpus_on_device(monkeypatch):
+    """The 200 random expressions of tests/golden/fuzz (bits from the reference's own code) through
+    every device engine that can take them: the planner's choice, K2 and K3 for the MFAs, the
+    bit-set engine in both forms for the memory-free ones, and the raw-text route."""
+    from cases import load_fuzz_corpus
+    corpus = load_fuzz_corpus()
+    engines_seen = set()
+    for regex, flags, kind, t, strings, bits in corpus:
+        chars, off = H.make_batch(strings)
+        tag = (regex, flags)
+        variants = [{}]
+        if kind == "mfa":
+            variants += [{"RXM_MFA_ENGINE": "k2"}, {"RXM_MFA_ENGINE": "k3"}]
+        else:
+            variants += [{"RXM_NFA_ENGINE": "bitset"}, {"RXM_NFA_ENGINE": "bitset", "RXM_K1B_WALK": "1"}]
+        for env in variants:
+            with monkeypatch.context() as mp:
+                for k, v in env.items():
+                    mp.setenv(k, v)
+                m = rxm.Matcher(t, 0)
+            engines_seen.add((rxm.ENGINE_NAMES[m.plan().engine], tuple(sorted(env.items()))))
+            got = m.match_host(chars, off)
+            assert np.array_equal(got, bits), (tag, env, [strings[i] for i in np.nonzero(got != bits)[0][:3]])
+            if not env:
+                assert np.array_equal(m.match_text_host(b" ".join(strings)), bits), ("text", tag)
+            assert m.overflow_count() == 0
+            m.close()
+    names = {e for e, _ in engines_seen}
+    assert {"K1_DFA", "K1_BITSET", "K2_THREAD", "K3_WARP"} <= names

@@ -1,0 +1,30 @@
+"""Debug helper: run the random-expression corpus through every device engine and list failures."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import helpers as H
+from cases import load_fuzz_corpus
+rxm = H.rxm
+bad = 0
+for regex, flags, kind, t, strings, bits in load_fuzz_corpus(sys.argv[1] if len(sys.argv) > 1 else None):
+    chars, off = H.make_batch(strings)
+    variants = [{}] + ([{"RXM_MFA_ENGINE": "k2"}, {"RXM_MFA_ENGINE": "k3"}] if kind == "mfa" else
+                       [{"RXM_NFA_ENGINE": "bitset"}, {"RXM_NFA_ENGINE": "bitset", "RXM_K1B_WALK": "1"}])
+    for env in variants:
+        for k in ("RXM_MFA_ENGINE", "RXM_NFA_ENGINE", "RXM_K1B_WALK"):
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        try:
+            m = rxm.Matcher(t, 0)
+        except rxm.RxmError as e:
+            print("UPLOAD", regex, flags, env, e, "states", t.c.n_states, "edges", t.c.n_edges, "cells", t.c.n_cells); bad += 1
+            continue
+        try:
+            got = m.match_host(chars, off)
+            if not np.array_equal(got, bits):
+                print("BITS", regex, flags, env, rxm.ENGINE_NAMES[m.plan().engine], int((got != bits).sum())); bad += 1
+        except rxm.RxmError as e:
+            print("MATCH", regex, flags, env, rxm.ENGINE_NAMES[m.plan().engine], e.status, "states", t.c.n_states, "edges", t.c.n_edges, "cells", t.c.n_cells); bad += 1
+        m.close()
+print("failures", bad)
