@@ -482,7 +482,9 @@ extern "C" int rxm_match_text(rxm_handle h, const uint8_t *text, uint64_t nbytes
     if (!m->d_tok_result) CU(cudaMalloc(reinterpret_cast<void **>(&m->d_tok_result), 64));
     rxm::TokWork w{m->d_tok_masks, m->d_tok_counts, m->cap_tok_blocks, m->d_tok_result};
     int launched = 0;
-    int st = rxm::tok_launch(d_text, nbytes, m->d_tok_begin, m->d_tok_end, out_cap, w, m->sm_count, stream, &launched);
+    // one span more than the caller has room for: an `exit` standing right behind the last token
+    // that fits must still be seen as the sentinel
+    int st = rxm::tok_launch(d_text, nbytes, m->d_tok_begin, m->d_tok_end, out_cap + 1, w, m->sm_count, stream, &launched);
     m->launches += uint64_t(launched);
     if (st != RXM_OK) return st;
     unsigned long long res[2] = {0, 0};

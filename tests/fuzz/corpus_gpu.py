@@ -1,7 +1,9 @@
-"""Debug helper: run the random-expression corpus through every device engine and list failures."""
+"""Test helper (uses the oracle loader of tests/helpers.py): run a random-expression corpus --
+the committed one or a larger one made by tests/golden/make_fuzz_corpus.py -- through every device
+engine and list the cases that differ from the reference's bits.  python tests/fuzz/corpus_gpu.py [corpus.jsonl]"""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+TESTS = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, TESTS)
 import numpy as np
 import helpers as H
 from cases import load_fuzz_corpus

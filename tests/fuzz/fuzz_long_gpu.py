@@ -2,10 +2,10 @@
 expression of tests/golden/fuzz/corpus.jsonl, strings are sampled from its language with heavily
 pumped stars (up to several thousand letters, long backreference blocks), mixed with near misses,
 in batches large enough for the tile-sorted hand-out order (>= 16384 strings); every device engine
-against the C restatement (oracle/, the checker).  python tools/fuzz_long_gpu.py [n_expr] [n_strings] [seed]"""
+against the C restatement (oracle/, the checker).  python tests/fuzz/fuzz_long_gpu.py [n_expr] [n_strings] [seed]"""
 import os, random, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+TESTS = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, TESTS)
 import numpy as np
 import helpers as H
 from cases import load_fuzz_corpus

@@ -513,3 +513,40 @@ def test_random_expression_corpus_on_device(monkeypatch):
             m.close()
     names = {e for e, _ in engines_seen}
     assert {"K1_DFA", "K1_BITSET", "K2_THREAD", "K3_WARP"} <= names
+
+
+def test_match_text_random_byte_soup():
+    """Tokeniser fuzz: texts of random bytes (letters, every whitespace kind in runs of random
+    length, NUL, high bytes, the word `exit` sprinkled in) of 0 .. 300 KB against bytes.split() +
+    the oracle, at every alignment of the device pointer mod 16."""
+    import torch
+    t, _, _ = load_case("nfa_config2")
+    m = rxm.Matcher(t, 0)
+    rng = np.random.default_rng(77)
+    pool = [b"a", b"b", b"a", b"b", b"ab", b"aaba", b" ", b"\n", b"\t", b"\r", b"\v", b"\f", b"  ", b"\n\n\n",
+            b"\x00", b"\xa0", b"\x85", b"\x1f", b"z", b"exi", b"xit"]
+    for rounds, (lo, hi, p_exit) in enumerate([(0, 40, 0.0), (0, 40, 0.2), (100, 3000, 0.0), (100, 3000, 0.01),
+                                                (20000, 300000, 0.0), (20000, 300000, 0.00002)] * 3):
+        k = int(rng.integers(lo, hi + 1))
+        idx = rng.integers(0, len(pool), size=k)
+        parts = [pool[i] for i in idx]
+        if p_exit:
+            for j in np.nonzero(rng.random(k) < p_exit)[0]:
+                parts[j] = b" exit "
+        text = b"".join(parts)
+        toks = _ref_tokens(text)
+        got = m.match_text_host(text)
+        assert len(got) == len(toks), (rounds, len(got), len(toks))
+        assert m.saw_exit.value == (1 if b"exit" in text.split() else 0)
+        if toks:
+            chars, off = H.make_batch(toks)
+            assert np.array_equal(got, H.oracle_bits(t, chars, off)), rounds
+        # device pointers at a random alignment
+        shift = int(rng.integers(0, 16))
+        d = torch.cat([torch.full((shift,), 32, dtype=torch.uint8), torch.frombuffer(bytearray(text) or bytearray(b" "), dtype=torch.uint8)]).cuda()
+        out = torch.empty(max(1, len(toks)), dtype=torch.uint8, device="cuda")
+        n = m.match_text_ptrs(d.data_ptr() + shift, len(text), out.data_ptr(), out.numel())
+        torch.cuda.synchronize()
+        assert n == len(toks)
+        assert np.array_equal(out[:n].cpu().numpy(), got)
+    m.close()

@@ -1,11 +1,12 @@
 """Tuning helper: K1B (bit-set engine) throughput on the 77-node nfa_blowup automaton."""
-import os, sys, time
+import importlib.util, os, sys, time
+import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "tests"))
-import helpers as H, torch
-from cases import load_case
-t, _, _ = load_case("nfa_blowup")
-m = H.rxm.Matcher(t, 0)
+spec = importlib.util.spec_from_file_location("rxm", os.path.join(ROOT, "re2-modification_b200", "rxm.py"))
+rxm = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(rxm)
+t = rxm.Tables.load(os.path.join(ROOT, "tests", "golden", "cases", "nfa_blowup.rxt"))
+m = rxm.Matcher(t, 0)
 n = 200000
 rng = torch.Generator(device="cuda").manual_seed(1)
 lens = torch.randint(64, 4097, (n,), device="cuda", generator=rng)
