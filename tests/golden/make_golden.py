@@ -44,6 +44,9 @@ NFA_EXPRESSIONS = [
     ("abba", "(ab|ba)*", ["abba", "abab", "aba"]),
     ("third", "(a|b)*a(a|b)(a|b)", ["abb", "aaa", "bab"]),
     ("lit", "abcabc", ["abcabc", "abcab", "abcabcc"]),
+    # an `a`, six letters, a `b`: 2^8 active sets -> more than 128, K1's two-lookup table form (K1_CLASSED)
+    ("mid", "(a|b)*a" + "(a|b)" * 6 + "b(a|b)*",
+     ["a" + "a" * 6 + "b", "b" * 30, "ab" * 20, "a" * 7 + "b", "a" * 6 + "b", "ba" + "b" * 6 + "ba"]),
     # an `a`, twelve letters, a `b`: 2^14 active sets in either reading direction -> beyond the
     # table engine's limit, runs on the bit-set engine (K1B); Thompson branch, 77 nodes
     ("blowup", "(a|b)*a" + "(a|b)" * 12 + "b(a|b)*",

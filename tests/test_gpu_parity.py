@@ -79,7 +79,7 @@ def _random_batch(rng, n, lo, hi, alphabet):
     return chars, off
 
 
-@pytest.mark.parametrize("name", ["nfa_config2", "nfa_quirk", "nfa_abb", "nfa_dots", "nfa_third"])
+@pytest.mark.parametrize("name", ["nfa_config2", "nfa_quirk", "nfa_abb", "nfa_dots", "nfa_third", "nfa_mid"])
 def test_nfa_random_batches_vs_oracle(name):
     t, _, _ = load_case(name)
     rng = np.random.default_rng(123)
@@ -150,6 +150,12 @@ def test_plan_reports_engine():
     m = rxm.Matcher(t, 0)
     assert rxm.ENGINE_NAMES[m.plan().engine] in ("K2_THREAD", "K3_WARP")
     m.close()
+    # 2^8 active sets: still a table, in its two-lookup form (byte class, then [class][set] u16)
+    t, _, _ = load_case("nfa_mid")
+    m = rxm.Matcher(t, 0)
+    p = m.plan()
+    assert rxm.ENGINE_NAMES[p.engine] == "K1_DFA" and 128 < p.dfa_states <= 4096 and p.dfa_stride == 1
+    m.close()
 
 
 def test_mixed_host_device_pointers_are_rejected():
@@ -165,7 +171,7 @@ def test_mixed_host_device_pointers_are_rejected():
     m.close()
 
 
-@pytest.mark.parametrize("name", ["nfa_config2", "nfa_abb", "nfa_dots"])
+@pytest.mark.parametrize("name", ["nfa_config2", "nfa_abb", "nfa_dots", "nfa_mid"])
 def test_k1_every_length_and_alignment(name):
     """Forward (config2) and right-to-left (abb, dots: reversed Glushkov) scans: every
     length 0..300 at every start alignment mod 16, plus a few long strings, so that the
