@@ -33,8 +33,9 @@ def load_fuzz_corpus(path=None):
     """Random-expression fixtures (tests/golden/make_fuzz_corpus.py; bits from the reference's own code).
     -> list of (regex, flags, kind, Tables, list[bytes], bits uint8[n])"""
     out = []
-    with open(path or os.path.join(H.GOLDEN, "fuzz", "corpus.jsonl")) as f:
-        for line in f:
+    paths = [path] if path else [os.path.join(H.GOLDEN, "fuzz", "corpus.jsonl"), os.path.join(H.GOLDEN, "fuzz", "corpus_9cells.jsonl")]
+    for pth in paths:
+        for line in open(pth):
             c = json.loads(line)
             out.append((c["regex"], c["flags"], c["kind"], H.rxm.Tables(c["tables"]),
                         [s.encode() for s in c["strings"]],

@@ -11,7 +11,8 @@ rxm = H.rxm
 bad = 0
 for regex, flags, kind, t, strings, bits in load_fuzz_corpus(sys.argv[1] if len(sys.argv) > 1 else None):
     chars, off = H.make_batch(strings)
-    variants = [{}] + ([{"RXM_MFA_ENGINE": "k2"}, {"RXM_MFA_ENGINE": "k3"}] if kind == "mfa" else
+    variants = [{}] + ([{"RXM_MFA_ENGINE": "k2"}] if kind == "mfa" and t.c.n_cells > 4 else
+                       [{"RXM_MFA_ENGINE": "k2"}, {"RXM_MFA_ENGINE": "k3"}] if kind == "mfa" else
                        [{"RXM_NFA_ENGINE": "bitset"}, {"RXM_NFA_ENGINE": "bitset", "RXM_K1B_WALK": "1"}])
     for env in variants:
         for k in ("RXM_MFA_ENGINE", "RXM_NFA_ENGINE", "RXM_K1B_WALK"):

@@ -8,7 +8,7 @@ handle (front end crashes / loops, epsilon cycles, tables outside the device lim
 and counted.  The C restatement must agree with the reference on every kept case, or the script
 stops.  Output: tests/golden/fuzz/corpus.jsonl (one case per line).
 
-Needs /root/reference builds (oracle/_ref, bin/rxm_compile).  Run:  python tests/golden/make_fuzz_corpus.py [n_cases] [seed] [output.jsonl]
+Needs /root/reference builds (oracle/_ref, bin/rxm_compile).  Run:  python tests/golden/make_fuzz_corpus.py [n_cases] [seed] [output.jsonl] [max_cell]
 """
 from __future__ import annotations
 
@@ -25,6 +25,9 @@ sys.path.insert(0, os.path.dirname(HERE))
 import helpers as H  # noqa: E402
 
 
+MAX_CELL = 3  # cell names drawn from 1..MAX_CELL (argv[4]; 9 exercises the engines' many-cell paths)
+
+
 def gen(rng: random.Random, depth: int, cells: list[int], under_star: bool):
     """-> AST: ("lit", c) | ("any",) | ("ref", k) | ("cat", x, y) | ("alt", x, y) | ("star", x) | ("mem", x, k)"""
     r = rng.random()
@@ -34,7 +37,7 @@ def gen(rng: random.Random, depth: int, cells: list[int], under_star: bool):
             return ("lit", rng.choice("aabbc"))
         if x < 0.78:
             return ("any",)
-        return ("ref", rng.choice(cells) if cells and rng.random() < 0.85 else rng.randint(1, 3))
+        return ("ref", rng.choice(cells) if cells and rng.random() < 0.85 else rng.randint(1, MAX_CELL))
     if r < 0.55:
         return ("cat", gen(rng, depth - 1, cells, under_star), gen(rng, depth - 1, cells, under_star))
     if r < 0.70:
@@ -43,7 +46,7 @@ def gen(rng: random.Random, depth: int, cells: list[int], under_star: bool):
         if rng.random() < 0.5:
             return ("star", ("lit", rng.choice("abc")))
         return ("star", gen(rng, depth - 1, cells, True))
-    k = rng.randint(1, 3)
+    k = rng.randint(1, MAX_CELL)
     inner = gen(rng, depth - 1, cells, under_star)
     if k not in cells:
         cells.append(k)
@@ -115,6 +118,9 @@ def main():
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 2026
     if not H.have_reference():
         raise SystemExit("needs oracle/_ref (make -C oracle) and bin/rxm_compile (make -C re2-modification_b200 front)")
+    global MAX_CELL
+    if len(sys.argv) > 4:
+        MAX_CELL = int(sys.argv[4])
     rng = random.Random(seed)
     kept, skipped, seen = [], {"compile": 0, "tables": 0, "reference": 0, "dup": 0}, set()
     attempts = 0
@@ -163,7 +169,7 @@ def main():
                      "bits": "".join(str(int(b)) for b in ref)})
         if len(kept) % 10 == 0:
             print(len(kept), "kept;", skipped, flush=True)
-    out_path = sys.argv[3] if len(sys.argv) > 3 else os.path.join(HERE, "fuzz", "corpus.jsonl")
+    out_path = sys.argv[3] if len(sys.argv) > 3 and sys.argv[3] != "-" else os.path.join(HERE, "fuzz", "corpus.jsonl")
     with open(out_path, "w") as f:
         for c in kept:
             f.write(json.dumps(c) + "\n")
