@@ -20,24 +20,56 @@ namespace rxm {
 namespace {
 
 constexpr uint64_t K3_EMPTY = ~0ull;
+#ifdef RXM_SIMT_HOST
+constexpr int K3_WARPS = 1;  // tests/hostsim/k3_simt.cpp: one emulated warp
+#else
 constexpr int K3_WARPS = 8;
+#endif
 
 __device__ __forceinline__ uint64_t k3_key(uint32_t first, uint32_t flags, uint32_t born) {
     return (uint64_t(first) << 36) | (uint64_t(lowvar(flags)) << 32) | born;
 }
 
-// mem[pa, pa+L) == mem[pb, pb+L) ?  Whole warp, 4 bytes per lane per iteration, any alignment.
+// Collectives of a tile.  The tiles of a warp run in lock-step and ALL control flow around a
+// collective is warp-uniform (trip counts are the maximum over the warp's tiles, the bodies are
+// predicated), so every vote / shuffle is issued once with the full mask and a tile takes its own
+// bits.  With per-tile masks the compiler has to group the lanes by mask value first (MATCH.ANY +
+// one VOTE / ENDCOLLECTIVE round per tile): measured at 28 % of the stall samples of the kernel.
 template <int TILE>
-__device__ __forceinline__ bool warp_span_equal(const uint8_t *pa, const uint8_t *pb, uint32_t L, uint32_t lane,
-                                                uint32_t tmask) {
-    if (pa == pb || L == 0) return true;
+struct TileOps {
+    static constexpr uint32_t ALL = 0xffffffffu;
+    static constexpr uint32_t TM = (TILE == 32) ? 0xffffffffu : ((1u << (TILE & 31)) - 1u);
+    uint32_t tshift;  // first warp lane of this tile
+    __device__ __forceinline__ uint32_t ballot(bool p) const { return (__ballot_sync(ALL, p) >> tshift) & TM; }
+    __device__ __forceinline__ bool any(bool p) const { return ballot(p) != 0u; }
+    __device__ __forceinline__ bool all(bool p) const { return ballot(p) == TM; }
+    __device__ __forceinline__ uint32_t min(uint32_t x) const {
+        if (TILE == 32) return __reduce_min_sync(ALL, x);
+#pragma unroll
+        for (int d = TILE / 2; d >= 1; d >>= 1) {
+            const uint32_t y = __shfl_xor_sync(ALL, x, d);
+            x = y < x ? y : x;
+        }
+        return x;
+    }
+};
+
+// mem[pa, pa+L) == mem[pb, pb+L) ?  per tile, 4 bytes per lane per iteration, any alignment.
+// Called by the whole warp; a tile without a comparison passes L == 0.
+template <int TILE>
+__device__ __forceinline__ bool tile_span_equal(const TileOps<TILE> &to, const uint8_t *pa, const uint8_t *pb, uint32_t L,
+                                                uint32_t lane) {
+    bool eq = true;
+    bool live = !(pa == pb || L == 0);
     const uint32_t ba = uint32_t(reinterpret_cast<uintptr_t>(pa)) & 3u, bb = uint32_t(reinterpret_cast<uintptr_t>(pb)) & 3u;
     const uint32_t *wa = reinterpret_cast<const uint32_t *>(pa - ba);
     const uint32_t *wb = reinterpret_cast<const uint32_t *>(pb - bb);
-    for (uint32_t base = 0; base < L; base += 4u * TILE) {
+    for (uint32_t base = 0;; base += 4u * TILE) {
+        live = live && base < L;
+        if (!__any_sync(TileOps<TILE>::ALL, live)) break;
         const uint32_t off = base + lane * 4u;
         bool ne = false;
-        if (off < L) {
+        if (live && off < L) {
             const uint32_t rem = L - off, take = rem < 4u ? rem : 4u;
             const uint32_t idx = off >> 2;
             const uint32_t a0 = __ldg(wa + idx), b0 = __ldg(wb + idx);
@@ -47,9 +79,12 @@ __device__ __forceinline__ bool warp_span_equal(const uint8_t *pa, const uint8_t
             if (take < 4u) x &= (1u << (8u * take)) - 1u;
             ne = x != 0u;
         }
-        if (__any_sync(tmask, ne)) return false;
+        if (to.any(ne)) {
+            eq = false;
+            live = false;
+        }
     }
-    return true;
+    return eq;
 }
 
 template <int NC>
@@ -118,20 +153,21 @@ __device__ __forceinline__ uint32_t k3_need(uint32_t flags, const uint32_t *len)
 
 // TILE lanes cooperate on one string (TILE = 32: the whole warp; 16 / 8: two / four strings
 // per warp when the edge programs are short -- the items of a step fit one pass anyway).
-template <int NC, int TILE>
 // Several strings per warp (TILE < 32): throughput work, issue-bound -- 5 blocks per SM (48
 // registers, a few spilled words) measured 17 % faster than 3 blocks at 73 registers.  TILE == 32
 // is chosen for long strings, where the single longest string bounds the batch: full registers.
+template <int NC, int TILE>
 __global__ void __launch_bounds__(K3_WARPS * 32, TILE == 32 ? 1 : 5)
 k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, uint32_t items_in_smem,
                    const uint8_t *__restrict__ chars, const Spans sp, const K1Rec *__restrict__ recs, uint64_t n,
                    uint8_t *__restrict__ out, unsigned long long *__restrict__ overflow,
                    unsigned long long *__restrict__ next_string) {
-    extern __shared__ __align__(16) uint8_t smem[];
+    RXM_DYN_SMEM(smem);
+    constexpr uint32_t ALL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & (TILE - 1u);              // rank inside the tile
     const uint32_t tile = threadIdx.x / TILE;                     // tile index inside the block
-    const uint32_t tshift = (threadIdx.x & 31u) & ~(TILE - 1u);   // first warp lane of this tile
-    const uint32_t FULL = (TILE == 32) ? 0xffffffffu : (((1u << TILE) - 1u) << tshift);
+    TileOps<TILE> to;
+    to.tshift = (threadIdx.x & 31u) & ~(TILE - 1u);
     // ---- block-shared program tables ----
     uint32_t *s_begin = reinterpret_cast<uint32_t *>(smem);
     uint32_t *s_count = s_begin + n_keys;
@@ -149,10 +185,10 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
     }
     __syncthreads();
     const ProgItem *items = items_in_smem ? s_items : gp.items;
-    // ---- per-warp frontier: two buffers of SP slots ----
+    // ---- per-tile frontier: two buffers of SP slots ----
     const uint32_t SP = (v.n_states + TILE - 1u) & ~(TILE - 1u);  // slots, a whole number of tile passes
-    const size_t per_warp = size_t(SP) * 2 * (8 + 4 + 8 * NC) + size_t(SP) * 12 + 16;
-    uint8_t *wb = smem + o + size_t(tile) * per_warp;
+    const size_t per_tile = size_t(SP) * 2 * (8 + 4 + 8 * NC) + size_t(SP) * 12 + 16;
+    uint8_t *wb = smem + o + size_t(tile) * per_tile;
     uint64_t *keys = reinterpret_cast<uint64_t *>(wb);                    // [2][SP]
     uint32_t *flg = reinterpret_cast<uint32_t *>(wb + size_t(SP) * 16);   // [2][SP]
     uint32_t *stt = flg + 2 * SP;                                         // [2][SP][NC]
@@ -161,71 +197,74 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
     uint32_t *l_pb = l_node + SP;                                         // [SP]   first program item,
     uint32_t *l_off = l_pb + SP;                                          // [SP+1] start in the laid-out items
 
-    // All tiles of a warp run the loop below in LOCK-STEP: one iteration is, per tile, either
-    // "take the next string" or "one step of the string in hand".  Tiles therefore execute the
-    // same instructions on different strings instead of drifting apart (which would serialise
-    // them); a tile that is out of work idles until every tile of the warp is.
+    // All tiles of a warp run the loop below in LOCK-STEP: one iteration is, per tile, "take the
+    // next string" (when it has none) and then "one step of the string in hand".  Control flow is
+    // warp-uniform -- a tile without work rides along predicated off -- so the tiles execute the
+    // same instructions on different strings and every collective runs once for the whole warp.
     bool have_str = false, exhausted = false;
     unsigned long long si = 0;
     const uint8_t *s = nullptr;
     uint32_t n32 = 0, cur = 0, i = 0;
     bool ovf = false;
     for (;;) {
-        if (TILE != 32) __syncwarp(0xffffffffu);
-        if (!have_str && !exhausted) {
-            if (lane == 0) si = atomicAdd(next_string, 1ull);
-            si = __shfl_sync(FULL, si, 0, TILE);
-            bool skip = false;
-            if (recs) {
-                // strings are handed out in the tile sort's order -- group g (32 records) of every tile
-                // of 4096 before group g+1 of any: the long strings of the whole batch go first, so
-                // the tail of the launch is made of short ones
-                const uint64_t ntiles = (n + K1_TILE_STRINGS - 1) / K1_TILE_STRINGS;
-                const uint64_t g = si / (ntiles * 32u), rem = si - g * (ntiles * 32u);
-                const uint64_t tl = rem >> 5, pos = tl * K1_TILE_STRINGS + g * 32u + (rem & 31u);
-                if (g >= K1_TILE_STRINGS / 32u) si = n;                              // all handed out
-                else if (pos >= min(n, (tl + 1u) * K1_TILE_STRINGS)) skip = true;    // the last tile is short
-                else si = recs[pos].idx;
-            }
-            if (skip) {
-                // nothing this round; the next iteration takes another ticket
-            } else if (si >= n) {
-                exhausted = true;
-            } else {
-                const uint64_t sb = sp.begin[si], se = sp.end[si];
-                if (se - sb >= (1ull << 28)) {  // first must fit 28 bits of the order key
-                    if (lane == 0) {
-                        atomicAdd(overflow, 1ull);
-                        out[si] = 0;
-                    }
+        const bool want = !have_str && !exhausted;
+        if (__any_sync(ALL, want)) {
+            unsigned long long t = 0;
+            if (want && lane == 0) t = atomicAdd(next_string, 1ull);
+            t = __shfl_sync(ALL, t, 0, TILE);
+            if (want) {  // no collective in here
+                si = t;
+                bool skip = false;
+                if (recs) {
+                    // strings are handed out in the tile sort's order -- group g (32 records) of every tile
+                    // of 4096 before group g+1 of any: the long strings of the whole batch go first, so
+                    // the tail of the launch is made of short ones
+                    const uint64_t ntiles = (n + K1_TILE_STRINGS - 1) / K1_TILE_STRINGS;
+                    const uint64_t g = si / (ntiles * 32u), rem = si - g * (ntiles * 32u);
+                    const uint64_t tl = rem >> 5, pos = tl * K1_TILE_STRINGS + g * 32u + (rem & 31u);
+                    if (g >= K1_TILE_STRINGS / 32u) si = n;                              // all handed out
+                    else if (pos >= min(n, (tl + 1u) * K1_TILE_STRINGS)) skip = true;    // the last tile is short
+                    else si = recs[pos].idx;
+                }
+                if (skip) {
+                    // nothing this round; the next iteration takes another ticket
+                } else if (si >= n) {
+                    exhausted = true;
                 } else {
-                    s = chars + sb;
-                    n32 = uint32_t(se - sb);
-                    for (uint32_t q = lane; q < 2 * SP; q += TILE) keys[q] = K3_EMPTY;
-                    __syncwarp(FULL);
-                    if (lane == 0) {  // (0, start, {})  mfa.cpp:217-219
-                        keys[v.start] = k3_key(0, 0, 0);
-                        flg[v.start] = 0;
+                    const uint64_t sb = sp.begin[si], se = sp.end[si];
+                    if (se - sb >= (1ull << 28)) {  // first must fit 28 bits of the order key
+                        if (lane == 0) {
+                            atomicAdd(overflow, 1ull);
+                            out[si] = 0;
+                        }
+                    } else {
+                        s = chars + sb;
+                        n32 = uint32_t(se - sb);
+                        for (uint32_t q = lane; q < 2 * SP; q += TILE) {
+                            const bool st0 = (q == v.start);  // (0, start, {})  mfa.cpp:217-219
+                            keys[q] = st0 ? k3_key(0, 0, 0) : K3_EMPTY;
+                            if (st0) flg[q] = 0;
+                        }
+                        cur = 0;
+                        i = 0;
+                        ovf = false;
+                        have_str = true;
                     }
-                    __syncwarp(FULL);
-                    cur = 0;
-                    i = 0;
-                    ovf = false;
-                    have_str = true;
                 }
             }
+            __syncwarp(ALL);
         }
-        if (__all_sync(0xffffffffu, exhausted && !have_str)) break;
-        if (!have_str) continue;
+        if (__all_sync(ALL, exhausted && !have_str)) break;
+        const bool act = have_str;  // this tile has a string in hand
         bool finished = false;
         {
             uint64_t *K = keys + cur * SP, *KN = keys + (cur ^ 1u) * SP;
             // ---- A. list the live configurations and lay their programs end to end ----
             uint32_t m = 0, T = 0;
             bool any_active = false;
-            for (uint32_t q = lane; q < SP; q += TILE) {  // tile-uniform trip count
-                const uint64_t k = K[q];
-                KN[q] = K3_EMPTY;
+            for (uint32_t q = lane; q < SP; q += TILE) {  // warp-uniform trip count
+                const uint64_t k = act ? K[q] : K3_EMPTY;
+                if (act) KN[q] = K3_EMPTY;
                 const bool lv = (k != K3_EMPTY);
                 uint32_t pb = 0, pc = 0;
                 if (lv) {
@@ -249,11 +288,11 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
                         else pc = s_count[pkey] & kProgCountMask;
                     }
                 }
-                const uint32_t bal = (__ballot_sync(FULL, lv) >> tshift) & ((TILE == 32) ? 0xffffffffu : ((1u << TILE) - 1u));
+                const uint32_t bal = to.ballot(lv);
                 uint32_t inc = pc;  // inclusive scan of the item counts over the tile's lanes
 #pragma unroll
                 for (int d = 1; d < TILE; d <<= 1) {
-                    const uint32_t u = __shfl_up_sync(FULL, inc, d, TILE);
+                    const uint32_t u = __shfl_up_sync(ALL, inc, d, TILE);
                     if (int(lane) >= d) inc += u;
                 }
                 if (lv) {
@@ -263,25 +302,27 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
                     l_off[j] = T + inc - pc;
                 }
                 m += __popc(bal);
-                T += __shfl_sync(FULL, inc, TILE - 1, TILE);
+                T += __shfl_sync(ALL, inc, TILE - 1, TILE);
             }
-            ovf = __any_sync(FULL, ovf);
-            any_active = __any_sync(FULL, any_active);
-            if (i < n32 && m == 0) finished = true;  // :224-225
-            else {
-            if (lane == 0) l_off[m] = T;
-            __syncwarp(FULL);
-            const uint32_t ch = (i < n32) ? uint32_t(v.reversed ? s[n32 - 1u - i] : s[i]) : 0u;
-            const uint32_t digit_bit = (i < n32 && ch >= '1' && ch <= '9') ? (1u << (ch - '1')) : 0u;
+            ovf = to.any(ovf);
+            any_active = to.any(any_active);
+            const bool dead = act && i < n32 && m == 0;  // :224-225
+            const bool run = act && !dead;
+            if (dead) finished = true;
+            if (run && lane == 0) l_off[m] = T;
+            __syncwarp(ALL);
+            const uint32_t ch = (run && i < n32) ? uint32_t(v.reversed ? s[n32 - 1u - i] : s[i]) : 0u;
+            const uint32_t digit_bit = (run && i < n32 && ch >= '1' && ch <= '9') ? (1u << (ch - '1')) : 0u;
             bool next_near = false;  // the new set holds a configuration that is active (or dead) at step i+1
             // ---- B. expand: one item per lane per pass ----
-            for (uint32_t t0 = 0; t0 < T; t0 += TILE) {
+            const uint32_t Tmax = __reduce_max_sync(ALL, run ? T : 0u);
+            for (uint32_t t0 = 0; t0 < Tmax; t0 += TILE) {
                 const uint32_t tt = t0 + lane;
                 bool have = false, need_cmp = false;
                 uint32_t cmp_vs = 0, cmp_L = 0;
                 K3Cfg<NC> cand, root;
                 ProgItem it{};
-                if (tt < T) {
+                if (run && tt < T) {
                     uint32_t j = 0;
                     while (l_off[j + 1] <= tt) j++;
                     const uint32_t x = tt - l_off[j], rn = l_node[j];
@@ -338,19 +379,22 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
                         }
                     }
                 }
-                // backreference blocks: the whole warp compares each pending span
-                uint32_t cm = (__ballot_sync(FULL, need_cmp) >> tshift) & ((TILE == 32) ? 0xffffffffu : ((1u << TILE) - 1u));
+                // backreference blocks: the whole tile compares each pending span; the loop runs
+                // until the last tile of the warp has none left
+                uint32_t cm = to.ballot(need_cmp);
                 bool cmp_ok = false;
-                while (cm) {
-                    const int src = __ffs(int(cm)) - 1;
-                    const uint32_t vs = __shfl_sync(FULL, cmp_vs, src, TILE), L = __shfl_sync(FULL, cmp_L, src, TILE);
+                while (__any_sync(ALL, cm != 0u)) {
+                    const int src = cm ? __ffs(int(cm)) - 1 : 0;
+                    const uint32_t vs = __shfl_sync(ALL, cmp_vs, src, TILE);
+                    uint32_t L = __shfl_sync(ALL, cmp_L, src, TILE);
+                    if (!cm) L = 0;
                     bool eq;
-                    if (!v.reversed) eq = warp_span_equal<TILE>(s + vs, s + i, L, lane, FULL);
-                    else eq = warp_span_equal<TILE>(s + (n32 - vs - L), s + (n32 - i - L), L, lane, FULL);
+                    if (!v.reversed) eq = tile_span_equal<TILE>(to, s + vs, s + i, L, lane);
+                    else eq = tile_span_equal<TILE>(to, s + (n32 - vs - L), s + (n32 - i - L), L, lane);
                     // every lane waiting for this very span takes the answer (e.g. &1 read from two nodes)
-                    const bool mine = need_cmp && cmp_vs == vs && cmp_L == L;
+                    const bool mine = need_cmp && cm && cmp_vs == vs && cmp_L == L;
                     if (mine) cmp_ok = eq;
-                    cm &= ~((__ballot_sync(FULL, mine) >> tshift) & ((TILE == 32) ? 0xffffffffu : ((1u << TILE) - 1u)));
+                    cm &= ~to.ballot(mine);
                 }
                 if (need_cmp && cmp_ok) {
                     const uint32_t stamp = cand.born;
@@ -369,7 +413,7 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
                     k64 = k3_key(cand.first, cand.flags, cand.born);
                     atomicMin(reinterpret_cast<unsigned long long *>(&KN[cand.node]), (unsigned long long)k64);
                 }
-                __syncwarp(FULL);
+                __syncwarp(ALL);
                 if (have && KN[cand.node] == k64) {
                     const uint32_t slot = (cur ^ 1u) * SP + cand.node;
                     flg[slot] = cand.flags;
@@ -379,20 +423,22 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
                         lnn[slot * NC + k] = cand.len[k];
                     }
                 }
-                __syncwarp(FULL);
+                __syncwarp(ALL);
             }
-            cur ^= 1u;  // states = new_states (:212)
-            __syncwarp(FULL);
+            if (run) cur ^= 1u;  // states = new_states (:212)
+            __syncwarp(ALL);
+            next_near = to.any(next_near);
             bool jumped = false;
-            if (ovf || i == n32) finished = true;
+            if (run && (ovf || i == n32)) finished = true;
             // ---- C0. every configuration of the new set waits (first >= i + 2) and is reproduced
             //          unchanged by a step (kProgStable): the steps up to the first activation /
             //          reversed-mode pruning are the identity and are not run at all ----
-            else if (i + 2 < n32 && !__any_sync(FULL, next_near)) {
+            const bool c0 = run && !finished && i + 2 < n32 && !next_near;
+            if (__any_sync(ALL, c0)) {
                 bool stable = true, any = false;
                 uint32_t ev = n32;
                 for (uint32_t q = lane; q < SP; q += TILE) {
-                    const uint64_t ka = keys[cur * SP + q];
+                    const uint64_t ka = c0 ? keys[cur * SP + q] : K3_EMPTY;
                     if (ka == K3_EMPTY) continue;
                     any = true;
                     const uint32_t fa = uint32_t(ka >> 36), sa = cur * SP + q, fla = flg[sa];
@@ -405,19 +451,23 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
                         if (ps < ev) ev = ps;
                     }
                 }
-                stable = __all_sync(FULL, stable) && __any_sync(FULL, any);
-                ev = __reduce_min_sync(FULL, ev);
-                if (stable && ev > i + 1) {
+                const uint32_t nstable = to.ballot(!stable);  // two votes, both by every tile: no short circuit
+                any = to.any(any);
+                stable = (nstable == 0u) && any;
+                ev = to.min(ev);
+                if (c0 && stable && ev > i + 1) {
                     i = ev - 1;  // the increment below makes the next step ev
                     jumped = true;
                 }
             }
             // ---- C. fast-forward over idle steps (see MfaSim::run); only after a step in which
             //         no configuration was active ----
-            if (!finished && !jumped && !any_active && i + 1 < n32) {
+            const bool c1 = run && !finished && !jumped && !any_active && i + 1 < n32;
+            if (__any_sync(ALL, c1)) {
                 bool same = true;
                 uint32_t ev = n32;
                 for (uint32_t q = lane; q < SP; q += TILE) {
+                    if (!c1) continue;
                     const uint64_t ka = keys[cur * SP + q], kb = keys[(cur ^ 1u) * SP + q];
                     const bool va = ka != K3_EMPTY, vb2 = kb != K3_EMPTY;
                     if (va != vb2) same = false;
@@ -443,14 +493,13 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
                         }
                     }
                 }
-                same = __all_sync(FULL, same);
-                ev = __reduce_min_sync(FULL, ev);
+                same = to.all(same);
+                ev = to.min(ev);
                 // prog_stamp does not depend on the step index: further idle steps reproduce this
                 // set bit for bit, so jump straight to the event step (the increment below adds 1)
-                if (same && ev > i + 1) i = ev - 1;
+                if (c1 && same && ev > i + 1) i = ev - 1;
             }
-            }  // else of (i < n32 && m == 0)
-            i++;
+            if (run) i++;
         }
         if (finished) {
             if (lane == 0) {
@@ -461,12 +510,13 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
                     out[si] = keys[cur * SP + v.finish] != K3_EMPTY ? 1 : 0;  // :230-235
                 }
             }
-            __syncwarp(FULL);
             have_str = false;
         }
+        __syncwarp(ALL);
     }
 }
 
+#ifndef RXM_SIMT_HOST
 template <int NC, int TILE>
 int launch_k3(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n_keys, const uint8_t *d_chars,
               Spans spans, const K1Rec *d_recs, uint64_t n, uint8_t *d_out, unsigned long long *d_overflow,
@@ -508,8 +558,11 @@ int launch_k3_tile(uint32_t tile, const MfaView &v, const ProgView &gp, uint32_t
     return st;
 }
 
+#endif  // RXM_SIMT_HOST
+
 }  // namespace
 
+#ifndef RXM_SIMT_HOST
 int k3_launch(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n_keys, uint32_t n_cells,
               uint32_t tile, const uint8_t *d_chars, Spans spans, const K1Rec *d_recs, uint64_t n, uint8_t *d_out,
               unsigned long long *d_overflow, unsigned long long *d_next, int sm_count, cudaStream_t stream,
@@ -523,5 +576,6 @@ int k3_launch(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n
     if (st == RXM_OK) *launched = 1;
     return st;
 }
+#endif  // RXM_SIMT_HOST
 
 }  // namespace rxm

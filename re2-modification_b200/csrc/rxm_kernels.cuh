@@ -2,7 +2,14 @@
 #ifndef RXM_KERNELS_CUH
 #define RXM_KERNELS_CUH
 
+#ifdef RXM_SIMT_HOST
+// tests/hostsim compiles a kernel source for the host under tests/hostsim/simt_shim.hpp
+typedef void *cudaStream_t;
+#define RXM_DYN_SMEM(name) uint8_t *name = simt::S().smem
+#else
 #include <cuda_runtime.h>
+#define RXM_DYN_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
+#endif
 
 #include <cstdint>
 #include <string>
