@@ -20,6 +20,10 @@ namespace rxm {
 namespace {
 
 constexpr uint64_t K3_EMPTY = ~0ull;
+#ifndef RXM_K3_MIN_BLOCKS
+#define RXM_K3_MIN_BLOCKS 4  // blocks per SM the several-strings-per-warp kernels are compiled for: 64 registers, no spills
+                             // (config 3: 43.6 ms against 46.4 at 5 blocks / 48 registers and 44.6 at 3 / 80)
+#endif
 #ifdef RXM_SIMT_HOST
 constexpr int K3_WARPS = 1;  // tests/hostsim/k3_simt.cpp: one emulated warp
 #else
@@ -157,7 +161,7 @@ __device__ __forceinline__ uint32_t k3_need(uint32_t flags, const uint32_t *len)
 // registers, a few spilled words) measured 17 % faster than 3 blocks at 73 registers.  TILE == 32
 // is chosen for long strings, where the single longest string bounds the batch: full registers.
 template <int NC, int TILE>
-__global__ void __launch_bounds__(K3_WARPS * 32, TILE == 32 ? 1 : 5)
+__global__ void __launch_bounds__(K3_WARPS * 32, TILE == 32 ? 1 : RXM_K3_MIN_BLOCKS)
 k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, uint32_t items_in_smem,
                    const uint8_t *__restrict__ chars, const Spans sp, const K1Rec *__restrict__ recs, uint64_t n,
                    uint8_t *__restrict__ out, unsigned long long *__restrict__ overflow,
@@ -207,6 +211,9 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
     uint32_t n32 = 0, cur = 0, i = 0;
     bool ovf = false;
     for (;;) {
+#ifdef RXM_SIMT_HOST
+        if (threadIdx.x == 0) rxm_k3_simt_iterations++;  // tests/hostsim/k3_simt.cpp: lock-step iterations of the warp
+#endif
         const bool want = !have_str && !exhausted;
         if (__any_sync(ALL, want)) {
             unsigned long long t = 0;
@@ -314,6 +321,10 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
             const uint32_t ch = (run && i < n32) ? uint32_t(v.reversed ? s[n32 - 1u - i] : s[i]) : 0u;
             const uint32_t digit_bit = (run && i < n32 && ch >= '1' && ch <= '9') ? (1u << (ch - '1')) : 0u;
             bool next_near = false;  // the new set holds a configuration that is active (or dead) at step i+1
+            // what C0 needs to know about the new set, gathered from the lanes that write it: every
+            // configuration stable and waiting, and the earliest event (activation / reversed-mode pruning)
+            bool w_stable = true, w_any = false;
+            uint32_t w_ev = n32;
             // ---- B. expand: one item per lane per pass ----
             const uint32_t Tmax = __reduce_max_sync(ALL, run ? T : 0u);
             for (uint32_t t0 = 0; t0 < Tmax; t0 += TILE) {
@@ -422,6 +433,20 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
                         stt[slot * NC + k] = cand.start[k];
                         lnn[slot * NC + k] = cand.len[k];
                     }
+                    // A configuration written in this pass may still be replaced in a later pass of the
+                    // same step (T > TILE): the lanes then describe a superset of the new set, which can
+                    // only withhold the jump or shorten it -- the step it lands on is run as usual.
+                    const uint32_t pkey = (cand.node << gp.n_cells) | exists_mask_n<NC>(cand.flags);
+                    if (cand.first < i + 2u || cand.first == n32 || s_begin[pkey] == 0xffffffffu ||
+                        !(s_count[pkey] & kProgStable))
+                        w_stable = false;
+                    w_any = true;
+                    if (cand.first < w_ev) w_ev = cand.first;
+                    if (v.reversed) {
+                        const uint32_t need = k3_need<NC>(cand.flags, cand.len);  // fresh: not yet tested against mfa.cpp:141
+                        const uint32_t ps = need > n32 ? 0u : n32 - need + 1u;
+                        if (ps < w_ev) w_ev = ps;
+                    }
                 }
                 __syncwarp(ALL);
             }
@@ -432,30 +457,14 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
             if (run && (ovf || i == n32)) finished = true;
             // ---- C0. every configuration of the new set waits (first >= i + 2) and is reproduced
             //          unchanged by a step (kProgStable): the steps up to the first activation /
-            //          reversed-mode pruning are the identity and are not run at all ----
+            //          reversed-mode pruning are the identity and are not run at all.  The facts come
+            //          from the lanes that wrote the set in B; the slots are not read again ----
             const bool c0 = run && !finished && i + 2 < n32 && !next_near;
             if (__any_sync(ALL, c0)) {
-                bool stable = true, any = false;
-                uint32_t ev = n32;
-                for (uint32_t q = lane; q < SP; q += TILE) {
-                    const uint64_t ka = c0 ? keys[cur * SP + q] : K3_EMPTY;
-                    if (ka == K3_EMPTY) continue;
-                    any = true;
-                    const uint32_t fa = uint32_t(ka >> 36), sa = cur * SP + q, fla = flg[sa];
-                    const uint32_t pkey = (q << gp.n_cells) | exists_mask_n<NC>(fla);
-                    if (fa < i + 2 || fa == n32 || s_begin[pkey] == 0xffffffffu || !(s_count[pkey] & kProgStable)) stable = false;
-                    if (fa < ev) ev = fa;
-                    if (v.reversed) {
-                        const uint32_t need = k3_need<NC>(fla, lnn + sa * NC);  // fresh: not yet tested against mfa.cpp:141
-                        const uint32_t ps = need > n32 ? 0u : n32 - need + 1u;
-                        if (ps < ev) ev = ps;
-                    }
-                }
-                const uint32_t nstable = to.ballot(!stable);  // two votes, both by every tile: no short circuit
-                any = to.any(any);
-                stable = (nstable == 0u) && any;
-                ev = to.min(ev);
-                if (c0 && stable && ev > i + 1) {
+                const uint32_t nstable = to.ballot(!w_stable);  // three collectives, each by every tile
+                const bool any = to.any(w_any);
+                const uint32_t ev = to.min(w_ev);
+                if (c0 && nstable == 0u && any && ev > i + 1) {
                     i = ev - 1;  // the increment below makes the next step ev
                     jumped = true;
                 }

@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 
+static unsigned long long rxm_k3_simt_iterations = 0;  // counted by the kernel under RXM_SIMT_HOST
 #include "../../re2-modification_b200/csrc/rxm_k3.cu"
 
 namespace {
@@ -128,4 +129,13 @@ extern "C" int hostsim_simt_selftest(int which, char *msg_out, uint32_t msg_cap)
     }
     if (which == 0 && rc == 0 && !ok) return -1;
     return rc;
+}
+
+// Collectives the last emulated launch executed (a proxy for the steps the kernel ran).
+extern "C" unsigned long long hostsim_simt_collectives() { return simt::S().collectives; }
+// Lock-step iterations (steps of the slowest tile) of all launches since the last call.
+extern "C" unsigned long long hostsim_k3_iterations() {
+    const unsigned long long r = rxm_k3_simt_iterations;
+    rxm_k3_simt_iterations = 0;
+    return r;
 }
