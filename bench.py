@@ -432,6 +432,12 @@ def main():
         j["bytes"] = int(j["offsets"][-1])
         j["out"] = torch.empty(j["n"], dtype=torch.uint8, device=dev)
         j["matcher"] = rxm.Matcher(j["tables"], local_rank)
+    # config 4 is bounded by its longest string in each of the two automata: the handles share the
+    # device (rxm_set_concurrency) so that the two launches run side by side; config 5's ten jobs are
+    # throughput-bound and stay at one launch filling the device after another
+    share = int(os.environ.get("RXM_BENCH_SHARE", len(jobs) if wl == "config4" else 1))
+    for j in jobs:
+        j["matcher"].set_concurrency(share)
     n = sum(j["n"] for j in jobs)
     total_bytes = sum(j["bytes"] for j in jobs)
     tables, chars, offsets, out, m = (jobs[0][k] for k in ("tables", "chars", "offsets", "out", "matcher"))
@@ -666,7 +672,7 @@ def main():
                        "engine": "+".join(sorted({rxm.ENGINE_NAMES.get(j["matcher"].plan().engine, "?") for j in jobs})),
                        "dfa_stride": int(jobs[0]["matcher"].plan().dfa_stride),
                        "jobs_per_step": len(jobs),
-                       "job_streams": max(1, len(job_streams)),
+                       "handles_sharing_device": share, "job_streams": max(1, len(job_streams)),
                        "numa_node": numa_node,
                        "l2": ("L2 flushed between timed steps (512 MB written; inputs are %.2f GB per GPU)" if flush else
                               "inputs (%.2f GB per GPU) are larger than the 126 MB L2") % (total_bytes / 1e9),

@@ -70,6 +70,7 @@ struct rxm_matcher {
     uint32_t *d_prog_count = nullptr;
     uint32_t k3_tile = 32;  // lanes per string
     bool k3_tile_forced = false;
+    uint32_t sharing = 1;  // rxm_set_concurrency: handles that run at once on this device
 
     // staging workspace for host buffers
     uint8_t *d_chars = nullptr;
@@ -275,6 +276,12 @@ extern "C" int rxm_launch_count(rxm_handle h, uint64_t *launches) {
     return RXM_OK;
 }
 
+extern "C" int rxm_set_concurrency(rxm_handle h, uint32_t handles) {
+    if (!h || handles == 0) return RXM_ERR_INVALID;
+    h->sharing = handles;
+    return RXM_OK;
+}
+
 extern "C" int rxm_overflow_count(rxm_handle h, uint64_t *count) {
     if (!h || !count) return RXM_ERR_INVALID;
     unsigned long long v = 0;
@@ -288,11 +295,15 @@ extern "C" int rxm_overflow_count(rxm_handle h, uint64_t *count) {
 // total_chars: offsets[n] - offsets[0] if the caller knows it, else ~0ull
 // Tile-sorted order of a batch (long strings first, equal lengths together) for the engines that
 // hand strings out one by one; *order stays null for small batches (and with RXM_K3_ORDER=index).
+// long_strings: the batch is in the one-warp-per-string regime (mean length > 4096), where the
+// longest strings bound the launch and 16 us of sorting pay at any batch size that outnumbers
+// the strings in flight.
 static int prepare_order(rxm_matcher *m, rxm::Spans spans, uint64_t n, cudaStream_t stream,
-                         const rxm::K1Rec **order, int *launched) {
+                         const rxm::K1Rec **order, int *launched, bool long_strings = false) {
     *order = nullptr;
     const char *lpt = getenv("RXM_K3_ORDER");  // "index": tuning
-    if (n < 4 * rxm::K1_TILE_STRINGS || n > 0xfffffff0ull || (lpt && std::strcmp(lpt, "index") == 0)) return RXM_OK;
+    const uint64_t least = long_strings ? 512 : 4 * rxm::K1_TILE_STRINGS;
+    if (n < least || n > 0xfffffff0ull || (lpt && std::strcmp(lpt, "index") == 0)) return RXM_OK;
     if (n > m->cap_recs) {
         cudaFree(m->d_recs);
         m->d_recs = nullptr;
@@ -350,20 +361,19 @@ static int launch_on_device(rxm_matcher *m, const uint8_t *d_chars, rxm::Spans s
         // block compares).  The mean length decides; with device buffers it costs one 8-byte
         // read-back of offsets[n].
         uint32_t tile = m->k3_tile;
-        if (tile < 32 && !m->k3_tile_forced) {
-            if (total_chars == ~0ull) {
-                uint64_t ends[1] = {0};
-                CU(cudaMemcpyAsync(ends, spans.end + (n - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
-                CU(cudaStreamSynchronize(stream));
-                total_chars = ends[0];
-            }
-            if (total_chars / n > 4096) tile = 32;
+        if (total_chars == ~0ull && ((tile < 32 && !m->k3_tile_forced) || n < 4 * rxm::K1_TILE_STRINGS)) {
+            uint64_t ends[1] = {0};  // (small batches: the hand-out order below wants the mean length too)
+            CU(cudaMemcpyAsync(ends, spans.end + (n - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+            CU(cudaStreamSynchronize(stream));
+            total_chars = ends[0];
         }
+        if (tile < 32 && !m->k3_tile_forced && total_chars / n > 4096) tile = 32;
         const rxm::K1Rec *order = nullptr;
-        if ((st = prepare_order(m, spans, n, stream, &order, &launched_extra)) != RXM_OK) return st;
+        const bool long_strings = (total_chars != ~0ull && total_chars / n > 4096);
+        if ((st = prepare_order(m, spans, n, stream, &order, &launched_extra, long_strings)) != RXM_OK) return st;
         st = rxm::k3_launch(v, gp, uint32_t(m->prog.items.size()), uint32_t(m->prog.begin.size()),
                             m->tables.n_cells, tile, d_chars, spans, order, n, d_out, m->d_overflow, m->d_overflow + 1,
-                            m->sm_count, stream, &launched);
+                            m->sm_count, m->sharing, stream, &launched);
     } else {
         rxm::MfaView v{m->d_edge_begin, m->d_edges, m->tables.n_states(), m->tables.start,
                        m->tables.finish, m->tables.reversed};

@@ -529,7 +529,7 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
 template <int NC, int TILE>
 int launch_k3(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n_keys, const uint8_t *d_chars,
               Spans spans, const K1Rec *d_recs, uint64_t n, uint8_t *d_out, unsigned long long *d_overflow,
-              unsigned long long *d_next, int sm_count, cudaStream_t stream) {
+              unsigned long long *d_next, int sm_count, uint32_t sharing, cudaStream_t stream) {
     constexpr int TILES = K3_WARPS * 32 / TILE;  // strings in flight per block
     const uint32_t SP = (v.n_states + TILE - 1u) & ~uint32_t(TILE - 1);
     const size_t per_tile = size_t(SP) * 2 * (8 + 4 + 8 * NC) + size_t(SP) * 12 + 16;
@@ -543,7 +543,9 @@ int launch_k3(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, K3_WARPS * 32, smem) != cudaSuccess || nb <= 0)
         return RXM_ERR_CUDA;
-    uint64_t blocks = uint64_t(sm_count) * nb;
+    // rxm_set_concurrency: other handles' kernels run beside this one only if it leaves them block slots
+    uint64_t blocks = uint64_t(sm_count) * nb / (sharing ? sharing : 1u);
+    if (blocks == 0) blocks = 1;
     const uint64_t need = (n + TILES - 1) / TILES;
     if (blocks > need) blocks = need;
     if (cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), stream) != cudaSuccess) return RXM_ERR_CUDA;
@@ -555,15 +557,15 @@ int launch_k3(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n
 template <int NC>
 int launch_k3_tile(uint32_t tile, const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n_keys,
                    const uint8_t *d_chars, Spans spans, const K1Rec *d_recs, uint64_t n, uint8_t *d_out,
-                   unsigned long long *d_overflow, unsigned long long *d_next, int sm_count, cudaStream_t stream) {
+                   unsigned long long *d_overflow, unsigned long long *d_next, int sm_count, uint32_t sharing, cudaStream_t stream) {
     // the per-string state (two buffers of one slot per node) of all strings of a block must fit
     // shared memory: automata with many nodes move to wider tiles (fewer strings per block)
     int st = RXM_ERR_UNSUPPORTED;
-    if (tile <= 8) st = launch_k3<NC, 8>(v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, stream);
+    if (tile <= 8) st = launch_k3<NC, 8>(v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream);
     if (st == RXM_ERR_UNSUPPORTED && tile <= 16)
-        st = launch_k3<NC, 16>(v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, stream);
+        st = launch_k3<NC, 16>(v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream);
     if (st == RXM_ERR_UNSUPPORTED)
-        st = launch_k3<NC, 32>(v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, stream);
+        st = launch_k3<NC, 32>(v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream);
     return st;
 }
 
@@ -574,13 +576,13 @@ int launch_k3_tile(uint32_t tile, const MfaView &v, const ProgView &gp, uint32_t
 #ifndef RXM_SIMT_HOST
 int k3_launch(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n_keys, uint32_t n_cells,
               uint32_t tile, const uint8_t *d_chars, Spans spans, const K1Rec *d_recs, uint64_t n, uint8_t *d_out,
-              unsigned long long *d_overflow, unsigned long long *d_next, int sm_count, cudaStream_t stream,
-              int *launched) {
+              unsigned long long *d_overflow, unsigned long long *d_next, int sm_count, uint32_t sharing,
+              cudaStream_t stream, int *launched) {
     *launched = 0;
     int st;
-    if (n_cells <= 1) st = launch_k3_tile<1>(tile, v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, stream);
-    else if (n_cells <= 2) st = launch_k3_tile<2>(tile, v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, stream);
-    else if (n_cells <= 4) st = launch_k3_tile<4>(tile, v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, stream);
+    if (n_cells <= 1) st = launch_k3_tile<1>(tile, v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream);
+    else if (n_cells <= 2) st = launch_k3_tile<2>(tile, v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream);
+    else if (n_cells <= 4) st = launch_k3_tile<4>(tile, v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream);
     else return RXM_ERR_UNSUPPORTED;
     if (st == RXM_OK) *launched = 1;
     return st;

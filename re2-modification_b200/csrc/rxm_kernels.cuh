@@ -102,8 +102,9 @@ int k2_launch(const MfaView &dev_view, uint32_t n_cells, uint32_t n_edges, const
 int k3_launch(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n_keys, uint32_t n_cells,
               uint32_t tile /* lanes per string: 8, 16 or 32 */, const uint8_t *d_chars, Spans spans,
               const K1Rec *d_recs /* tile-sorted order, or null: index order */, uint64_t n, uint8_t *d_out,
-              unsigned long long *d_overflow, unsigned long long *d_next, int sm_count, cudaStream_t stream,
-              int *launched);
+              unsigned long long *d_overflow, unsigned long long *d_next, int sm_count,
+              uint32_t sharing /* handles running at once on the device: the grid takes 1/sharing of the block slots */,
+              cudaStream_t stream, int *launched);
 
 // ---- tokeniser: whitespace-delimited text -> spans (rxm_tok.cu) ------------------------------
 // Same token boundaries as `cin >> text` (matchers/match.cpp:22-23): whitespace is

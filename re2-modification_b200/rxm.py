@@ -32,7 +32,7 @@ ENGINE_NAMES = {1: "K1_DFA", 2: "K1_BITSET", 3: "K2_THREAD", 4: "K3_WARP"}
 ABI_SYMBOLS = [
     "rxm_tables_format", "rxm_tables_parse", "rxm_tables_release", "rxm_tables_validate",
     "rxm_tables_upload", "rxm_plan_query", "rxm_free", "rxm_match_batch", "rxm_match_text",
-    "rxm_launch_count", "rxm_overflow_count", "rxm_strerror", "rxm_last_cuda_error",
+    "rxm_launch_count", "rxm_overflow_count", "rxm_set_concurrency", "rxm_strerror", "rxm_last_cuda_error",
 ]
 
 
@@ -97,6 +97,8 @@ def lib() -> C.CDLL:
         L.rxm_match_text.restype = C.c_int
         L.rxm_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.rxm_launch_count.restype = C.c_int
+        L.rxm_set_concurrency.argtypes = [C.c_void_p, C.c_uint32]
+        L.rxm_set_concurrency.restype = C.c_int
         L.rxm_overflow_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.rxm_overflow_count.restype = C.c_int
         L.rxm_strerror.argtypes = [C.c_int]
@@ -216,6 +218,12 @@ class Matcher:
             e.n_tokens = n.value
             raise e
         return n.value
+
+    def set_concurrency(self, handles: int):
+        """rxm_set_concurrency: `handles` matchers run at once on this device (streams of their own)."""
+        st = lib().rxm_set_concurrency(self._h, handles)
+        if st != RXM_OK:
+            raise RxmError(st, "rxm_set_concurrency")
 
     def launch_count(self) -> int:
         v = C.c_uint64(0)
