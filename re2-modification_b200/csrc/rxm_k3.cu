@@ -47,6 +47,10 @@ struct TileOps {
     __device__ __forceinline__ uint32_t ballot(bool p) const { return (__ballot_sync(ALL, p) >> tshift) & TM; }
     __device__ __forceinline__ bool any(bool p) const { return ballot(p) != 0u; }
     __device__ __forceinline__ bool all(bool p) const { return ballot(p) == TM; }
+    // p has the same value in every lane of a tile: is it set in any / every tile of the warp?
+    // (TILE == 32: the tile is the warp, no vote)
+    __device__ __forceinline__ static bool warp_any(bool p) { return TILE == 32 ? p : __any_sync(ALL, p); }
+    __device__ __forceinline__ static bool warp_all(bool p) { return TILE == 32 ? p : __all_sync(ALL, p); }
     __device__ __forceinline__ uint32_t min(uint32_t x) const {
         if (TILE == 32) return __reduce_min_sync(ALL, x);
 #pragma unroll
@@ -70,7 +74,7 @@ __device__ __forceinline__ bool tile_span_equal(const TileOps<TILE> &to, const u
     const uint32_t *wb = reinterpret_cast<const uint32_t *>(pb - bb);
     for (uint32_t base = 0;; base += 4u * TILE) {
         live = live && base < L;
-        if (!__any_sync(TileOps<TILE>::ALL, live)) break;
+        if (!TileOps<TILE>::warp_any(live)) break;
         const uint32_t off = base + lane * 4u;
         bool ne = false;
         if (live && off < L) {
@@ -215,7 +219,7 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
         if (threadIdx.x == 0) rxm_k3_simt_iterations++;  // tests/hostsim/k3_simt.cpp: lock-step iterations of the warp
 #endif
         const bool want = !have_str && !exhausted;
-        if (__any_sync(ALL, want)) {
+        if (TileOps<TILE>::warp_any(want)) {
             unsigned long long t = 0;
             if (want && lane == 0) t = atomicAdd(next_string, 1ull);
             t = __shfl_sync(ALL, t, 0, TILE);
@@ -261,7 +265,7 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
             }
             __syncwarp(ALL);
         }
-        if (__all_sync(ALL, exhausted && !have_str)) break;
+        if (TileOps<TILE>::warp_all(exhausted && !have_str)) break;
         const bool act = have_str;  // this tile has a string in hand
         bool finished = false;
         {
@@ -302,14 +306,15 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
                     const uint32_t u = __shfl_up_sync(ALL, inc, d, TILE);
                     if (int(lane) >= d) inc += u;
                 }
+                const uint32_t before = inc - pc, total = __shfl_sync(ALL, inc, TILE - 1, TILE);
                 if (lv) {
                     const uint32_t j = m + __popc(bal & ((1u << lane) - 1u));
                     l_node[j] = q;
                     l_pb[j] = pb;
-                    l_off[j] = T + inc - pc;
+                    l_off[j] = T + before;
                 }
                 m += __popc(bal);
-                T += __shfl_sync(ALL, inc, TILE - 1, TILE);
+                T += total;
             }
             ovf = to.any(ovf);
             any_active = to.any(any_active);
@@ -394,7 +399,7 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
                 // until the last tile of the warp has none left
                 uint32_t cm = to.ballot(need_cmp);
                 bool cmp_ok = false;
-                while (__any_sync(ALL, cm != 0u)) {
+                while (TileOps<TILE>::warp_any(cm != 0u)) {
                     const int src = cm ? __ffs(int(cm)) - 1 : 0;
                     const uint32_t vs = __shfl_sync(ALL, cmp_vs, src, TILE);
                     uint32_t L = __shfl_sync(ALL, cmp_L, src, TILE);
@@ -460,7 +465,7 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
             //          reversed-mode pruning are the identity and are not run at all.  The facts come
             //          from the lanes that wrote the set in B; the slots are not read again ----
             const bool c0 = run && !finished && i + 2 < n32 && !next_near;
-            if (__any_sync(ALL, c0)) {
+            if (TileOps<TILE>::warp_any(c0)) {
                 const uint32_t nstable = to.ballot(!w_stable);  // three collectives, each by every tile
                 const bool any = to.any(w_any);
                 const uint32_t ev = to.min(w_ev);
@@ -472,7 +477,7 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
             // ---- C. fast-forward over idle steps (see MfaSim::run); only after a step in which
             //         no configuration was active ----
             const bool c1 = run && !finished && !jumped && !any_active && i + 1 < n32;
-            if (__any_sync(ALL, c1)) {
+            if (TileOps<TILE>::warp_any(c1)) {
                 bool same = true;
                 uint32_t ev = n32;
                 for (uint32_t q = lane; q < SP; q += TILE) {

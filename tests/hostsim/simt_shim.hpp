@@ -291,6 +291,7 @@ struct alignas(16) uint4 {
 };
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
+static inline int __clz(int x) { return x ? __builtin_clz(unsigned(x)) : 32; }
 static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
     return unsigned(((uint64_t(hi) << 32) | lo) >> (shift & 31u));
 }
