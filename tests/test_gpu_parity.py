@@ -558,3 +558,35 @@ def test_match_text_random_byte_soup():
         assert n == len(toks)
         assert np.array_equal(out[:n].cpu().numpy(), got)
     m.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ex02_fwd", "ex02_rev", "ex05_fwd"])
+def test_set_concurrency_changes_the_grid_not_the_bits(name):
+    """rxm_set_concurrency: handles sharing the device launch smaller persistent grids (down to a
+    single block); results are identical, and two handles on streams of their own agree too."""
+    import torch
+    t, strings, bits = load_case(name)
+    big = strings * 12  # several waves of strings for a one-block grid
+    chars, off = H.make_batch(big)
+    want = np.tile(bits, 12)
+    with pytest.raises(H.rxm.RxmError):
+        H.rxm.Matcher(t, 0).set_concurrency(0)
+    for share in (1, 2, 7, 100000):
+        m = H.rxm.Matcher(t, 0)
+        m.set_concurrency(share)
+        got = m.match_host(chars, off)
+        assert np.array_equal(got, want), share
+        m.close()
+    dev = torch.device("cuda:0")
+    dc, do = torch.from_numpy(chars).to(dev), torch.from_numpy(off.astype(np.int64)).to(dev)
+    ms = [H.rxm.Matcher(t, 0) for _ in range(2)]
+    outs = [torch.empty(len(big), dtype=torch.uint8, device=dev) for _ in ms]
+    sts = [torch.cuda.Stream(device=dev) for _ in ms]
+    torch.cuda.synchronize()
+    for m, o, st in zip(ms, outs, sts):
+        m.set_concurrency(2)
+        m.match_ptrs(dc.data_ptr(), do.data_ptr(), len(big), o.data_ptr(), st.cuda_stream)
+    torch.cuda.synchronize()
+    for o in outs:
+        assert np.array_equal(o.cpu().numpy(), want)
