@@ -17,7 +17,7 @@ namespace {
 template <int NC, int TILE>
 int run_k3(const rxm::MfaView &v, const rxm::ProgView &gp, uint32_t n_items, uint32_t n_keys, const uint8_t *chars,
            const uint64_t *off, const rxm::K1Rec *recs, uint64_t n, uint8_t *out, unsigned long long *overflow,
-           uint64_t limit, const char **msg) {
+           uint64_t limit, const char **msg, uint64_t seed) {
     // shared-memory budget exactly as launch_k3 computes it, for one warp
     constexpr int TILES = 32 / TILE;
     const uint32_t SP = (v.n_states + TILE - 1u) & ~uint32_t(TILE - 1);
@@ -30,16 +30,16 @@ int run_k3(const rxm::MfaView &v, const rxm::ProgView &gp, uint32_t n_items, uin
         [&]() {
             rxm::k3_mfa_warp_kernel<NC, TILE>(v, gp, n_items, n_keys, 1u, chars, sp, recs, n, out, overflow, &next);
         },
-        smem, limit, msg);
+        smem, limit, msg, seed);
 }
 
 template <int NC>
 int run_k3_tile(uint32_t tile, const rxm::MfaView &v, const rxm::ProgView &gp, uint32_t n_items, uint32_t n_keys,
                 const uint8_t *chars, const uint64_t *off, const rxm::K1Rec *recs, uint64_t n, uint8_t *out,
-                unsigned long long *overflow, uint64_t limit, const char **msg) {
-    if (tile == 8) return run_k3<NC, 8>(v, gp, n_items, n_keys, chars, off, recs, n, out, overflow, limit, msg);
-    if (tile == 16) return run_k3<NC, 16>(v, gp, n_items, n_keys, chars, off, recs, n, out, overflow, limit, msg);
-    return run_k3<NC, 32>(v, gp, n_items, n_keys, chars, off, recs, n, out, overflow, limit, msg);
+                unsigned long long *overflow, uint64_t limit, const char **msg, uint64_t seed) {
+    if (tile == 8) return run_k3<NC, 8>(v, gp, n_items, n_keys, chars, off, recs, n, out, overflow, limit, msg, seed);
+    if (tile == 16) return run_k3<NC, 16>(v, gp, n_items, n_keys, chars, off, recs, n, out, overflow, limit, msg, seed);
+    return run_k3<NC, 32>(v, gp, n_items, n_keys, chars, off, recs, n, out, overflow, limit, msg, seed);
 }
 
 }  // namespace
@@ -48,9 +48,10 @@ int run_k3_tile(uint32_t tile, const rxm::MfaView &v, const rxm::ProgView &gp, u
 // order: null (strings handed out by index) or the K1Rec array of the tile sort's order (only
 // .idx is read).  Returns 0; RXM status if the programs do not compile; 100 + emulator failure
 // code (1 divergent collective, 2 deadlock, 3 watchdog) with the report in msg_out.
+// seed: 0 = lanes run round-robin between collectives, else a shuffled order (races between lanes).
 extern "C" int hostsim_k3_batch(const rxm_tables *t, const uint8_t *chars, const uint64_t *off, uint64_t n,
                                 uint8_t *out, uint32_t tile, const uint32_t *order_idx, uint64_t limit,
-                                unsigned long long *overflow_out, char *msg_out, uint32_t msg_cap) {
+                                unsigned long long *overflow_out, char *msg_out, uint32_t msg_cap, uint64_t seed) {
     rxm::MfaProgram prog;
     std::string err;
     int st = rxm::compile_programs(*t, prog, &err);
@@ -73,9 +74,9 @@ extern "C" int hostsim_k3_batch(const rxm_tables *t, const uint8_t *chars, const
     const uint32_t n_items = uint32_t(prog.items.size()), n_keys = uint32_t(prog.begin.size());
     const rxm::K1Rec *rp = order_idx ? recs.data() : nullptr;
     int rc;
-    if (prog.n_cells <= 1) rc = run_k3_tile<1>(tile, v, gp, n_items, n_keys, chars, off, rp, n, out, &overflow, limit, &msg);
-    else if (prog.n_cells <= 2) rc = run_k3_tile<2>(tile, v, gp, n_items, n_keys, chars, off, rp, n, out, &overflow, limit, &msg);
-    else rc = run_k3_tile<4>(tile, v, gp, n_items, n_keys, chars, off, rp, n, out, &overflow, limit, &msg);
+    if (prog.n_cells <= 1) rc = run_k3_tile<1>(tile, v, gp, n_items, n_keys, chars, off, rp, n, out, &overflow, limit, &msg, seed);
+    else if (prog.n_cells <= 2) rc = run_k3_tile<2>(tile, v, gp, n_items, n_keys, chars, off, rp, n, out, &overflow, limit, &msg, seed);
+    else rc = run_k3_tile<4>(tile, v, gp, n_items, n_keys, chars, off, rp, n, out, &overflow, limit, &msg, seed);
     if (overflow_out) *overflow_out = overflow;
     if (msg_out && msg_cap) {
         strncpy(msg_out, msg, msg_cap - 1);
@@ -86,10 +87,13 @@ extern "C" int hostsim_k3_batch(const rxm_tables *t, const uint8_t *chars, const
 
 // The emulator's own checks on tiny kernels: 0 well-formed (returns 0 when the results are right),
 // 1 vote in a lane-dependent branch, 2 a lane returns early, 3 short-circuited votes, 4 endless
-// loop, 5 partial mask.  Returns the emulator's failure code.
+// loop, 5 partial mask; 6 / 7 an unsynchronised neighbour read under round-robin / shuffled lane
+// order (returns 1000 + the number of lanes that saw the neighbour's write).  Otherwise returns the
+// emulator's failure code.
 extern "C" int hostsim_simt_selftest(int which, char *msg_out, uint32_t msg_cap) {
     const char *msg = "";
     uint32_t sums[32] = {0};
+    unsigned long long race_hits = 0;  // lanes that saw their neighbour's write
     bool ok = true;
     const int rc = simt::launch_warp(
         [&]() {
@@ -118,16 +122,24 @@ extern "C" int hostsim_simt_selftest(int which, char *msg_out, uint32_t msg_cap)
                 (void)__ballot_sync(0xffffffffu, true);
             } else if (which == 4) {
                 for (;;) (void)__ballot_sync(0xffffffffu, true);
-            } else {
+            } else if (which == 5) {
                 (void)__ballot_sync(0x0000ffffu, true);
+            } else {  // 6 / 7: a read of the neighbour's word with no __syncwarp between write and read
+                uint32_t *w = reinterpret_cast<uint32_t *>(simt::S().smem);
+                if (lane == 0) sums[0] = 0;
+                (void)__ballot_sync(0xffffffffu, true);
+                w[lane] = lane + 100;
+                if (w[(lane + 1) & 31] == ((lane + 1) & 31) + 100) atomicAdd(&race_hits, 1ull);
+                (void)__ballot_sync(0xffffffffu, true);
             }
         },
-        64, 100000, &msg);
+        256, 100000, &msg, which == 7 ? 12345 : 0);
     if (msg_out && msg_cap) {
         strncpy(msg_out, msg, msg_cap - 1);
         msg_out[msg_cap - 1] = 0;
     }
     if (which == 0 && rc == 0 && !ok) return -1;
+    if (which >= 6 && rc == 0) return 1000 + int(race_hits);
     return rc;
 }
 

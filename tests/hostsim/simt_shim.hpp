@@ -45,6 +45,7 @@ struct State {
     int arrived;
     int cur;                 // running lane
     uint64_t collectives, limit;
+    uint64_t rng;            // 0: lanes run round-robin; else the order between collectives is shuffled
     int failed;              // 0 ok, 1 divergent collective, 2 deadlock, 3 watchdog
     char msg[512];
     uint8_t *smem;
@@ -99,13 +100,21 @@ inline void fail(int code, const char *what) {
     to_main();  // never resumed
 }
 
-// Hand the processor to the next lane that has not returned.
+// Hand the processor to another lane that has not returned: the next one, or (rng != 0) a random
+// one -- between two collectives the lanes of a real warp run in no particular order, and code that
+// needs one (a read that must precede another lane's write, without a __syncwarp) should fail here.
 inline void yield_next() {
     State &s = S();
     const int me = s.cur;
-    for (int k = 1; k <= kLanes; k++) {
-        const int nx = (me + k) % kLanes;
-        if (nx == me) break;
+    int first = 1;
+    if (s.rng) {
+        s.rng ^= s.rng << 13;
+        s.rng ^= s.rng >> 7;
+        s.rng ^= s.rng << 17;
+        first = 1 + int(s.rng % (kLanes - 1));
+    }
+    for (int k = 0; k < kLanes - 1; k++) {
+        const int nx = (me + 1 + (first - 1 + k) % (kLanes - 1)) % kLanes;
         if (!s.done[nx]) {
             s.cur = nx;
             simt_switch(&s.sp[me], s.sp[nx]);
@@ -129,6 +138,7 @@ inline unsigned meet(unsigned mask, int site, uint64_t value) {
         s.arrived = 0;
         s.gen = gen + 1;
         if (++s.collectives > s.limit) fail(3, "watchdog: collective limit exceeded (endless loop?)");
+        if (s.rng) yield_next();  // the last lane to arrive is not always the first to go on
     } else {
         for (int l = 0; l < kLanes; l++)
             if (s.done[l]) fail(2, "deadlock: a lane returned while others wait in a collective");
@@ -160,7 +170,8 @@ inline void fiber_entry() {
 }
 
 // Run `body` as one block of 32 threads.  Returns 0, or the failure code with *msg set.
-inline int launch_warp(const std::function<void()> &body, size_t smem_bytes, uint64_t limit, const char **msg) {
+inline int launch_warp(const std::function<void()> &body, size_t smem_bytes, uint64_t limit, const char **msg,
+                       uint64_t seed = 0) {
     State &s = S();
     s.body = body;
     s.stacks.assign(kStack * kLanes, 0);
@@ -171,6 +182,7 @@ inline int launch_warp(const std::function<void()> &body, size_t smem_bytes, uin
     s.ndone = 0;
     s.collectives = 0;
     s.limit = limit;
+    s.rng = seed ? seed * 0x9e3779b97f4a7c15ull + 1 : 0;
     s.failed = 0;
     s.msg[0] = 0;
     s.bdim = Idx{kLanes, 1, 1};
