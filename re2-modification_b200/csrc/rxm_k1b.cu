@@ -29,7 +29,7 @@ k1b_bitset_kernel(const uint16_t *__restrict__ g_eb, const uint32_t *__restrict_
                   const uint8_t *__restrict__ chars, const Spans sp, const K1Rec *__restrict__ recs, uint64_t n,
                   uint8_t *__restrict__ out,
                   unsigned long long *__restrict__ overflow, unsigned long long *__restrict__ next_string) {
-    extern __shared__ __align__(16) uint8_t smem[];
+    RXM_DYN_SMEM(smem);
     uint32_t *ed = reinterpret_cast<uint32_t *>(smem);
     uint16_t *eb = reinterpret_cast<uint16_t *>(smem + size_t(n_edges) * 4);
     for (uint32_t i = threadIdx.x; i < n_edges; i += blockDim.x) ed[i] = g_ed[i];
@@ -84,7 +84,7 @@ k1b_mask_kernel(const uint64_t *__restrict__ g_ls, const uint8_t *__restrict__ g
                 const uint8_t *__restrict__ chars, const Spans sp, const K1Rec *__restrict__ recs, uint64_t n,
                 uint8_t *__restrict__ out, unsigned long long *__restrict__ overflow,
                 unsigned long long *__restrict__ next_string) {
-    extern __shared__ __align__(16) uint8_t smem[];
+    RXM_DYN_SMEM(smem);
     uint64_t *ls = reinterpret_cast<uint64_t *>(smem);
     uint8_t *bc = smem + size_t(n_classes) * n_states * 16;
     for (uint32_t i = threadIdx.x; i < n_classes * n_states * 2; i += blockDim.x) ls[i] = g_ls[i];
@@ -143,8 +143,7 @@ int k1b_mask_launch(const uint64_t *d_ls, const uint8_t *d_class, uint32_t n_sta
     const uint64_t need = (n + K1B_THREADS - 1) / K1B_THREADS;
     if (blocks > need) blocks = need;
     if (cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), stream) != cudaSuccess) return RXM_ERR_CUDA;
-    k1b_mask_kernel<<<unsigned(blocks), K1B_THREADS, smem, stream>>>(d_ls, d_class, n_states, n_classes, start, acc_lo, acc_hi,
-                                                                     reversed, d_chars, spans, d_recs, n, d_out, d_overflow, d_next);
+    RXM_LAUNCH(k1b_mask_kernel, unsigned(blocks), K1B_THREADS, smem, stream, d_ls, d_class, n_states, n_classes, start, acc_lo, acc_hi, reversed, d_chars, spans, d_recs, n, d_out, d_overflow, d_next);
     *launched = 1;
     return RXM_OK;
 }
@@ -172,8 +171,7 @@ int k1b_launch(const uint16_t *d_eb, const uint32_t *d_ed, uint32_t n_states, ui
     const uint64_t need = (n + K1B_THREADS - 1) / K1B_THREADS;
     if (blocks > need) blocks = need;
     if (cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), stream) != cudaSuccess) return RXM_ERR_CUDA;
-    k1b_bitset_kernel<<<unsigned(blocks), K1B_THREADS, smem, stream>>>(d_eb, d_ed, n_states, n_edges, start, finish, reversed,
-                                                                       d_chars, spans, d_recs, n, d_out, d_overflow, d_next);
+    RXM_LAUNCH(k1b_bitset_kernel, unsigned(blocks), K1B_THREADS, smem, stream, d_eb, d_ed, n_states, n_edges, start, finish, reversed, d_chars, spans, d_recs, n, d_out, d_overflow, d_next);
     *launched = 1;
     return RXM_OK;
 }

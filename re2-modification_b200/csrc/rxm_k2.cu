@@ -35,7 +35,7 @@ k2_mfa_thread_kernel(MfaView gv, uint32_t n_edges, const uint8_t *__restrict__ c
                      unsigned long long *__restrict__ overflow, unsigned long long *__restrict__ next_string,
                      uint32_t threads_used) {
     typedef K2Geom<NC, CAP, DMAX> G;
-    extern __shared__ __align__(16) uint8_t smem[];
+    RXM_DYN_SMEM(smem);
     uint64_t *s_edges = reinterpret_cast<uint64_t *>(smem);
     uint16_t *s_begin = reinterpret_cast<uint16_t *>(smem + size_t(n_edges) * 8);
     const size_t tab_bytes = (size_t(n_edges) * 8 + (size_t(gv.n_states) + 1) * 2 + 15) & ~size_t(15);
@@ -96,8 +96,7 @@ int launch_k2(const MfaView &v, uint32_t n_edges, const uint8_t *d_chars, Spans 
     const uint64_t need = (n + threads - 1) / threads;
     if (blocks > need) blocks = need;
     if (cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), stream) != cudaSuccess) return RXM_ERR_CUDA;
-    kern<<<unsigned(blocks), K2_THREADS, smem, stream>>>(v, n_edges, d_chars, spans, n, d_out, d_overflow,
-                                                        d_next, threads);
+    RXM_LAUNCH(kern, unsigned(blocks), K2_THREADS, smem, stream, v, n_edges, d_chars, spans, n, d_out, d_overflow, d_next, threads);
     return RXM_OK;
 }
 

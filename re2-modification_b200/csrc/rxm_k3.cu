@@ -24,11 +24,7 @@ constexpr uint64_t K3_EMPTY = ~0ull;
 #define RXM_K3_MIN_BLOCKS 4  // blocks per SM the several-strings-per-warp kernels are compiled for: 64 registers, no spills
                              // (config 3: 43.6 ms against 46.4 at 5 blocks / 48 registers and 44.6 at 3 / 80)
 #endif
-#ifdef RXM_SIMT_HOST
-constexpr int K3_WARPS = 1;  // tests/hostsim/k3_simt.cpp: one emulated warp
-#else
 constexpr int K3_WARPS = 8;
-#endif
 
 __device__ __forceinline__ uint64_t k3_key(uint32_t first, uint32_t flags, uint32_t born) {
     return (uint64_t(first) << 36) | (uint64_t(lowvar(flags)) << 32) | born;
@@ -216,7 +212,7 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
     bool ovf = false;
     for (;;) {
 #ifdef RXM_SIMT_HOST
-        if (threadIdx.x == 0) rxm_k3_simt_iterations++;  // tests/hostsim/k3_simt.cpp: lock-step iterations of the warp
+        if (threadIdx.x == 0) rxm_k3_simt_iterations++;  // tests/hostsim/kernels_simt.cpp: lock-step iterations of the warp
 #endif
         const bool want = !have_str && !exhausted;
         if (TileOps<TILE>::warp_any(want)) {
@@ -530,7 +526,6 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
     }
 }
 
-#ifndef RXM_SIMT_HOST
 template <int NC, int TILE>
 int launch_k3(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n_keys, const uint8_t *d_chars,
               Spans spans, const K1Rec *d_recs, uint64_t n, uint8_t *d_out, unsigned long long *d_overflow,
@@ -554,8 +549,8 @@ int launch_k3(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n
     const uint64_t need = (n + TILES - 1) / TILES;
     if (blocks > need) blocks = need;
     if (cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), stream) != cudaSuccess) return RXM_ERR_CUDA;
-    kern<<<unsigned(blocks), K3_WARPS * 32, smem, stream>>>(v, gp, n_items, n_keys, in_smem ? 1u : 0u, d_chars,
-                                                           spans, d_recs, n, d_out, d_overflow, d_next);
+    RXM_LAUNCH(kern, unsigned(blocks), K3_WARPS * 32, smem, stream, v, gp, n_items, n_keys, in_smem ? 1u : 0u, d_chars, spans,
+               d_recs, n, d_out, d_overflow, d_next);
     return RXM_OK;
 }
 
@@ -574,11 +569,8 @@ int launch_k3_tile(uint32_t tile, const MfaView &v, const ProgView &gp, uint32_t
     return st;
 }
 
-#endif  // RXM_SIMT_HOST
-
 }  // namespace
 
-#ifndef RXM_SIMT_HOST
 int k3_launch(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n_keys, uint32_t n_cells,
               uint32_t tile, const uint8_t *d_chars, Spans spans, const K1Rec *d_recs, uint64_t n, uint8_t *d_out,
               unsigned long long *d_overflow, unsigned long long *d_next, int sm_count, uint32_t sharing,
@@ -592,6 +584,5 @@ int k3_launch(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n
     if (st == RXM_OK) *launched = 1;
     return st;
 }
-#endif  // RXM_SIMT_HOST
 
 }  // namespace rxm

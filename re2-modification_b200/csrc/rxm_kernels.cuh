@@ -2,12 +2,12 @@
 #ifndef RXM_KERNELS_CUH
 #define RXM_KERNELS_CUH
 
-#ifdef RXM_SIMT_HOST
-// tests/hostsim compiles a kernel source for the host under tests/hostsim/simt_shim.hpp
-typedef void *cudaStream_t;
-#define RXM_DYN_SMEM(name) uint8_t *name = simt::S().smem
-#else
+#ifndef RXM_SIMT_HOST
 #include <cuda_runtime.h>
+// kernel<<<grid, block, dynamic shared memory, stream>>>(...) and the kernel's view of that memory.
+// tests/hostsim/simt_shim.hpp defines both for the host, so that the kernel sources AND their launch
+// functions run in the CPU test tier on a SIMT emulator.
+#define RXM_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define RXM_DYN_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
 #endif
 

@@ -149,6 +149,9 @@ tok_offsets_kernel(uint64_t *__restrict__ counts, uint64_t n, unsigned long long
         __syncthreads();
         if (warp == 0) {  // 128 tile totals in entry order: tile (k, w) covers entries k*1024 + w*32 ..
             uint64_t x[TOKO_SUB], run = 0;
+            // read before the shuffles below, which order it against lane 31's rewrite after them (found by
+            // the SIMT emulator's shuffled lane order: nothing else keeps the lanes of a warp in step)
+            const uint64_t carry_in = s_carry;
 #pragma unroll
             for (int k = 0; k < TOKO_SUB; k++) x[k] = s_w[lane * TOKO_SUB + k];  // lane owns tiles 4*lane .. 4*lane+3
 #pragma unroll
@@ -159,7 +162,7 @@ tok_offsets_kernel(uint64_t *__restrict__ counts, uint64_t n, unsigned long long
                 const uint64_t u = __shfl_up_sync(0xffffffffu, incl, d);
                 if (int(lane) >= d) incl += u;
             }
-            uint64_t ex = s_carry + incl - run;
+            uint64_t ex = carry_in + incl - run;
 #pragma unroll
             for (int k = 0; k < TOKO_SUB; k++) {
                 s_w[lane * TOKO_SUB + k] = ex;
@@ -261,16 +264,16 @@ int tok_launch(const uint8_t *d_text, uint64_t nbytes, uint64_t *d_begin, uint64
     if (cudaMemsetAsync(w.d_result + 1, 0xff, sizeof(unsigned long long), stream) != cudaSuccess) return RXM_ERR_CUDA;
     const uint64_t nwarps = nblocks * (TOK_THREADS / 32);
     uint64_t *d_within = w.d_counts + w.blocks_cap;  // [blocks_cap * 8] after the block totals
-    tok_classify_kernel<<<unsigned(nblocks), TOK_THREADS, 0, stream>>>(d_text - pad, pad, n0, w.d_masks, w.d_counts, d_within);
-    tok_offsets_kernel<<<1, TOKO_THREADS, 0, stream>>>(w.d_counts, nblocks, w.d_result);
+    RXM_LAUNCH(tok_classify_kernel, unsigned(nblocks), TOK_THREADS, 0, stream, d_text - pad, pad, n0, w.d_masks, w.d_counts, d_within);
+    RXM_LAUNCH(tok_offsets_kernel, 1, TOKO_THREADS, 0, stream, w.d_counts, nblocks, w.d_result);
     const uint64_t eblocks = (nwarps + TOKE_PIECES * (TOK_THREADS / 32) - 1) / (TOKE_PIECES * (TOK_THREADS / 32));
-    tok_emit_kernel<<<unsigned(eblocks), TOK_THREADS, 0, stream>>>(w.d_masks, w.d_counts, d_within, nwarps, pad, d_begin, d_end, cap);
+    RXM_LAUNCH(tok_emit_kernel, unsigned(eblocks), TOK_THREADS, 0, stream, w.d_masks, w.d_counts, d_within, nwarps, pad, d_begin, d_end, cap);
     *launched = 3;
     uint64_t eb = (cap + 255) / 256;
     const uint64_t ecap = uint64_t(sm_count) * 8;
     if (eb > ecap) eb = ecap;
     if (eb == 0) eb = 1;
-    tok_exit_kernel<<<unsigned(eb), 256, 0, stream>>>(d_text, d_begin, d_end, cap, w.d_result);
+    RXM_LAUNCH(tok_exit_kernel, unsigned(eb), 256, 0, stream, d_text, d_begin, d_end, cap, w.d_result);
     *launched = 4;
     return RXM_OK;
 }
