@@ -188,6 +188,7 @@ k1_tilesort_kernel(const Spans sp, uint64_t n, K1Rec *__restrict__ recs,
 // 16-byte asynchronous copy, L1 bypassed; the L2::256B hint makes L2 fetch the whole 256-byte
 // block on first touch, so DRAM sees 256-byte bursts per string instead of 64-byte ones
 // (measured: 0.443 -> 0.418 ms per config-2 step; L2::128B changes nothing, .ca doubles the time).
+#ifndef RXM_SIMT_HOST
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gsrc, bool pred) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t"
@@ -200,6 +201,27 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
+__device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) {  // FMA pipe, not the ALU's
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+#else  // tests/hostsim: the copy lands at once (a legal outcome of the asynchronous one), shared addresses
+       // are offsets into the emulated block's memory (simt_shim.hpp)
+inline void cp_async16(uint32_t smem_dst, const void *gsrc, bool pred) {
+    if (pred) memcpy(simt::shared_ptr(smem_dst), gsrc, 16);
+}
+inline void cp_async_commit() {}
+template <int N>
+inline void cp_async_wait() {}
+inline uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
+inline uint4 lds128(uint32_t addr) { return *reinterpret_cast<const uint4 *>(simt::shared_ptr(addr)); }
+#endif
 
 // q' = T[byte][q] with T[byte][SP] u8 in shared memory.  The index is formed with one
 // integer multiply-add (FMA pipe) so that the ALU pipe only carries the byte extraction.
@@ -207,9 +229,7 @@ template <int L>
 struct DirectStep {
     const uint8_t *T;  // shared-memory table (address space resolved after inlining)
     __device__ __forceinline__ uint32_t operator()(uint32_t q, uint32_t byte) const {
-        uint32_t idx;
-        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(idx) : "r"(byte), "n"(1 << L), "r"(q));
-        return T[idx];
+        return T[mad_lo(byte, 1u << L, q)];
     }
 };
 struct ClassedStep {  // cmap[256] u8, then trans[class][n_states] u16
@@ -252,12 +272,6 @@ __device__ __forceinline__ uint32_t step_vec(const Step &st, uint32_t q, const u
     return q;
 }
 
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
-
 // Quad stride (four bytes per lookup, DESIGN.md "K1").  x = word - lo4 maps the window's
 // letters to 0..3 in every byte; any other byte leaves a bit under 0xFC in its own or a lower
 // byte position and raises `bad`.  x * (1 + 2^10 + 2^20 + 2^30) gathers the four 2-bit codes
@@ -275,9 +289,7 @@ struct QuadStep {
         const uint32_t x = w + neg_lo4;
         bad |= x;
         const uint32_t code = (x * 0x40100401u) >> 24;
-        uint32_t idx;
-        asm("mad.lo.u32 %0, %1, 256, %2;" : "=r"(idx) : "r"(q), "r"(code));
-        return Q[idx];
+        return Q[mad_lo(q, 256u, code)];
     }
     template <bool REV>
     __device__ __forceinline__ uint32_t vec(uint32_t q, const uint32_t (&w)[4], uint32_t &bad) const {
@@ -507,7 +519,7 @@ k1_dfa_direct_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict_
     constexpr uint32_t TB = 256u << L;
     __shared__ __align__(16) uint8_t s_table[TB];   // static: its offset folds into the LDS
     __shared__ __align__(16) uint8_t s_accept[256];
-    extern __shared__ __align__(128) uint8_t ring[];
+    RXM_DYN_SMEM_128(ring);
     const uint4 *s4 = reinterpret_cast<const uint4 *>(g_table);
     uint4 *d4 = reinterpret_cast<uint4 *>(s_table);
     for (uint32_t i = threadIdx.x; i < TB / 16; i += blockDim.x) d4[i] = s4[i];
@@ -529,7 +541,7 @@ k1_dfa_quad_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict__ 
     constexpr uint32_t TB = 256u << L;
     __shared__ __align__(16) uint8_t s_table[2 * TB];  // T then Q; static: offsets fold into the LDS
     __shared__ __align__(16) uint8_t s_accept[256];
-    extern __shared__ __align__(128) uint8_t ring[];
+    RXM_DYN_SMEM_128(ring);
     const uint4 *s4 = reinterpret_cast<const uint4 *>(g_table);
     uint4 *d4 = reinterpret_cast<uint4 *>(s_table);
     for (uint32_t i = threadIdx.x; i < 2 * TB / 16; i += blockDim.x) d4[i] = s4[i];
@@ -549,7 +561,7 @@ k1_dfa_classed_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict
                       uint8_t *__restrict__ out, const uint8_t *__restrict__ g_table, uint32_t table_bytes,
                       const uint8_t *__restrict__ g_accept, uint32_t accept_bytes, uint32_t n_states,
                       uint32_t start, uint32_t *__restrict__ task_counter) {
-    extern __shared__ __align__(128) uint8_t smem[];
+    RXM_DYN_SMEM_128(smem);
     const uint4 *s4 = reinterpret_cast<const uint4 *>(g_table);
     uint4 *d4 = reinterpret_cast<uint4 *>(smem);
     for (uint32_t i = threadIdx.x; i < table_bytes / 16; i += blockDim.x) d4[i] = s4[i];
@@ -598,8 +610,7 @@ int launch_direct_v(const K1Tables &kt, const K1Launch &a) {
     uint64_t blocks = uint64_t(a.sm_count) * nb;
     const uint64_t need = (tasks + K1_WARPS - 1) / K1_WARPS;
     if (blocks > need) blocks = need;
-    kern<<<unsigned(blocks), K1_WARPS * 32, smem, a.stream>>>(a.d_chars, a.d_recs, a.n, a.d_out, a.d_table,
-                                                             a.d_accept, kt.start, a.d_task_counter);
+    RXM_LAUNCH(kern, unsigned(blocks), K1_WARPS * 32, smem, a.stream, a.d_chars, a.d_recs, a.n, a.d_out, a.d_table, a.d_accept, kt.start, a.d_task_counter);
     return RXM_OK;
 }
 
@@ -627,8 +638,7 @@ int launch_quad_w(const K1Tables &kt, const K1Launch &a) {
     uint64_t blocks = uint64_t(a.sm_count) * nb;
     const uint64_t need = (tasks + WARPS - 1) / WARPS;
     if (blocks > need) blocks = need;
-    kern<<<unsigned(blocks), WARPS * 32, smem, a.stream>>>(a.d_chars, a.d_recs, a.n, a.d_out, a.d_table, a.d_accept,
-                                                          kt.start, kt.quad_lo, a.d_task_counter);
+    RXM_LAUNCH(kern, unsigned(blocks), WARPS * 32, smem, a.stream, a.d_chars, a.d_recs, a.n, a.d_out, a.d_table, a.d_accept, kt.start, kt.quad_lo, a.d_task_counter);
     return RXM_OK;
 }
 
@@ -677,9 +687,7 @@ int launch_classed(const K1Tables &kt, const K1Launch &a) {
     uint64_t blocks = uint64_t(a.sm_count) * nb;
     const uint64_t need = (tasks + K1_WARPS - 1) / K1_WARPS;
     if (blocks > need) blocks = need;
-    kern<<<unsigned(blocks), K1_WARPS * 32, smem, a.stream>>>(a.d_chars, a.d_recs, a.n, a.d_out, a.d_table,
-                                                             kt.table_bytes, a.d_accept, kt.accept_bytes,
-                                                             kt.n_states, kt.start, a.d_task_counter);
+    RXM_LAUNCH(kern, unsigned(blocks), K1_WARPS * 32, smem, a.stream, a.d_chars, a.d_recs, a.n, a.d_out, a.d_table, kt.table_bytes, a.d_accept, kt.accept_bytes, kt.n_states, kt.start, a.d_task_counter);
     return RXM_OK;
 }
 
@@ -692,7 +700,7 @@ int k1_tilesort_launch(Spans spans, uint64_t n, K1Rec *d_recs, uint32_t *d_count
     const uint64_t cap = uint64_t(sm_count) * 2;
     if (blocks > cap) blocks = cap;
     if (blocks == 0) return RXM_OK;
-    k1_tilesort_kernel<<<unsigned(blocks), K1_SORT_THREADS, 0, stream>>>(spans, n, d_recs, d_counter, d_overflow);
+    RXM_LAUNCH(k1_tilesort_kernel, unsigned(blocks), K1_SORT_THREADS, 0, stream, spans, n, d_recs, d_counter, d_overflow);
     return RXM_OK;
 }
 
@@ -702,8 +710,7 @@ int k1_launch(const K1Tables &kt, const K1Launch &a, int *launched) {
     uint64_t blocks = ntiles;
     const uint64_t cap = uint64_t(a.sm_count) * 2;
     if (blocks > cap) blocks = cap;
-    k1_tilesort_kernel<<<unsigned(blocks), K1_SORT_THREADS, 0, a.stream>>>(a.spans, a.n, a.d_recs, a.d_task_counter,
-                                                                          a.d_overflow);
+    RXM_LAUNCH(k1_tilesort_kernel, unsigned(blocks), K1_SORT_THREADS, 0, a.stream, a.spans, a.n, a.d_recs, a.d_task_counter, a.d_overflow);
     *launched = 1;
     int st;
     if (kt.mode == K1_DIRECT) st = kt.reversed ? launch_direct_l<true>(kt, a) : launch_direct_l<false>(kt, a);

@@ -9,6 +9,7 @@
 // functions run in the CPU test tier on a SIMT emulator.
 #define RXM_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define RXM_DYN_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
+#define RXM_DYN_SMEM_128(name) extern __shared__ __align__(128) uint8_t name[]
 #endif
 
 #include <cstdint>

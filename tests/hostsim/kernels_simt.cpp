@@ -2,8 +2,9 @@
 // (rxm_k1b.cu) and the tokeniser (rxm_tok.cu), kernels AND launch functions -- compiled for the
 // HOST under the SIMT emulator of simt_shim.hpp, so that the code the GPU runs (not a restatement
 // of it) is checked against the golden vectors in the CPU test tier, and a divergent collective,
-// a deadlock or an endless loop is reported here instead of hanging a GPU.  (K1's scan kernel uses
-// cp.async and inline PTX and stays GPU-only.)  Built into tests/hostsim/libhostsim.so and loaded
+// a deadlock or an endless loop is reported here instead of hanging a GPU.  (K1's five PTX helpers --
+// cp.async, ld.shared.v4, mad.lo -- have host twins in rxm_k1.cu; everything else is the same text.)
+// Built into tests/hostsim/libhostsim.so and loaded
 // only by tests.
 #define RXM_SIMT_HOST 1
 #include "simt_shim.hpp"
@@ -12,6 +13,7 @@
 #include <vector>
 
 static unsigned long long rxm_k3_simt_iterations = 0;  // counted by the K3 kernel under RXM_SIMT_HOST
+#include "../../re2-modification_b200/csrc/rxm_k1.cu"
 #include "../../re2-modification_b200/csrc/rxm_k1b.cu"
 #include "../../re2-modification_b200/csrc/rxm_k2.cu"
 #include "../../re2-modification_b200/csrc/rxm_k3.cu"
@@ -86,6 +88,39 @@ extern "C" int hostsim_k3_batch(const rxm_tables *t, const uint8_t *chars, const
                         rxm::Spans{off, off + 1}, order_idx ? recs.data() : nullptr, n, out, &work[0], &work[1],
                         /*sm_count=*/2, /*sharing=*/1, nullptr, &launched);
     if (overflow_out) *overflow_out = work[0];
+    return run.finish(st, msg_out, msg_cap);
+}
+
+// K1 through rxm::plan_dfa, rxm::k1_build_tables and rxm::k1_launch: the tile sort, then the scan
+// kernel the tables select (quad stride / direct / two-lookup; RXM_K1_NOQUAD and RXM_K1_VARIANT are
+// read as on the device).  info3 (may be null) <- sets, byte classes, bytes per lookup.
+extern "C" int hostsim_k1_batch(const rxm_tables *t, const uint8_t *chars, const uint64_t *off, uint64_t n,
+                                uint8_t *out, uint64_t limit, unsigned long long *overflow_out, uint32_t *info3,
+                                char *msg_out, uint32_t msg_cap, uint64_t seed) {
+    rxm::DfaPlan p;
+    std::string err;
+    int st = rxm::plan_dfa(*t, p, &err);
+    if (st != RXM_OK) return st;
+    rxm::K1Tables kt;
+    std::vector<uint8_t> table, accept;
+    st = rxm::k1_build_tables(p, kt, table, accept, &err);
+    if (st != RXM_OK) return st;
+    if (info3) {
+        info3[0] = p.n_states;
+        info3[1] = p.n_classes;
+        info3[2] = kt.quad ? 4 : 1;
+    }
+    table.resize(table.size() + 64);  // the kernels copy whole 16-byte vectors
+    accept.resize(accept.size() + 256);
+    std::vector<rxm::K1Rec> recs(n + (n >> 3) + 32);
+    uint32_t counter[64] = {0};
+    unsigned long long overflow = 0;
+    Run run(limit, seed);
+    int launched = 0;
+    rxm::K1Launch a{table.data(), accept.data(), chars, rxm::Spans{off, off + 1}, n, out, recs.data(), counter, &overflow,
+                    /*sm_count=*/2, nullptr};
+    st = rxm::k1_launch(kt, a, &launched);
+    if (overflow_out) *overflow_out = overflow;
     return run.finish(st, msg_out, msg_cap);
 }
 

@@ -281,12 +281,12 @@ inline int launch_block(const std::function<void()> &body, int nthreads, uint8_t
 // One warp (the emulator's self-tests use it).
 inline int launch_warp(const std::function<void()> &body, size_t smem_bytes, uint64_t limit, const char **msg,
                        uint64_t seed = 0) {
-    std::vector<uint8_t> smem(smem_bytes + 64, 0xcd);  // dirty: the kernel must initialise what it reads
+    std::vector<uint8_t> smem(smem_bytes + 256, 0xcd);  // dirty: the kernel must initialise what it reads
     State &s = S();
     s.bidx = Idx{0, 0, 0};
     s.gdim = Idx{1, 1, 1};
     return launch_block(body, kLanes,
-                        reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem.data()) + 15) & ~uintptr_t(15)), limit,
+                        reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem.data()) + 127) & ~uintptr_t(127)), limit,
                         msg, seed);
 }
 
@@ -297,8 +297,8 @@ inline void launch_grid(unsigned grid, unsigned block, size_t smem_bytes, const 
     State &s = S();
     s.launches++;
     if (s.last_failure) return;
-    std::vector<uint8_t> smem(smem_bytes + 64, 0xcd);
-    uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem.data()) + 15) & ~uintptr_t(15));
+    std::vector<uint8_t> smem(smem_bytes + 256, 0xcd);
+    uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem.data()) + 127) & ~uintptr_t(127));
     s.gdim = Idx{grid, 1, 1};
     for (unsigned b = 0; b < grid; b++) {
         s.bidx = Idx{b, 0, 0};
@@ -379,6 +379,13 @@ inline unsigned reduce_add(unsigned mask, unsigned v, int site) {
     return r;
 }
 
+// 32-bit shared-memory addresses (PTX ld.shared / cp.async operands): offsets into the emulated
+// block's dynamic shared memory, biased so that 0 is never a valid one.
+constexpr uint32_t kSharedBias = 1u << 16;  // a multiple of every alignment the kernels ask for
+inline uint8_t *shared_ptr(uint32_t addr) { return S().smem + (addr - kSharedBias); }
+inline unsigned mask_or_full() { return 0xffffffffu; }  // __syncwarp() without a mask
+inline unsigned mask_or_full(unsigned m) { return m; }
+
 }  // namespace simt
 
 // ---- the device vocabulary ----
@@ -395,7 +402,7 @@ inline unsigned reduce_add(unsigned mask, unsigned v, int site) {
 #define gridDim (simt::S().gdim)
 
 #define __syncthreads() simt::sync_block(__LINE__)
-#define __syncwarp(m) ((void)simt::meet((m), __LINE__, 0))
+#define __syncwarp(...) ((void)simt::meet(simt::mask_or_full(__VA_ARGS__), __LINE__, 0))
 #define __ballot_sync(m, p) simt::ballot((m), (p), __LINE__)
 #define __any_sync(m, p) (simt::ballot((m), (p), __LINE__) != 0u)
 #define __all_sync(m, p) (simt::ballot((m), (p), __LINE__) == 0xffffffffu)
@@ -433,6 +440,15 @@ static inline unsigned __brev(unsigned x) {
 }
 static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
     return unsigned(((uint64_t(hi) << 32) | lo) >> (shift & 31u));
+}
+static inline size_t __cvta_generic_to_shared(const void *p) {
+    return size_t(static_cast<const uint8_t *>(p) - simt::S().smem) + simt::kSharedBias;
+}
+static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned sel) {
+    const uint64_t v = (uint64_t(y) << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) r |= unsigned((v >> (8 * ((sel >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+    return r;
 }
 template <typename T>
 static inline T __ldg(const T *p) {
@@ -492,5 +508,6 @@ static inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t
 #define RXM_LAUNCH(kern, grid, block, smem, stream, ...) \
     simt::launch_grid((grid), (block), (smem), [&]() { kern(__VA_ARGS__); })
 #define RXM_DYN_SMEM(name) uint8_t *name = simt::S().smem
+#define RXM_DYN_SMEM_128(name) uint8_t *name = simt::S().smem
 
 #endif
