@@ -1,16 +1,23 @@
 """Tuning helper (GPU): config 4's two jobs (example 2 forward / -reverse on attack strings) timed
 alone and side by side, with and without rxm_set_concurrency.  python tools/k3_jobs_time.py"""
 import os
-import sys
 
 import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "tests"))
-import helpers as H  # noqa: E402  (only for the module loaders; the oracle is not touched)
+PKG = os.path.join(ROOT, "re2-modification_b200")
 
-rxm, W = H.rxm, H.load_workloads()
+
+def _load(name):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(name, os.path.join(PKG, name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+rxm, W = _load("rxm"), _load("workloads")
 dev = torch.device("cuda:0")
 c_np, o_np = W.attack_batch(["bbaa", "aaba", "bbaa"], "c", "", 4096, 435, 65536, 1000)
 ch, of = torch.from_numpy(c_np).to(dev), torch.from_numpy(o_np.astype(np.int64)).to(dev)
