@@ -681,7 +681,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel_ms": k_ms,
-                         "algorithmic_bytes_per_launch": algo_bytes},
+                         "algorithmic_bytes_per_launch": algo_bytes,
+                         "frac_of_nominal_8_tb_s": achieved / 8000.0},  # both denominators
             "e2e": {"value": e2e_value, "unit": "strings/s",
                     "h2d_bytes_per_step": total_bytes + 8 * (n + len(jobs)), "d2h_bytes_per_step": n + 8 * len(jobs),
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
