@@ -106,3 +106,18 @@ def test_epsilon_cycle_is_unsupported(text):
     with pytest.raises(rxm.RxmError) as e:
         rxm.Matcher(t, 0)
     assert e.value.status == rxm.RXM_ERR_UNSUPPORTED
+
+
+def test_every_kernel_launch_goes_through_rxm_launch():
+    """The CPU tier runs the kernel sources on the SIMT emulator (tests/hostsim) only as long as
+    no launch bypasses RXM_LAUNCH and no kernel declares its dynamic shared memory by hand."""
+    import glob
+    import re
+    csrc = os.path.join(H.PKG, "csrc")
+    for path in glob.glob(os.path.join(csrc, "*.cu")):
+        text = open(path).read()
+        text = re.sub(r"//[^\n]*", "", text)
+        assert "<<<" not in text, path
+        assert "extern __shared__" not in text, path
+    header = re.sub(r"//[^\n]*", "", open(os.path.join(csrc, "rxm_kernels.cuh")).read())
+    assert header.count("<<<") == 1 and "RXM_LAUNCH" in header
