@@ -167,10 +167,10 @@ int rxm_match_text(rxm_handle h, const uint8_t *text, uint64_t nbytes, uint8_t *
 
 /*
  * Hint (optional; default 1): up to `handles` matchers are used at once on this device, each on
- * a stream of its own.  The MFA kernels are persistent -- one launch occupies every block slot
+ * a stream of its own.  The MFA kernel K3 is persistent -- one launch occupies every block slot
  * of the device until its strings are handed out -- so a second handle's kernel would start
- * when the first one's blocks retire.  With the hint each launch of `h` takes 1/handles of the
- * slots and the others run beside it.  Worth it for batches bounded by their longest string
+ * when the first one's blocks retire.  With the hint each K3 launch of `h` takes 1/handles of the
+ * slots and the others run beside it (the other engines ignore it).  Worth it for batches bounded by their longest string
  * (the reference's attack strings: forward and -reverse automaton of one expression side by
  * side); throughput-bound batches are better left at 1.  No reference counterpart: the
  * reference matches one expression per process (matchers/match.cpp:10-32).
