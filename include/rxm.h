@@ -170,10 +170,11 @@ int rxm_match_text(rxm_handle h, const uint8_t *text, uint64_t nbytes, uint8_t *
  * a stream of its own.  The MFA kernel K3 is persistent -- one launch occupies every block slot
  * of the device until its strings are handed out -- so a second handle's kernel would start
  * when the first one's blocks retire.  With the hint each K3 launch of `h` takes 1/handles of the
- * slots and the others run beside it (the other engines ignore it).  Worth it for batches bounded by their longest string
- * (the reference's attack strings: forward and -reverse automaton of one expression side by
- * side); throughput-bound batches are better left at 1.  No reference counterpart: the
- * reference matches one expression per process (matchers/match.cpp:10-32).
+ * slots and the others run beside it (the other engines ignore it).  Worth it for batches
+ * bounded by their longest string (the reference's attack strings: forward and -reverse
+ * automaton of one expression side by side); throughput-bound batches are better left at 1.
+ * No reference counterpart: the reference matches one expression per process
+ * (matchers/match.cpp:10-32).
  */
 int rxm_set_concurrency(rxm_handle h, uint32_t handles);
 
