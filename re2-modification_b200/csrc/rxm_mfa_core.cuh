@@ -594,6 +594,9 @@ RXM_UNROLL
         }
         for (uint32_t i = 0;; i++) {
             if (i < n && cnt[nb ^ 1u] == 0) break;
+#ifdef RXM_PROGSIM_OBSERVE  // tests/hostsim: statistics on the sets the steps start from
+            RXM_PROGSIM_OBSERVE(buf[nb ^ 1u], cnt[nb ^ 1u], i, rd);
+#endif
             step(t, pv, rd, i);
             steps_run++;
             nb ^= 1u;

@@ -7,10 +7,68 @@
 #include <vector>
 
 #include "../../include/rxm.h"
+
+// How periodic is the work?  Before every step ProgSim runs, its starting set is compared with the
+// set the previous step started from: `periodic` = the same set with every `first` moved on by the
+// distance between the two steps (cells, flags, stamps identical), the same input letter, forward
+// reading -- a step whose outcome is fixed by the outcome of its block compares alone;
+// `confirmed` = the step before it was periodic too, over the same distance (the phase goes on).
+static uint64_t g_obs_steps = 0, g_obs_periodic = 0, g_obs_confirmed = 0;
+static int g_obs_relaxed = 0;  // 1: open cells may grow by the distance (letter loops inside a cell)
+template <class CfgT, class ReaderT>
+static void progsim_observe(const CfgT *cur, uint32_t m, uint32_t i, const ReaderT &rd);
+#define RXM_PROGSIM_OBSERVE(cur, m, i, rd) progsim_observe(cur, m, i, rd)
 #include "../../re2-modification_b200/csrc/rxm_mfa_core.cuh"
 #include "../../re2-modification_b200/csrc/rxm_mfa_dispatch.hpp"
 #include "../../re2-modification_b200/csrc/rxm_nfa_core.cuh"
 #include "../../re2-modification_b200/csrc/rxm_plan.hpp"
+
+template <class CfgT, class ReaderT>
+static void progsim_observe(const CfgT *cur, uint32_t m, uint32_t i, const ReaderT &rd) {
+    static std::vector<CfgT> prev;
+    static uint32_t prev_i = 0, prev_delta = 0;
+    static bool prev_periodic = false;
+    g_obs_steps++;
+    bool periodic = false;
+    uint32_t delta = 0;
+    if (i != 0) {
+        delta = i - prev_i;
+        periodic = !rd.reversed && i < rd.n && m == prev.size() && rd.at(i) == rd.at(prev_i);
+        for (uint32_t j = 0; j < m && periodic; j++) {
+            bool found = false;
+            for (const CfgT &q : prev) {
+                if (q.node != cur[j].node) continue;
+                CfgT moved = q;
+                moved.first += delta;
+                if (g_obs_relaxed) {  // an open cell may have grown by the letters read in between
+                    for (int k = 0; k < int(sizeof(q.len) / sizeof(q.len[0])); k++)
+                        if (rxm::fl_exists(q.flags, k) && rxm::fl_open(q.flags, k)) {
+                            if (moved.len[k] == 0) moved.start[k] = cur[j].start[k];
+                            moved.len[k] += delta;
+                        }
+                }
+                found = rxm::cfg_same(moved, cur[j]) && q.born == cur[j].born;
+                break;
+            }
+            periodic = found;
+        }
+        if (periodic) {
+            g_obs_periodic++;
+            if (prev_periodic && prev_delta == delta) g_obs_confirmed++;
+        }
+    }
+    prev.assign(cur, cur + m);
+    prev_i = i;
+    prev_delta = delta;
+    prev_periodic = periodic;
+}
+extern "C" void hostsim_periodic_relaxed(int on) { g_obs_relaxed = on; }
+extern "C" void hostsim_periodic_stats(uint64_t *steps, uint64_t *periodic, uint64_t *confirmed) {
+    *steps = g_obs_steps;
+    *periodic = g_obs_periodic;
+    *confirmed = g_obs_confirmed;
+    g_obs_steps = g_obs_periodic = g_obs_confirmed = 0;
+}
 
 static uint64_t g_steps_run = 0, g_steps_skipped = 0;
 extern "C" void hostsim_step_stats(uint64_t *run, uint64_t *skipped) {
