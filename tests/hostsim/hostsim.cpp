@@ -15,6 +15,7 @@
 // `confirmed` = the step before it was periodic too, over the same distance (the phase goes on).
 static uint64_t g_obs_steps = 0, g_obs_periodic = 0, g_obs_confirmed = 0;
 static int g_obs_relaxed = 0;  // 1: open cells may grow by the distance (letter loops inside a cell)
+static int g_obs_period = 1;   // compare with the set this many steps back (1..8)
 template <class CfgT, class ReaderT>
 static void progsim_observe(const CfgT *cur, uint32_t m, uint32_t i, const ReaderT &rd);
 #define RXM_PROGSIM_OBSERVE(cur, m, i, rd) progsim_observe(cur, m, i, rd)
@@ -23,46 +24,61 @@ static void progsim_observe(const CfgT *cur, uint32_t m, uint32_t i, const Reade
 #include "../../re2-modification_b200/csrc/rxm_nfa_core.cuh"
 #include "../../re2-modification_b200/csrc/rxm_plan.hpp"
 
+template <class CfgT>
+static bool moved_equal(const std::vector<CfgT> &prev, const CfgT *cur, uint32_t m, uint32_t delta) {
+    if (m != prev.size()) return false;
+    for (uint32_t j = 0; j < m; j++) {
+        bool found = false;
+        for (const CfgT &q : prev) {
+            if (q.node != cur[j].node) continue;
+            CfgT moved = q;
+            moved.first += delta;
+            if (g_obs_relaxed) {  // an open cell may have grown by the letters read in between
+                for (int k = 0; k < int(sizeof(q.len) / sizeof(q.len[0])); k++)
+                    if (rxm::fl_exists(q.flags, k) && rxm::fl_open(q.flags, k)) {
+                        if (moved.len[k] == 0) moved.start[k] = cur[j].start[k];
+                        moved.len[k] += delta;
+                    }
+            }
+            found = rxm::cfg_same(moved, cur[j]) && q.born == cur[j].born;
+            break;
+        }
+        if (!found) return false;
+    }
+    return true;
+}
+
+// g_obs_period = p: the set is compared with the one p steps back (p = 1: the step before).
 template <class CfgT, class ReaderT>
 static void progsim_observe(const CfgT *cur, uint32_t m, uint32_t i, const ReaderT &rd) {
-    static std::vector<CfgT> prev;
-    static uint32_t prev_i = 0, prev_delta = 0;
+    constexpr int H = 8;
+    static std::vector<CfgT> hist[H];
+    static uint32_t hist_i[H];
+    static int n_hist = 0;
+    static uint32_t prev_delta = 0;
     static bool prev_periodic = false;
+    if (i == 0) n_hist = 0, prev_periodic = false;
     g_obs_steps++;
     bool periodic = false;
     uint32_t delta = 0;
-    if (i != 0) {
-        delta = i - prev_i;
-        periodic = !rd.reversed && i < rd.n && m == prev.size() && rd.at(i) == rd.at(prev_i);
-        for (uint32_t j = 0; j < m && periodic; j++) {
-            bool found = false;
-            for (const CfgT &q : prev) {
-                if (q.node != cur[j].node) continue;
-                CfgT moved = q;
-                moved.first += delta;
-                if (g_obs_relaxed) {  // an open cell may have grown by the letters read in between
-                    for (int k = 0; k < int(sizeof(q.len) / sizeof(q.len[0])); k++)
-                        if (rxm::fl_exists(q.flags, k) && rxm::fl_open(q.flags, k)) {
-                            if (moved.len[k] == 0) moved.start[k] = cur[j].start[k];
-                            moved.len[k] += delta;
-                        }
-                }
-                found = rxm::cfg_same(moved, cur[j]) && q.born == cur[j].born;
-                break;
-            }
-            periodic = found;
-        }
+    const int p = g_obs_period;
+    if (n_hist >= p) {
+        const int slot = (n_hist - p) % H;
+        delta = i - hist_i[slot];
+        periodic = !rd.reversed && i < rd.n && rd.at(i) == rd.at(hist_i[slot]) && moved_equal(hist[slot], cur, m, delta);
         if (periodic) {
             g_obs_periodic++;
             if (prev_periodic && prev_delta == delta) g_obs_confirmed++;
         }
     }
-    prev.assign(cur, cur + m);
-    prev_i = i;
+    hist[n_hist % H].assign(cur, cur + m);
+    hist_i[n_hist % H] = i;
+    n_hist++;
     prev_delta = delta;
     prev_periodic = periodic;
 }
 extern "C" void hostsim_periodic_relaxed(int on) { g_obs_relaxed = on; }
+extern "C" void hostsim_periodic_period(int p) { g_obs_period = p < 1 ? 1 : (p > 8 ? 8 : p); }
 extern "C" void hostsim_periodic_stats(uint64_t *steps, uint64_t *periodic, uint64_t *confirmed) {
     *steps = g_obs_steps;
     *periodic = g_obs_periodic;
