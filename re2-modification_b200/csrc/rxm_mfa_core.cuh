@@ -481,6 +481,19 @@ struct ProgSim {
     uint32_t nb;
     uint32_t steps_run, steps_skipped;
     bool overflow;
+    // REPEATED STEPS (host study for the next K3 step; off unless `replay` is set): a
+    // step that starts from the set the previous step started from, moved on by the distance delta
+    // between the two, with the same letter and the same outcomes of the same block compares, ends
+    // in the previous result moved on by delta -- so only the compares are evaluated.
+    bool replay = false;
+    uint32_t steps_replayed = 0;
+    struct CmpLog {
+        uint32_t vs, L;
+        bool attempted, ok;
+    };
+    CmpLog cmp_log[16];
+    uint32_t n_cmp = 0;
+    bool log_bad = false;  // a read of an OPEN cell (its text changes) or more reads than the log holds
 
     RXM_HD void insert(const cfg_t &c) {
         cfg_t *nxt = buf[nb];
@@ -553,7 +566,13 @@ RXM_UNROLL
                 const bool fresh = (pi_created(it) >> k) & 1u;
                 const uint32_t L = fresh ? 0u : root.len[k < NC ? k : 0];
                 const uint32_t vs = root.start[k < NC ? k : 0];
-                if (n - i >= L && (L == 0 || rd.span_equal(vs, i, L))) {
+                const bool attempted = (n - i >= L) && L != 0;
+                const bool eq = (n - i >= L) && (L == 0 || rd.span_equal(vs, i, L));
+                if (replay) {
+                    if (n_cmp == 16 || (!fresh && fl_open(root.flags, k < NC ? k : 0))) log_bad = true;
+                    else cmp_log[n_cmp++] = CmpLog{vs, L, attempted, eq};
+                }
+                if (eq) {
                     cfg_t nx;
                     prog_working<NC>(nx, root, pi_created(it), pi_created_open(it),
                                      pi_prior_reads(it) & ~digit_bit);
@@ -574,8 +593,36 @@ RXM_UNROLL
         for (uint32_t j = 0; j < ncur; j++) eval(t, pv, rd, cur[j], i);  // any order: see prog_stamp
     }
 
+    // b == a with every `first` moved on by delta and every open cell grown by delta (the letters read)
+    RXM_HD static bool moved_on(const cfg_t *a, uint32_t na, const cfg_t *b, uint32_t nbb, uint32_t delta) {
+        if (na != nbb) return false;
+        for (uint32_t j = 0; j < nbb; j++) {
+            bool found = false;
+            for (uint32_t q = 0; q < na; q++) {
+                if (a[q].node != b[j].node) continue;
+                cfg_t mv = a[q];
+                mv.first += delta;
+RXM_UNROLL
+                for (int k = 0; k < NC; k++)
+                    if (fl_exists(mv.flags, k) && fl_open(mv.flags, k)) {
+                        if (mv.len[k] == 0) mv.start[k] = b[j].start[k];
+                        mv.len[k] += delta;
+                    }
+                found = cfg_same<NC>(mv, b[j]) && mv.born == b[j].born;
+                break;
+            }
+            if (!found) return false;
+        }
+        return true;
+    }
+
     RXM_HD int run(const MfaView &t, const ProgView &pv, const Reader &rd) {
         const uint32_t n = rd.n;
+        bool have_prev = false;
+        uint32_t prev_i = 0;
+        n_cmp = 0;
+        log_bad = false;
+        steps_replayed = 0;
         overflow = false;
         born = 0;
         steps_run = steps_skipped = 0;
@@ -597,6 +644,36 @@ RXM_UNROLL
 #ifdef RXM_PROGSIM_OBSERVE  // tests/hostsim: statistics on the sets the steps start from
             RXM_PROGSIM_OBSERVE(buf[nb ^ 1u], cnt[nb ^ 1u], i, rd);
 #endif
+            if (replay && have_prev && !t.reversed && !log_bad && i < n && i > prev_i &&
+                moved_on(buf[nb], cnt[nb], buf[nb ^ 1u], cnt[nb ^ 1u], i - prev_i)) {
+                const uint32_t delta = i - prev_i;
+                cfg_t *P = buf[nb ^ 1u];
+                const uint32_t m = cnt[nb ^ 1u];
+                for (;;) {
+                    // everything the step and the jump after it ask about the end of the string stays as it was
+                    bool same = uint64_t(i) + delta + 2 < n && rd.at(i) == rd.at(prev_i);
+                    for (uint32_t j = 0; j < m && same; j++)
+                        if (uint64_t(P[j].first) + delta >= n) same = false;
+                    for (uint32_t c = 0; c < n_cmp && same; c++) {
+                        const CmpLog &cl = cmp_log[c];
+                        if (!cl.attempted) continue;  // the cell's text was too long for the rest: it still is
+                        if (n - i < cl.L || rd.span_equal(cl.vs, i, cl.L) != cl.ok) same = false;
+                    }
+                    if (!same) break;
+                    for (uint32_t j = 0; j < m; j++) {  // the previous result, moved on by delta
+                        P[j].first += delta;
+RXM_UNROLL
+                        for (int k = 0; k < NC; k++)
+                            if (fl_exists(P[j].flags, k) && fl_open(P[j].flags, k)) P[j].len[k] += delta;
+                    }
+                    i += delta;
+                    steps_replayed++;
+                }
+            }
+            n_cmp = 0;
+            log_bad = false;
+            have_prev = true;
+            prev_i = i;
             step(t, pv, rd, i);
             steps_run++;
             nb ^= 1u;

@@ -86,11 +86,20 @@ extern "C" void hostsim_periodic_stats(uint64_t *steps, uint64_t *periodic, uint
     g_obs_steps = g_obs_periodic = g_obs_confirmed = 0;
 }
 
-static uint64_t g_steps_run = 0, g_steps_skipped = 0;
+static uint64_t g_steps_run = 0, g_steps_skipped = 0, g_steps_replayed = 0;
+static int g_prog_replay = 0;  // ProgSim::replay for the next hostsim_prog_batch calls
 extern "C" void hostsim_step_stats(uint64_t *run, uint64_t *skipped) {
     *run = g_steps_run;
     *skipped = g_steps_skipped;
     g_steps_run = g_steps_skipped = 0;
+}
+// Repeated steps (ProgSim::replay): switch, and the number of steps answered by their block compares
+// alone since the last call.
+extern "C" void hostsim_prog_replay(int on) { g_prog_replay = on; }
+extern "C" uint64_t hostsim_steps_replayed() {
+    const uint64_t r = g_steps_replayed;
+    g_steps_replayed = 0;
+    return r;
 }
 
 template <int NC, int CAP, int DMAX>
@@ -126,11 +135,13 @@ template <int NC, int CAP, int DMAX>
 static void run_prog_batch(const rxm::MfaView &v, const rxm::ProgView &pv, const uint8_t *chars,
                            const uint64_t *off, uint64_t n, uint8_t *out) {
     auto *sim = new rxm::ProgSim<NC, CAP>();
+    sim->replay = g_prog_replay != 0;
     for (uint64_t i = 0; i < n; i++) {
         rxm::Reader rd{chars + off[i], uint32_t(off[i + 1] - off[i]), v.reversed};
         out[i] = uint8_t(sim->run(v, pv, rd));
         g_steps_run += sim->steps_run;
         g_steps_skipped += sim->steps_skipped;
+        g_steps_replayed += sim->steps_replayed;
     }
     delete sim;
 }
