@@ -108,7 +108,10 @@ enum {
     RXM_ENGINE_K1_BITSET = 2,  /* memory-free automaton too large to determinise: the active set
                                   itself on the device (follow masks, or an edge walk)             */
     RXM_ENGINE_K2_THREAD = 3,  /* MFA, one thread per string                                        */
-    RXM_ENGINE_K3_WARP = 4     /* MFA, one warp per string (long strings / large automata)          */
+    RXM_ENGINE_K3_WARP = 4,    /* MFA, one warp per string (large automata; takes over the strings that
+                                  outgrow K4's per-thread sets)                                     */
+    RXM_ENGINE_K4_THREAD = 5   /* MFA, one thread per string over host-compiled edge programs, repeated
+                                  steps answered by their block compares alone                      */
 };
 
 typedef struct rxm_plan_info {

@@ -70,6 +70,13 @@ struct rxm_matcher {
     uint32_t *d_prog_count = nullptr;
     uint32_t k3_tile = 32;  // lanes per string
     bool k3_tile_forced = false;
+    // K4: the programs' item lists; strings that outgrow a thread's sets go to K3 through the redo list
+    uint32_t *d_prog_lbeg = nullptr, *d_prog_lcnt = nullptr;
+    uint16_t *d_prog_sel = nullptr;
+    uint32_t k4_maxl = 0;
+    uint32_t *d_redo_list = nullptr;
+    size_t cap_redo = 0;
+    unsigned long long *d_redo_n = nullptr;
     uint32_t sharing = 1;  // rxm_set_concurrency: handles that run at once on this device
 
     // staging workspace for host buffers
@@ -212,7 +219,11 @@ extern "C" int rxm_tables_upload(const rxm_tables *host_tables, int device, rxm_
             if ((st = upload_vec(m->prog.items, &m->d_items)) != RXM_OK) return fail(st);
             if ((st = upload_vec(m->prog.begin, &m->d_prog_begin)) != RXM_OK) return fail(st);
             if ((st = upload_vec(m->prog.count, &m->d_prog_count)) != RXM_OK) return fail(st);
-            m->info.engine = RXM_ENGINE_K3_WARP;
+            if ((st = upload_vec(m->prog.lbeg, &m->d_prog_lbeg)) != RXM_OK) return fail(st);
+            if ((st = upload_vec(m->prog.lcnt, &m->d_prog_lcnt)) != RXM_OK) return fail(st);
+            if ((st = upload_vec(m->prog.sel, &m->d_prog_sel)) != RXM_OK) return fail(st);
+            m->k4_maxl = t.n_states < 8u ? t.n_states : 8u;
+            m->info.engine = (force && std::strcmp(force, "k3") == 0) ? RXM_ENGINE_K3_WARP : RXM_ENGINE_K4_THREAD;
             // short programs: several strings per warp (a step's items fit one pass of the tile)
             m->k3_tile = m->prog.max_count <= 8 ? 8 : (m->prog.max_count <= 16 ? 16 : 32);
             if (const char *tl = getenv("RXM_K3_TILE")) {
@@ -222,8 +233,8 @@ extern "C" int rxm_tables_upload(const rxm_tables *host_tables, int device, rxm_
                     m->k3_tile_forced = true;
                 }
             }
-        } else if (force && std::strcmp(force, "k3") == 0) {
-            err = "RXM_MFA_ENGINE=k3 but the edge programs cannot be built: " + perr;
+        } else if (force && (std::strcmp(force, "k3") == 0 || std::strcmp(force, "k4") == 0)) {
+            err = "RXM_MFA_ENGINE=k3/k4 but the edge programs cannot be built: " + perr;
             return fail(RXM_ERR_UNSUPPORTED);
         }
     }
@@ -255,6 +266,11 @@ extern "C" int rxm_free(rxm_handle h) {
     cudaFree(h->d_items);
     cudaFree(h->d_prog_begin);
     cudaFree(h->d_prog_count);
+    cudaFree(h->d_prog_lbeg);
+    cudaFree(h->d_prog_lcnt);
+    cudaFree(h->d_prog_sel);
+    cudaFree(h->d_redo_list);
+    cudaFree(h->d_redo_n);
     cudaFree(h->d_chars);
     cudaFree(h->d_offsets);
     cudaFree(h->d_bits);
@@ -352,6 +368,40 @@ static int launch_on_device(rxm_matcher *m, const uint8_t *d_chars, rxm::Spans s
         st = rxm::k1b_launch(m->d_edge_begin, m->d_k1b_edges, m->tables.n_states(), m->tables.n_edges(),
                              m->tables.start, m->tables.finish, m->tables.reversed, d_chars, spans, order, n, d_out,
                              m->d_overflow, m->d_overflow + 1, m->sm_count, stream, &launched);
+    } else if (m->info.engine == RXM_ENGINE_K4_THREAD) {
+        rxm::MfaView v{m->d_edge_begin, m->d_edges, m->tables.n_states(), m->tables.start,
+                       m->tables.finish, m->tables.reversed};
+        rxm::K4Prog kp{m->d_items, m->d_prog_begin, m->d_prog_count, m->d_prog_lbeg, m->d_prog_lcnt, m->d_prog_sel,
+                       m->prog.n_cells};
+        const rxm::K1Rec *order = nullptr;
+        if ((st = prepare_order(m, spans, n, stream, &order, &launched_extra)) != RXM_OK) return st;
+        // automata with more nodes than a thread has slots: strings that outgrow them are run by K3
+        const bool redo = m->tables.n_states() > m->k4_maxl;
+        if (redo) {
+            if (n > 0xfffffff0ull) return RXM_ERR_UNSUPPORTED;
+            if (n > m->cap_redo) {
+                cudaFree(m->d_redo_list);
+                m->d_redo_list = nullptr;
+                m->cap_redo = 0;
+                const size_t want = size_t(n + (n >> 3) + 32);
+                CU(cudaMalloc(reinterpret_cast<void **>(&m->d_redo_list), want * sizeof(uint32_t)));
+                m->cap_redo = want;
+            }
+            if (!m->d_redo_n) CU(cudaMalloc(reinterpret_cast<void **>(&m->d_redo_n), sizeof(unsigned long long)));
+            CU(cudaMemsetAsync(m->d_redo_n, 0, sizeof(unsigned long long), stream));
+        }
+        st = rxm::k4_launch(v, kp, uint32_t(m->prog.items.size()), uint32_t(m->prog.begin.size()),
+                            uint32_t(m->prog.sel.size()), m->tables.n_cells, m->k4_maxl, d_chars, spans, order, n, d_out,
+                            m->d_overflow, m->d_overflow + 1, redo ? m->d_redo_list : nullptr, m->d_redo_n, m->sm_count,
+                            m->sharing, stream, &launched);
+        if (st == RXM_OK && redo) {
+            int l3 = 0;
+            rxm::ProgView gp{m->d_items, m->d_prog_begin, m->d_prog_count, m->prog.n_cells};
+            st = rxm::k3_launch(v, gp, uint32_t(m->prog.items.size()), uint32_t(m->prog.begin.size()), m->tables.n_cells,
+                                m->k3_tile, d_chars, spans, nullptr, n, d_out, m->d_overflow, m->d_overflow + 1,
+                                m->sm_count, m->sharing, stream, &l3, m->d_redo_list, m->d_redo_n);
+            launched_extra += l3;
+        }
     } else if (m->info.engine == RXM_ENGINE_K3_WARP) {
         rxm::MfaView v{m->d_edge_begin, m->d_edges, m->tables.n_states(), m->tables.start,
                        m->tables.finish, m->tables.reversed};

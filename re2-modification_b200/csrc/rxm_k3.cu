@@ -165,8 +165,12 @@ __global__ void __launch_bounds__(K3_WARPS * 32, TILE == 32 ? 1 : RXM_K3_MIN_BLO
 k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, uint32_t items_in_smem,
                    const uint8_t *__restrict__ chars, const Spans sp, const K1Rec *__restrict__ recs, uint64_t n,
                    uint8_t *__restrict__ out, unsigned long long *__restrict__ overflow,
-                   unsigned long long *__restrict__ next_string) {
+                   unsigned long long *__restrict__ next_string, const uint32_t *__restrict__ list,
+                   const unsigned long long *__restrict__ list_n) {
     RXM_DYN_SMEM(smem);
+    // list != null: the strings to run are list[0 .. *list_n) (K4 hands over the strings that outgrew its
+    // per-thread sets; the count is only known on the device)
+    if (list) n = *list_n;
     constexpr uint32_t ALL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & (TILE - 1u);              // rank inside the tile
     const uint32_t tile = threadIdx.x / TILE;                     // tile index inside the block
@@ -238,6 +242,7 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
                 } else if (si >= n) {
                     exhausted = true;
                 } else {
+                    if (list) si = list[si];
                     const uint64_t sb = sp.begin[si], se = sp.end[si];
                     if (se - sb >= (1ull << 28)) {  // first must fit 28 bits of the order key
                         if (lane == 0) {
@@ -529,7 +534,8 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
 template <int NC, int TILE>
 int launch_k3(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n_keys, const uint8_t *d_chars,
               Spans spans, const K1Rec *d_recs, uint64_t n, uint8_t *d_out, unsigned long long *d_overflow,
-              unsigned long long *d_next, int sm_count, uint32_t sharing, cudaStream_t stream) {
+              unsigned long long *d_next, int sm_count, uint32_t sharing, cudaStream_t stream, const uint32_t *d_list,
+              const unsigned long long *d_list_n) {
     constexpr int TILES = K3_WARPS * 32 / TILE;  // strings in flight per block
     const uint32_t SP = (v.n_states + TILE - 1u) & ~uint32_t(TILE - 1);
     const size_t per_tile = size_t(SP) * 2 * (8 + 4 + 8 * NC) + size_t(SP) * 12 + 16;
@@ -538,7 +544,8 @@ int launch_k3(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n
     const size_t smem = tab + (in_smem ? size_t(n_items) * sizeof(ProgItem) : 0) + TILES * per_tile;
     if (smem > 200 * 1024) return RXM_ERR_UNSUPPORTED;
     auto kern = k3_mfa_warp_kernel<NC, TILE>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+    // always the same value: handles that share a kernel instantiation may launch from several threads
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
         return RXM_ERR_CUDA;
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, K3_WARPS * 32, smem) != cudaSuccess || nb <= 0)
@@ -550,22 +557,23 @@ int launch_k3(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n
     if (blocks > need) blocks = need;
     if (cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), stream) != cudaSuccess) return RXM_ERR_CUDA;
     RXM_LAUNCH(kern, unsigned(blocks), K3_WARPS * 32, smem, stream, v, gp, n_items, n_keys, in_smem ? 1u : 0u, d_chars, spans,
-               d_recs, n, d_out, d_overflow, d_next);
+               d_recs, n, d_out, d_overflow, d_next, d_list, d_list_n);
     return RXM_OK;
 }
 
 template <int NC>
 int launch_k3_tile(uint32_t tile, const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n_keys,
                    const uint8_t *d_chars, Spans spans, const K1Rec *d_recs, uint64_t n, uint8_t *d_out,
-                   unsigned long long *d_overflow, unsigned long long *d_next, int sm_count, uint32_t sharing, cudaStream_t stream) {
+                   unsigned long long *d_overflow, unsigned long long *d_next, int sm_count, uint32_t sharing, cudaStream_t stream,
+                   const uint32_t *d_list, const unsigned long long *d_list_n) {
     // the per-string state (two buffers of one slot per node) of all strings of a block must fit
     // shared memory: automata with many nodes move to wider tiles (fewer strings per block)
     int st = RXM_ERR_UNSUPPORTED;
-    if (tile <= 8) st = launch_k3<NC, 8>(v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream);
+    if (tile <= 8) st = launch_k3<NC, 8>(v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream, d_list, d_list_n);
     if (st == RXM_ERR_UNSUPPORTED && tile <= 16)
-        st = launch_k3<NC, 16>(v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream);
+        st = launch_k3<NC, 16>(v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream, d_list, d_list_n);
     if (st == RXM_ERR_UNSUPPORTED)
-        st = launch_k3<NC, 32>(v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream);
+        st = launch_k3<NC, 32>(v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream, d_list, d_list_n);
     return st;
 }
 
@@ -574,12 +582,12 @@ int launch_k3_tile(uint32_t tile, const MfaView &v, const ProgView &gp, uint32_t
 int k3_launch(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n_keys, uint32_t n_cells,
               uint32_t tile, const uint8_t *d_chars, Spans spans, const K1Rec *d_recs, uint64_t n, uint8_t *d_out,
               unsigned long long *d_overflow, unsigned long long *d_next, int sm_count, uint32_t sharing,
-              cudaStream_t stream, int *launched) {
+              cudaStream_t stream, int *launched, const uint32_t *d_list, const unsigned long long *d_list_n) {
     *launched = 0;
     int st;
-    if (n_cells <= 1) st = launch_k3_tile<1>(tile, v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream);
-    else if (n_cells <= 2) st = launch_k3_tile<2>(tile, v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream);
-    else if (n_cells <= 4) st = launch_k3_tile<4>(tile, v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream);
+    if (n_cells <= 1) st = launch_k3_tile<1>(tile, v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream, d_list, d_list_n);
+    else if (n_cells <= 2) st = launch_k3_tile<2>(tile, v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream, d_list, d_list_n);
+    else if (n_cells <= 4) st = launch_k3_tile<4>(tile, v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream, d_list, d_list_n);
     else return RXM_ERR_UNSUPPORTED;
     if (st == RXM_OK) *launched = 1;
     return st;

@@ -18,6 +18,7 @@
 
 #include "../../include/rxm.h"
 #include "rxm_mfa_core.cuh"
+#include "rxm_k4_core.cuh"
 #include "rxm_plan.hpp"
 
 namespace rxm {
@@ -105,7 +106,17 @@ int k3_launch(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n
               const K1Rec *d_recs /* tile-sorted order, or null: index order */, uint64_t n, uint8_t *d_out,
               unsigned long long *d_overflow, unsigned long long *d_next, int sm_count,
               uint32_t sharing /* handles running at once on the device: the grid takes 1/sharing of the block slots */,
-              cudaStream_t stream, int *launched);
+              cudaStream_t stream, int *launched,
+              const uint32_t *d_list = nullptr /* run strings d_list[0 .. *d_list_n) instead of 0 .. n (n = the list's capacity) */,
+              const unsigned long long *d_list_n = nullptr);
+
+// ---- K4: MFA, one thread per string, over the same edge programs (rxm_k4_core.cuh) ------------
+// maxl = live configurations a thread keeps per set; a string that needs more is appended to
+// d_redo_list (capacity n) / *d_redo_n for K3 to run, or counted in d_overflow when the list is null.
+int k4_launch(const MfaView &v, const K4Prog &gp, uint32_t n_items, uint32_t n_keys, uint32_t n_sel, uint32_t n_cells,
+              uint32_t maxl, const uint8_t *d_chars, Spans spans, const K1Rec *d_recs, uint64_t n, uint8_t *d_out,
+              unsigned long long *d_overflow, unsigned long long *d_next, uint32_t *d_redo_list,
+              unsigned long long *d_redo_n, int sm_count, uint32_t sharing, cudaStream_t stream, int *launched);
 
 // ---- tokeniser: whitespace-delimited text -> spans (rxm_tok.cu) ------------------------------
 // Same token boundaries as `cin >> text` (matchers/match.cpp:22-23): whitespace is

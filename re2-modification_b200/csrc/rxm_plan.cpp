@@ -273,6 +273,25 @@ int compile_programs(const rxm_tables &t, MfaProgram &out, std::string *err) {
         for (size_t x = g.root_start + 1; x < out.items.size() && stable; x++)
             if (!(out.items[x].a & 1u) && (out.items[x].a & 4u)) stable = false;  // a deeper call with a leaf
         if (stable) out.count[key] |= kProgStable;
+        {   // K4's item lists: leaves, then the enters that can insert
+            if (out.lbeg.empty()) {
+                out.lbeg.assign(out.begin.size(), 0);
+                out.lcnt.assign(out.begin.size(), 0);
+            }
+            out.lbeg[key] = uint32_t(out.sel.size());
+            uint32_t leaves = 0, enters = 0;
+            for (size_t x = g.root_start; x < out.items.size(); x++)
+                if (out.items[x].a & 1u) {
+                    out.sel.push_back(uint16_t(x - g.root_start));
+                    leaves++;
+                }
+            for (size_t x = g.root_start; x < out.items.size(); x++)
+                if (!(out.items[x].a & 1u) && ((out.items[x].a & 4u) || (out.items[x].a >> 16) == t.finish)) {
+                    out.sel.push_back(uint16_t(x - g.root_start));
+                    enters++;
+                }
+            out.lcnt[key] = leaves | (enters << 16);
+        }
         for (const auto &f : g.found) {
             const size_t k2 = (size_t(f.first) << t.n_cells) | (f.second & (nm - 1));
             if (out.begin[k2] == 0xffffffffu) work.push_back(f);

@@ -57,6 +57,13 @@ struct MfaProgram {
     std::vector<uint32_t> begin;  // [node << n_cells | mask] -> first item, 0xffffffff if unreachable
     std::vector<uint32_t> count;  // [node << n_cells | mask] -> number of items
     uint32_t max_count = 0;
+    // K4 (thread per string) walks only the items that can act for the configuration in hand: per
+    // key, sel[lbeg .. lbeg + leaves) are the LEAF items (an ACTIVE configuration, mfa.cpp:161-193)
+    // and the next `enters` entries the ENTER items that can insert (a WAITING / final one,
+    // mfa.cpp:138-140, 195-197: the call has a leaf, or it is a call on `finish`); entries are item
+    // indices relative to begin[key], in program order.  lcnt[key] = leaves | enters << 16.
+    std::vector<uint32_t> lbeg, lcnt;
+    std::vector<uint16_t> sel;
 };
 
 // RXM_OK, or RXM_ERR_UNSUPPORTED (more than kProgMaxCells cells, program too large).

@@ -26,7 +26,7 @@ RXM_ERR_PARSE = 6
 RXM_ERR_OVERFLOW = 7
 
 RXM_KIND_NFA, RXM_KIND_MFA = 0, 1
-ENGINE_NAMES = {1: "K1_DFA", 2: "K1_BITSET", 3: "K2_THREAD", 4: "K3_WARP"}
+ENGINE_NAMES = {1: "K1_DFA", 2: "K1_BITSET", 3: "K2_THREAD", 4: "K3_WARP", 5: "K4_THREAD"}
 
 # every symbol include/rxm.h declares (tests check that the library exports them all)
 ABI_SYMBOLS = [

@@ -20,6 +20,7 @@ template <class CfgT, class ReaderT>
 static void progsim_observe(const CfgT *cur, uint32_t m, uint32_t i, const ReaderT &rd);
 #define RXM_PROGSIM_OBSERVE(cur, m, i, rd) progsim_observe(cur, m, i, rd)
 #include "../../re2-modification_b200/csrc/rxm_mfa_core.cuh"
+#include "../../re2-modification_b200/csrc/rxm_k4_core.cuh"
 #include "../../re2-modification_b200/csrc/rxm_mfa_dispatch.hpp"
 #include "../../re2-modification_b200/csrc/rxm_nfa_core.cuh"
 #include "../../re2-modification_b200/csrc/rxm_plan.hpp"
@@ -170,6 +171,50 @@ extern "C" int hostsim_prog_batch(const rxm_tables *t, const uint8_t *chars, con
     RXM_MFA_DISPATCH(t->n_cells, t->n_states, CALL);
 #undef CALL
     return rxm_dispatch_ok ? 0 : 2;
+}
+
+extern "C" int hostsim_span_equal(const uint8_t *a, const uint8_t *b, uint32_t L) { return rxm::k4_span_equal(a, b, L) ? 1 : 0; }
+
+// K4's per-string simulation (rxm_k4_core.cuh) on the host, plain storage; `maxl` slots per set.
+// info3 (may be null) <- steps run in full, repeated steps answered by their compares, strings that met a limit.
+template <int NC>
+static void run_k4_batch(const rxm::MfaView &v, const rxm::K4Prog &kp, uint32_t maxl, const uint8_t *chars,
+                         const uint64_t *off, uint64_t n, uint8_t *out, uint64_t *info3) {
+    std::vector<uint32_t> words(rxm::k4_words(NC, maxl));
+    rxm::K4Sim<NC> sim;
+    sim.mem = rxm::K4Mem{words.data(), 1};
+    sim.maxl = maxl;
+    for (uint64_t i = 0; i < n; i++) {
+        const int r = sim.run(v, kp, chars + off[i], uint32_t(off[i + 1] - off[i]));
+        out[i] = uint8_t(r);
+        if (info3) {
+            info3[0] += sim.steps_run;
+            info3[1] += sim.steps_replayed;
+            info3[2] += (r == 2);
+        }
+    }
+}
+
+extern "C" int hostsim_k4core_batch(const rxm_tables *t, const uint8_t *chars, const uint64_t *off, uint64_t n,
+                                    uint8_t *out, uint32_t maxl, uint64_t *info3) {
+    rxm::MfaProgram prog;
+    std::string err;
+    int st = rxm::compile_programs(*t, prog, &err);
+    if (st != RXM_OK) return st;
+    std::vector<uint16_t> eb(t->n_states + 1);
+    for (uint32_t q = 0; q <= t->n_states; q++) eb[q] = uint16_t(t->edge_begin[q]);
+    std::vector<uint64_t> er(t->n_edges);
+    for (uint32_t e = 0; e < t->n_edges; e++)
+        er[e] = rxm::pack_edge(t->edge_kind[e], t->edge_sym[e], t->edge_to[e], t->edge_open[e], t->edge_close[e]);
+    rxm::MfaView v{eb.data(), er.data(), t->n_states, t->start, t->finish, t->reversed};
+    rxm::K4Prog kp{prog.items.data(), prog.begin.data(), prog.count.data(), prog.lbeg.data(), prog.lcnt.data(),
+                   prog.sel.data(), prog.n_cells};
+    if (info3) info3[0] = info3[1] = info3[2] = 0;
+    if (maxl == 0) maxl = t->n_states;
+    if (t->n_cells <= 1) run_k4_batch<1>(v, kp, maxl, chars, off, n, out, info3);
+    else if (t->n_cells <= 2) run_k4_batch<2>(v, kp, maxl, chars, off, n, out, info3);
+    else run_k4_batch<4>(v, kp, maxl, chars, off, n, out, info3);
+    return 0;
 }
 
 // DFA built by the planner, stepped on the host (checks plan_dfa against the oracle).

@@ -17,6 +17,7 @@ static unsigned long long rxm_k3_simt_iterations = 0;  // counted by the K3 kern
 #include "../../re2-modification_b200/csrc/rxm_k1b.cu"
 #include "../../re2-modification_b200/csrc/rxm_k2.cu"
 #include "../../re2-modification_b200/csrc/rxm_k3.cu"
+#include "../../re2-modification_b200/csrc/rxm_k4.cu"
 #include "../../re2-modification_b200/csrc/rxm_tok.cu"
 
 namespace {
@@ -88,6 +89,47 @@ extern "C" int hostsim_k3_batch(const rxm_tables *t, const uint8_t *chars, const
                         rxm::Spans{off, off + 1}, order_idx ? recs.data() : nullptr, n, out, &work[0], &work[1],
                         /*sm_count=*/2, /*sharing=*/1, nullptr, &launched);
     if (overflow_out) *overflow_out = work[0];
+    return run.finish(st, msg_out, msg_cap);
+}
+
+// K4 through rxm::k4_launch (128-thread blocks, per-thread sets of `maxl` slots in emulated shared
+// memory), then -- as rxm_api.cu does -- K3 over the strings K4 handed on (the redo list) when the
+// automaton has more nodes than a thread has slots.  redo_out (may be null) <- strings handed on.
+extern "C" int hostsim_k4_batch(const rxm_tables *t, const uint8_t *chars, const uint64_t *off, uint64_t n,
+                                uint8_t *out, uint32_t maxl, const uint32_t *order_idx, uint64_t limit,
+                                unsigned long long *overflow_out, unsigned long long *redo_out, char *msg_out,
+                                uint32_t msg_cap, uint64_t seed) {
+    rxm::MfaProgram prog;
+    std::string err;
+    int st = rxm::compile_programs(*t, prog, &err);
+    if (st != RXM_OK) return st;
+    DevTables dt;
+    const rxm::MfaView v = dt.view(t);
+    rxm::K4Prog kp{prog.items.data(), prog.begin.data(), prog.count.data(), prog.lbeg.data(), prog.lcnt.data(),
+                   prog.sel.data(), prog.n_cells};
+    std::vector<rxm::K1Rec> recs = make_recs(order_idx, n);
+    // the tile sort's layout: a short last tile is padded out by the kernel's own skip rule, so the
+    // records of a permutation must be laid out tile by tile as k1_tilesort_kernel does
+    unsigned long long work[2] = {0, 0};
+    std::vector<uint32_t> redo(n + 1);
+    unsigned long long redo_n = 0;
+    if (maxl == 0) maxl = t->n_states < 8u ? t->n_states : 8u;
+    const bool use_redo = t->n_states > maxl;
+    Run run(limit, seed);
+    int launched = 0;
+    st = rxm::k4_launch(v, kp, uint32_t(prog.items.size()), uint32_t(prog.begin.size()), uint32_t(prog.sel.size()),
+                        t->n_cells, maxl, chars, rxm::Spans{off, off + 1}, order_idx ? recs.data() : nullptr, n, out,
+                        &work[0], &work[1], use_redo ? redo.data() : nullptr, &redo_n, /*sm_count=*/2, /*sharing=*/1,
+                        nullptr, &launched);
+    if (st == RXM_OK && simt::S().last_failure == 0 && use_redo) {
+        rxm::ProgView gp{prog.items.data(), prog.begin.data(), prog.count.data(), prog.n_cells};
+        const uint32_t tile = prog.max_count <= 8 ? 8 : (prog.max_count <= 16 ? 16 : 32);
+        st = rxm::k3_launch(v, gp, uint32_t(prog.items.size()), uint32_t(prog.begin.size()), t->n_cells, tile, chars,
+                            rxm::Spans{off, off + 1}, nullptr, n, out, &work[0], &work[1], 2, 1, nullptr, &launched,
+                            redo.data(), &redo_n);
+    }
+    if (overflow_out) *overflow_out = work[0];
+    if (redo_out) *redo_out = redo_n;
     return run.finish(st, msg_out, msg_cap);
 }
 

@@ -19,12 +19,12 @@ def _engine_cases():
         if BY_NAME[name]["kind"] == "nfa":
             out.append((name, None))
         else:
-            out += [(name, "k2"), (name, "k3")]
+            out += [(name, "k2"), (name, "k3"), (name, "k4")]
     return out
 
 
 def _matcher(t, engine):
-    """engine: None (planner's choice) or "k2"/"k3" (RXM_MFA_ENGINE override at upload)."""
+    """engine: None (planner's choice) or "k2"/"k3"/"k4" (RXM_MFA_ENGINE override at upload)."""
     import os
     old = os.environ.get("RXM_MFA_ENGINE")
     if engine:
@@ -38,7 +38,7 @@ def _matcher(t, engine):
             else:
                 os.environ["RXM_MFA_ENGINE"] = old
     if engine:
-        assert rxm.ENGINE_NAMES[m.plan().engine] == {"k2": "K2_THREAD", "k3": "K3_WARP"}[engine]
+        assert rxm.ENGINE_NAMES[m.plan().engine] == {"k2": "K2_THREAD", "k3": "K3_WARP", "k4": "K4_THREAD"}[engine]
     return m
 
 
@@ -90,7 +90,7 @@ def test_nfa_random_batches_vs_oracle(name):
     m.close()
 
 
-@pytest.mark.parametrize("engine", ["k2", "k3"])
+@pytest.mark.parametrize("engine", ["k2", "k3", "k4"])
 @pytest.mark.parametrize("name", ["ex01_fwd", "ex02_fwd", "ex02_rev", "ex05_fwd", "ex05_rev",
                                   "ex08_rev", "ex09_fwd", "ex14_rev", "ex15_rev", "ex17_rev"])
 def test_mfa_random_batches_vs_oracle(name, engine):
@@ -106,7 +106,7 @@ def test_mfa_random_batches_vs_oracle(name, engine):
     m.close()
 
 
-@pytest.mark.parametrize("engine", ["k2", "k3"])
+@pytest.mark.parametrize("engine", ["k2", "k3", "k4"])
 def test_mfa_long_blocks_and_attack_strings(engine):
     """Long backreference blocks (idle-step skipping, warp-wide block compare) and the
     reference's attack strings (pump.txt recipes) up to 16 K chars, forward and reversed."""
@@ -148,7 +148,7 @@ def test_plan_reports_engine():
     m.close()
     t, _, _ = load_case("ex05_fwd")
     m = rxm.Matcher(t, 0)
-    assert rxm.ENGINE_NAMES[m.plan().engine] in ("K2_THREAD", "K3_WARP")
+    assert rxm.ENGINE_NAMES[m.plan().engine] == "K4_THREAD"
     m.close()
     # 2^8 active sets: still a table, in its two-lookup form (byte class, then [class][set] u16)
     t, _, _ = load_case("nfa_mid")
@@ -422,7 +422,7 @@ def test_match_text_device_pointers_alignment_and_capacity():
     m.close()
 
 
-@pytest.mark.parametrize("engine", ["k3", "k2"])
+@pytest.mark.parametrize("engine", ["k4", "k3", "k2"])
 def test_mfa_large_batch_properties(engine):
     """BASELINE-shaped MFA batch (config 3: example 5 on x c x c x^m strings of 64-4096; 200 k strings
     for K3, 20 k for K2): the bits are a pure function of each string -- a permuted batch gives the
@@ -431,7 +431,7 @@ def test_mfa_large_batch_properties(engine):
     import torch
     t, _, _ = load_case("ex05_fwd")
     W = H.load_workloads()
-    n = 200_000 if engine == "k3" else 20_000
+    n = 20_000 if engine == "k2" else 200_000
     chars, off = W.example5_strings(n, 64, 4096, 9, "cuda")
     m = _matcher(t, engine)
     s = torch.cuda.current_stream().cuda_stream
@@ -504,7 +504,7 @@ def test_random_expression_corpus_on_device(monkeypatch):
         if kind == "mfa" and t.c.n_cells > 4:
             variants += [{"RXM_MFA_ENGINE": "k2"}]  # more than 4 cells: the planner's choice is K2 as well
         elif kind == "mfa":
-            variants += [{"RXM_MFA_ENGINE": "k2"}, {"RXM_MFA_ENGINE": "k3"}]
+            variants += [{"RXM_MFA_ENGINE": "k2"}, {"RXM_MFA_ENGINE": "k3"}, {"RXM_MFA_ENGINE": "k4"}]
         else:
             variants += [{"RXM_NFA_ENGINE": "bitset"}, {"RXM_NFA_ENGINE": "bitset", "RXM_K1B_WALK": "1"}]
         for env in variants:
@@ -520,7 +520,7 @@ def test_random_expression_corpus_on_device(monkeypatch):
             assert m.overflow_count() == 0
             m.close()
     names = {e for e, _ in engines_seen}
-    assert {"K1_DFA", "K1_BITSET", "K2_THREAD", "K3_WARP"} <= names
+    assert {"K1_DFA", "K1_BITSET", "K2_THREAD", "K3_WARP", "K4_THREAD"} <= names
 
 
 def test_match_text_random_byte_soup():
@@ -590,3 +590,99 @@ def test_set_concurrency_changes_the_grid_not_the_bits(name):
     torch.cuda.synchronize()
     for o in outs:
         assert np.array_equal(o.cpu().numpy(), want)
+
+
+# ---- BASELINE configs 4 and 5 as bench.py builds them ---------------------------
+
+
+@pytest.mark.parametrize("engine", [None, "k3", "k2"])
+@pytest.mark.parametrize("name", ["ex02_fwd", "ex02_rev"])
+def test_config4_attack_batch_every_bit(name, engine):
+    """BASELINE config 4: example 2's attack strings (bbaa)^k aaba (bbaa)^k [c] (test/example_2/pump.txt,
+    generator matchers/example_runner.cpp:15-29) of 435 .. 65 536 letters, forward and -reverse tables,
+    1024 strings (256 for the thread-per-string K2): EVERY bit against the C restatement, through the
+    planner's choice and the other MFA engines; device pointers (the long-string hand-out of rxm_api.cu)."""
+    import torch
+    W = H.load_workloads()
+    t, _, _ = load_case(name)
+    n = 256 if engine == "k2" else 1024
+    chars, off = W.attack_batch(["bbaa", "aaba", "bbaa"], "c", "", n, 435, 65536, 4004)
+    assert int(np.diff(off).max()) > 60000
+    want = H.oracle_bits(t, chars, off)
+    m = _matcher(t, engine)
+    d_chars = torch.from_numpy(chars).cuda()
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    d_out = torch.full((n,), 7, dtype=torch.uint8, device="cuda")
+    m.match_ptrs(d_chars.data_ptr(), d_off.data_ptr(), n, d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy()
+    assert m.overflow_count() == 0
+    assert np.array_equal(got, want), [int(off[i + 1] - off[i]) for i in np.nonzero(got != want)[0][:8]]
+    if name == "ex02_fwd":
+        assert 0 < int(want.sum()) < n
+    assert np.array_equal(m.match_host(chars, off), want)  # host buffers: the staged route
+    m.close()
+
+
+@pytest.mark.skipif(not H.have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name,flags", [("ex02_fwd", []), ("ex02_rev", ["-reverse"])])
+def test_config4_longest_strings_against_the_reference_itself(name, flags):
+    """The longest attack strings the reference's own code (oracle/_ref/diploma_ref_bump) finishes in the
+    time limit -- it is O(len^2) per string, mfa.cpp:136,203 copy the input per call: 16 strings up to
+    16 K letters -- against the device."""
+    W = H.load_workloads()
+    t, _, _ = load_case(name)
+    chars, off = W.attack_batch(["bbaa", "aaba", "bbaa"], "c", "", 16, 4000, 16384, 4005, log_uniform=False)
+    ref = H.reference_bits(W.README_EXAMPLES[2][0], flags, chars, off, timeout=900)
+    m = rxm.Matcher(t, 0)
+    got = m.match_host(chars, off)
+    m.close()
+    assert np.array_equal(got, ref)
+    assert np.array_equal(H.oracle_bits(t, chars, off), ref)
+
+
+def test_config5_mixed_example_batches_on_their_own_streams():
+    """BASELINE config 5 as bench.py runs it: the ten README examples (README.md:78-89), 20 000 mixed
+    strings each (pumped / near-miss / random, 16-512 letters), ten matchers on ten streams at once;
+    every bit against the C restatement."""
+    import torch
+    W = H.load_workloads()
+    dev = torch.device("cuda:0")
+    jobs = []
+    for ex in range(1, 11):
+        t, _, _ = load_case(f"ex{ex:02d}_fwd")
+        chars, off = W.mixed_example_batch(ex, 20000, 1000 * ex)
+        jobs.append({"t": t, "chars": chars, "off": off, "m": rxm.Matcher(t, 0),
+                     "d_chars": torch.from_numpy(chars).to(dev), "d_off": torch.from_numpy(off.astype(np.int64)).to(dev),
+                     "d_out": torch.full((20000,), 7, dtype=torch.uint8, device=dev), "st": torch.cuda.Stream(device=dev)})
+    torch.cuda.synchronize()
+    for j in jobs:
+        j["m"].match_ptrs(j["d_chars"].data_ptr(), j["d_off"].data_ptr(), 20000, j["d_out"].data_ptr(), j["st"].cuda_stream)
+    torch.cuda.synchronize()
+    engines = set()
+    for ex, j in enumerate(jobs, 1):
+        want = H.oracle_bits(j["t"], j["chars"], j["off"])
+        got = j["d_out"].cpu().numpy()
+        assert j["m"].overflow_count() == 0
+        assert np.array_equal(got, want), (ex, int((got != want).sum()))
+        engines.add(rxm.ENGINE_NAMES[j["m"].plan().engine])
+        j["m"].close()
+    assert engines == {"K4_THREAD"}
+
+
+@pytest.mark.parametrize("name", ["ex02_rev", "ex08_rev", "ex15_rev", "ex05_rev"])
+def test_k4_hands_outgrown_strings_to_k3_on_the_device(name):
+    """Automata with more nodes than a K4 thread has slots: a batch large enough for the tile-sorted
+    hand-out (20 000 strings), the strings K4 cannot hold are run by K3's list mode in the same call;
+    all bits against the C restatement."""
+    t, strings, bits = load_case(name)
+    rng = np.random.default_rng(31)
+    extra = [bytes(rng.choice(np.frombuffer(b"aaabbc", dtype=np.uint8), size=int(L))) for L in rng.integers(0, 120, size=20000)]
+    chars, off = H.make_batch(strings + extra)
+    m = rxm.Matcher(t, 0)
+    assert rxm.ENGINE_NAMES[m.plan().engine] == "K4_THREAD"
+    got = m.match_host(chars, off)
+    assert m.overflow_count() == 0
+    assert np.array_equal(got[:len(bits)], bits)
+    assert np.array_equal(got, H.oracle_bits(t, chars, off))
+    m.close()
