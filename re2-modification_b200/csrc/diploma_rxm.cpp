@@ -102,7 +102,10 @@ static bool read_line(FILE *f, std::string &out) {
     return any;
 }
 
-static int run_configuration_examples_gpu(const std::string &number, int device, size_t max_len) {
+// bits_path (additive, `-bits FILE`): also write, per cumulative string, `RUNNER <len> <bit plain> <bit bnf>
+// <bit reverse>` and -- for the same string before its failing suffix is appended -- a `RUNNER_NS` line:
+// the format of oracle/ref_runner.cpp, which prints the reference's own bits for the same loop.
+static int run_configuration_examples_gpu(const std::string &number, int device, size_t max_len, const char *bits_path) {
     const std::string dir = "test/example_" + number + "/";
     FILE *regex_file = std::fopen((dir + "regexp.txt").c_str(), "r");
     FILE *pump_file = std::fopen((dir + "pump.txt").c_str(), "r");
@@ -153,6 +156,19 @@ static int run_configuration_examples_gpu(const std::string &number, int device,
         uint8_t bit;
         for (int a = 0; a < 3; a++) rxm_match_batch(h[a], w, off, 1, &bit, nullptr);
     }
+    FILE *bits_file = bits_path ? std::fopen(bits_path, "w") : nullptr;
+    if (bits_path && !bits_file) return 2;
+    auto bits_line = [&](const char *tag, const std::string &str) {
+        std::fprintf(bits_file, "%s %zu", tag, str.length());
+        for (int a = 0; a < 3; a++) {
+            const uint64_t off[2] = {0, uint64_t(str.length())};
+            uint8_t bit = 0;
+            const int st = rxm_match_batch(h[a], reinterpret_cast<const uint8_t *>(str.data()), off, 1, &bit, nullptr);
+            if (st == RXM_OK) std::fprintf(bits_file, " %d", int(bit));
+            else std::fprintf(bits_file, " E%d", st);
+        }
+        std::fprintf(bits_file, "\n");
+    };
     bool timeouted[3] = {false, false, false};
     int count = 0;
     long long pump_size = 500;
@@ -160,9 +176,14 @@ static int run_configuration_examples_gpu(const std::string &number, int device,
     int rc = 0;
     while ((!timeouted[0] || !timeouted[1] || !timeouted[2]) && len < max_len) {  // :120
         if (pump_size > (1ll << 30)) break;
+        const std::string no_suffix = bits_file ? prefix + pumped_string(int(pump_size), pump) : std::string();
         prefix.append(pumped_string(int(pump_size), pump)).append(suffix);  // :123 -- cumulative
         const std::string &input_str = prefix;
         len = input_str.length();
+        if (bits_file && len <= max_len) {
+            bits_line("RUNNER", input_str);
+            bits_line("RUNNER_NS", no_suffix);
+        }
         pump_size += pump_size;
         for (int a = 0; a < 3; a++) {
             if (timeouted[a]) continue;
@@ -188,6 +209,7 @@ static int run_configuration_examples_gpu(const std::string &number, int device,
         std::fclose(out[a]);
         rxm_free(h[a]);
     }
+    if (bits_file) std::fclose(bits_file);
     return rc;
 }
 
@@ -202,11 +224,13 @@ int main(int argc, char **argv) {
     if (argc > 2 && argv[2][0] >= '0' && argv[2][0] <= '9') {  // main.cpp:11-13: -match N
         int device = 0;
         size_t max_len = size_t(1) << 24;
+        const char *bits_path = nullptr;
         for (int i = 3; i + 1 < argc; i++) {
             if (std::strcmp(argv[i], "-device") == 0) device = std::atoi(argv[i + 1]);
             if (std::strcmp(argv[i], "-maxlen") == 0) max_len = std::strtoull(argv[i + 1], nullptr, 10);
+            if (std::strcmp(argv[i], "-bits") == 0) bits_path = argv[i + 1];
         }
-        return run_configuration_examples_gpu(argv[2], device, max_len);
+        return run_configuration_examples_gpu(argv[2], device, max_len, bits_path);
     }
     bool bnf = false, reverse = false, ssnf = false;
     const char *batch_in = nullptr, *batch_out = nullptr;
@@ -290,6 +314,12 @@ int main(int argc, char **argv) {
             return 2;
         }
         std::fclose(f);
+        bool sane = off[0] == 0 && off[n] == total;  // the header is not trusted: rxm_match_batch copies off[n] bytes
+        for (uint64_t i = 0; i < n && sane; i++) sane = off[i] <= off[i + 1];
+        if (!sane) {
+            std::fprintf(stderr, "diploma_rxm: %s: offsets do not describe %llu bytes\n", batch_in, (unsigned long long)total);
+            return 2;
+        }
         st = rxm_match_batch(h, chars.data(), off.data(), n, bits.data(), nullptr);
         if (st != RXM_OK) {
             std::fprintf(stderr, "diploma_rxm: match: %s (%s)\n", rxm_strerror(st), rxm_last_cuda_error());

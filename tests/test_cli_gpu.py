@@ -118,3 +118,53 @@ def test_match_driver_benchmark_route():
             rows = [ln.split() for ln in open(os.path.join(ex, name)).read().splitlines()]
             assert [int(a) for a, _ in rows] == want[:len(rows)], name
             assert len(rows) >= 3 and all(0 < float(b) < 1 for _, b in rows)
+
+
+RUNNER_REF = os.path.join(H.REF_DIR, "diploma_ref_runner")
+
+
+def _runner_golden(n):
+    """tests/golden/runner/exNN.txt (tests/golden/make_runner_golden.py: the reference's own bits)."""
+    meta, lines = {}, []
+    for ln in open(os.path.join(H.GOLDEN, "runner", f"ex{n:02d}.txt")).read().splitlines():
+        if ln.startswith("#"):
+            continue
+        key, _, rest = ln.partition(" ")
+        if key in ("REGEX", "PUMP", "SUFFIX", "PREFIX"):
+            meta[key] = rest
+        elif key.startswith("RUNNER"):
+            lines.append(ln)
+    return meta, lines
+
+
+@pytest.mark.skipif(not os.path.exists(DRIVER), reason="diploma_rxm not built")
+@pytest.mark.parametrize("n", list(range(1, 11)))
+def test_match_driver_benchmark_route_bits_equal_the_reference(n):
+    """f4 (matchers/example_runner.cpp:84-151): `diploma_rxm -match N -bits FILE` -- the three automata
+    (plain / -bnf / -reverse, :109-111) on the cumulative attack strings (:123) -- gives, string by string,
+    the lengths AND the match bits the reference's own code gives for the same loop
+    (oracle/ref_runner.cpp: the reference's pumped_string / split linked from example_runner.cpp, its
+    parse / compile / MFA::match; committed as tests/golden/runner/), and the same again live where
+    oracle/_ref/diploma_ref_runner exists.  README examples 1-10; the `len seconds` result files keep the
+    reference's format."""
+    meta, want = _runner_golden(n)
+    assert len(want) >= 8
+    with tempfile.TemporaryDirectory() as td:
+        ex = os.path.join(td, "test", f"example_{n}")
+        os.makedirs(ex)
+        open(os.path.join(ex, "regexp.txt"), "w").write(meta["REGEX"] + "\n")
+        open(os.path.join(ex, "pump.txt"), "w").write(meta["PUMP"] + "\n" + meta["SUFFIX"] + "\n" + meta["PREFIX"] + "\n")
+        bits = os.path.join(td, "bits.txt")
+        r = subprocess.run([DRIVER, "-match", str(n), "-maxlen", "16000", "-bits", bits], capture_output=True, cwd=td,
+                           timeout=600)
+        assert r.returncode == 0, r.stderr.decode()[-400:]
+        got = open(bits).read().splitlines()
+        assert got == want
+        lens = [int(ln.split()[1]) for ln in want if ln.startswith("RUNNER ")]
+        for name in ("diploma_results.txt", "diploma_bnf_results.txt", "diploma_reverse_results.txt"):
+            rows = [ln.split() for ln in open(os.path.join(ex, name)).read().splitlines()]
+            assert [int(a) for a, _ in rows] == lens[:len(rows)] and len(rows) >= 3, name
+        if os.path.exists(RUNNER_REF):
+            live = subprocess.run([RUNNER_REF, str(n), "-maxlen", "16000"], capture_output=True, cwd=td, timeout=900)
+            assert live.returncode == 0
+            assert [ln for ln in live.stdout.decode(errors="replace").splitlines() if ln.startswith("RUNNER")] == got
