@@ -126,9 +126,9 @@ def run_port(tables, chars, offsets):
     return time.perf_counter() - t0, bits
 
 
-def cpu_sample(W, wl, table_text, per_core, cores, seed):
-    import torch
-    dev = "cuda" if torch.cuda.is_available() else "cpu"
+def cpu_sample(W, wl, table_text, per_core, cores, seed, dev="cpu"):
+    """A bounded sample of the workload for the CPU legs; generated on the CPU unless the caller (the GPU
+    arm's cpu_baseline leg, which owns a device anyway) says otherwise."""
     chars, offsets = make_workload(W, wl, table_text, per_core * cores, seed, dev)
     return chars.cpu().numpy(), offsets.cpu().numpy().astype(np.uint64)
 
@@ -141,16 +141,18 @@ def reference_binary():
     return None, None
 
 
-def cpu_baseline(W, rxm, wl, tables, regex, flags):
-    """Reference -match code on the host cores, on a bounded sample of the workload."""
+def cpu_baseline(W, rxm, wl, tables, regex, flags, gpu_bits=None):
+    """Reference -match code on the host cores, on a bounded sample of the workload.
+    gpu_bits(chars, offsets) -> the device's bits for the same sample (SURVEY 7 policy: gate on the
+    canonical allocation-order build, also report the stock-glibc build)."""
     cores = host_cores()
     res = {}
     binary, bname = reference_binary()
     if binary:
         per_core = 1500 if wl == "config2" else 60
-        chars, offsets = cpu_sample(W, wl, tables.text, per_core, cores, 4242)
+        chars, offsets = cpu_sample(W, wl, tables.text, per_core, cores, 4242, "cuda")
         n = len(offsets) - 1
-        t_all, _ = run_reference_parallel(binary, regex, flags, chars, offsets, cores)
+        t_all, bits_stock = run_reference_parallel(binary, regex, flags, chars, offsets, cores)
         one = slice(0, per_core + 1)
         o1 = offsets[one]
         t_one, _ = run_reference_parallel(binary, regex, flags, chars[:int(o1[-1])], o1, 1)
@@ -170,6 +172,24 @@ def cpu_baseline(W, rxm, wl, tables, regex, flags):
             t0, _ = run_reference_parallel(o0, regex, flags, chars[:int(ok[-1])], ok, 1)
             res["single_thread_O0_upstream_flags"] = {"value": k / t0, "unit": "strings/s",
                                                        "cores": 1, "sample": f"{k} strings"}
+            # upstream's own flags (CMakeLists.txt:5-6 sets no -O), string-parallel over every core
+            kp = max(1, per_core // 8) * cores
+            okp = offsets[:kp + 1]
+            t0p, _ = run_reference_parallel(o0, regex, flags, chars[:int(okp[-1])], okp, cores)
+            res["string_parallel_O0_upstream_flags"] = {"value": kp / t0p, "unit": "strings/s", "cores": cores,
+                                                         "sample": f"{kp} strings, {cores} processes"}
+        bump = os.path.join(REF_DIR, "diploma_ref_bump_O2")
+        if os.path.exists(bump):
+            # the gate is the canonical (allocation-order) build; the stock-glibc build is reported
+            _, bits_bump = run_reference_parallel(bump, regex, flags, chars, offsets, cores)
+            dis = {"strings": int(n), "stock_vs_canonical": int((bits_stock != bits_bump).sum()),
+                   "note": "stock = diploma_ref_O2 (glibc malloc, heap-order tie-breaks), canonical = "
+                           "diploma_ref_bump_O2 (never-reuse allocator); the device is gated on canonical"}
+            if gpu_bits is not None:
+                got = gpu_bits(chars, offsets)
+                dis["device_vs_canonical"] = int((got != bits_bump).sum())
+                dis["device_vs_stock"] = int((got != bits_stock).sum())
+            res["stock_glibc_disagreement"] = dis
     else:
         per = 20000 if wl == "config2" else 2000
         chars, offsets = cpu_sample(W, wl, tables.text, per, 1, 4242)
@@ -219,12 +239,21 @@ def reference_arm(args, W, rxm):
     if rank != 0:
         return 0
     wl = args.workload
+    if wl not in ("config2", "config3"):
+        raise SystemExit("bench.py --impl reference: config2 / config3 (the multi-job workloads report their "
+                         "reference figure in the GPU arm's cpu_baseline)")
     case, regex, flags, desc = WORKLOADS[wl]
-    tables = rxm.Tables.load(os.path.join(CASES, case + ".rxt"))
+    # this arm maps neither the product library nor the GPU: the table text is only needed by the string
+    # generator (plain Python), the sample is made on the CPU, the timed region is the reference's own
+    # processes
+    table_text = open(os.path.join(CASES, case + ".rxt")).read()
     cores = host_cores()
     binary, bname = reference_binary()
     per_core = 1500 if wl == "config2" else 60
-    chars, offsets = cpu_sample(W, wl, tables.text, per_core, cores if binary else 1, 4242)
+    chars, offsets = cpu_sample(W, wl, table_text, per_core, cores if binary else 1, 4242, "cpu")
+    tables = None
+    if not binary:  # no oracle/_ref on this box: the C restatement needs the parsed table (librxm's parser)
+        tables = rxm.Tables(table_text)
     n = len(offsets) - 1
     times = []
     for step in range(args.warmup + args.steps):
@@ -366,9 +395,10 @@ def main():
     RESULT_OUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
 
-    rxm = _load("rxm", os.path.join(PKG, "rxm.py"))
+    rxm = _load("rxm", os.path.join(PKG, "rxm.py"))  # ctypes declarations only: librxm.so is mapped on first use
     W = _load("workloads", os.path.join(PKG, "workloads.py"))
     if args.impl == "reference":
+        os.environ["CUDA_VISIBLE_DEVICES"] = ""  # the reference arm does not touch a GPU
         return reference_arm(args, W, rxm)
 
     import torch

@@ -222,8 +222,11 @@ extern "C" int rxm_tables_upload(const rxm_tables *host_tables, int device, rxm_
             if ((st = upload_vec(m->prog.lbeg, &m->d_prog_lbeg)) != RXM_OK) return fail(st);
             if ((st = upload_vec(m->prog.lcnt, &m->d_prog_lcnt)) != RXM_OK) return fail(st);
             if ((st = upload_vec(m->prog.sel, &m->d_prog_sel)) != RXM_OK) return fail(st);
-            m->k4_maxl = t.n_states < 8u ? t.n_states : 8u;
-            m->info.engine = (force && std::strcmp(force, "k3") == 0) ? RXM_ENGINE_K3_WARP : RXM_ENGINE_K4_THREAD;
+            m->k4_maxl = rxm::k4_pool_for(t.n_states);  // slots per thread: the current set and the one being built share them
+            // K4 (one thread per string) unless the automaton is large: its sets outgrow a thread's slots, K3 (one
+            // warp per string, one slot per node) runs the whole batch
+            const bool big = t.n_states > rxm::K4_MAX_STATES && !(force && std::strcmp(force, "k4") == 0);
+            m->info.engine = ((force && std::strcmp(force, "k3") == 0) || big) ? RXM_ENGINE_K3_WARP : RXM_ENGINE_K4_THREAD;
             // short programs: several strings per warp (a step's items fit one pass of the tile)
             m->k3_tile = m->prog.max_count <= 8 ? 8 : (m->prog.max_count <= 16 ? 16 : 32);
             if (const char *tl = getenv("RXM_K3_TILE")) {
@@ -376,7 +379,7 @@ static int launch_on_device(rxm_matcher *m, const uint8_t *d_chars, rxm::Spans s
         const rxm::K1Rec *order = nullptr;
         if ((st = prepare_order(m, spans, n, stream, &order, &launched_extra)) != RXM_OK) return st;
         // automata with more nodes than a thread has slots: strings that outgrow them are run by K3
-        const bool redo = m->tables.n_states() > m->k4_maxl;
+        const bool redo = 2 * m->tables.n_states() > m->k4_maxl;
         if (redo) {
             if (n > 0xfffffff0ull) return RXM_ERR_UNSUPPORTED;
             if (n > m->cap_redo) {

@@ -4,8 +4,8 @@
 // kernel around it: tables and per-thread sets in shared memory, strings handed out in the tile
 // sort's order so that the 32 strings of a warp have nearly the same length.
 //
-// Strings that need more than `maxl` live configurations (possible only for automata with more
-// nodes than that) are not answered here: their indices go to `redo_list` and K3 runs them.
+// Strings that need more than `maxl` configuration slots at a time (the current set and the one being
+// built share a thread's pool) are not answered here: their indices go to `redo_list` and K3 runs them.
 #include "rxm_k4_core.cuh"
 #include "rxm_kernels.cuh"
 
@@ -50,9 +50,10 @@ k4_mfa_thread_kernel(MfaView v, K4Prog gp, uint32_t n_items, uint32_t n_keys, ui
     __syncthreads();
     const K4Prog p{items_in_smem ? s_items : gp.items, s_begin, s_count, s_lbeg, s_lcnt, s_sel, gp.n_cells};
 
-    K4Sim<NC> sim;
-    sim.mem = K4Mem{reinterpret_cast<uint32_t *>(smem + o) + threadIdx.x, blockDim.x};
-    sim.maxl = maxl;
+    K4Sim<NC, K4_THREADS> sim;
+    sim.base = reinterpret_cast<uint32_t *>(smem + o) + threadIdx.x;
+    sim.pool = maxl;
+    sim.want = K4_WANT_NONE;
 
     // tickets: with the tile sort's records, ticket t is record (t mod 32) of group g of tile tl, group g
     // of every tile before group g+1 of any (the long strings of the whole batch first)
@@ -93,7 +94,7 @@ k4_mfa_thread_kernel(MfaView v, K4Prog gp, uint32_t n_items, uint32_t n_keys, ui
                             atomicAdd(overflow, 1ull);
                             out[si] = 0;
                         } else {
-                            sim.start(chars + sb, uint32_t(se - sb), v.reversed, v);
+                            sim.start(chars + sb, uint32_t(se - sb), v.reversed, v.start);
                             have = true;
                         }
                     }
@@ -103,17 +104,28 @@ k4_mfa_thread_kernel(MfaView v, K4Prog gp, uint32_t n_items, uint32_t n_keys, ui
             wnext += took < avail ? took : avail;
         }
         if (__all_sync(ALL, exhausted && !have)) break;
-        if (have) {
-            int r = 0;
-            if (sim.advance(v, p, r)) {
-                if (r == 2) {
-                    r = 0;
-                    if (redo_list) redo_list[atomicAdd(redo_n, 1ull)] = uint32_t(si);
-                    else atomicAdd(overflow, 1ull);
-                }
-                out[si] = uint8_t(r);
-                have = false;
+        // One round.  Every string says what it needs next -- a burst of repeated steps (phase A: a flat loop,
+        // every lane in it runs the same few instructions) or one step in full (phase B) -- and the warp runs
+        // the phase MOST of its strings want; the others wait for a round of their kind.  Lanes that wait
+        // cost no issue slots, and each phase runs with most lanes of the warp in it.
+        if (have) sim.pre();
+        const uint32_t w = have ? sim.want : uint32_t(K4_WANT_NONE);
+        const uint32_t mA = __ballot_sync(ALL, w == K4_WANT_A), mB = __ballot_sync(ALL, w == K4_WANT_B);
+        if (mA != 0u && __popc(mA) >= __popc(mB)) {
+            if (w == K4_WANT_A) sim.phase_a();
+        } else if (mB != 0u) {
+            if (w == K4_WANT_B) sim.phase_b(v, p);
+        }
+        __syncwarp(ALL);
+        if (have && sim.want == K4_DONE) {
+            int r = sim.result;
+            if (r == 2) {
+                r = 0;
+                if (redo_list) redo_list[atomicAdd(redo_n, 1ull)] = uint32_t(si);
+                else atomicAdd(overflow, 1ull);
             }
+            out[si] = uint8_t(r);
+            have = false;
         }
     }
 }

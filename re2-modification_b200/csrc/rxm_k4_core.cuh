@@ -3,23 +3,28 @@
 // The same simulation as ProgSim (rxm_mfa_core.cuh) -- MFA::match / evaluateStates / evaluateState
 // (mfa.cpp:215-236 / 203-213 / 136-200) with cells as spans, one slot per node and prog_stamp
 // creation order -- arranged for a thread that owns its string:
-//   * the two sets live in a few dozen words of per-thread storage reached through K4Mem (on the
-//     device: shared memory, word w of thread t at w * blockDim + t, so the 32 lanes of a warp never
-//     meet in a bank whatever slot each of them touches; on the host: a plain array);
+//   * the thread has a POOL of a few configuration slots (words reached through base[w * STRIDE]: on the
+//     device shared memory with word w of thread t at w * blockDim + t, so the 32 lanes of a warp never
+//     meet in a bank whatever slot each of them touches; on the host a plain array).  The sets of the
+//     simulation -- the current one, the one being built, the one the last full step started from --
+//     are BIT MASKS over the pool, and a waiting configuration that a step re-inserts unchanged
+//     (mfa.cpp:195-197) is not copied: its slot simply joins the new set;
 //   * a configuration only walks the items that can act for it: the LEAF items of its program when
 //     it is ACTIVE (first == i, mfa.cpp:161-193), the ENTER items that can insert when it WAITS or
 //     sits at the end of the input (mfa.cpp:138-140, 195-197) -- lists made by the planner
 //     (MfaProgram::sel);
 //   * backreference blocks (mfa.cpp:176-193) are compared 8 bytes per iteration from aligned words
 //     at any alignment of the two spans; a block already compared in this step is not compared again;
-//   * REPEATED STEPS are answered by their block compares alone (ProgSim::replay, proven out on the
-//     host in round 1): when the set a step starts from is the set the previous step started from,
-//     moved on by the distance between the two, the letter is the same and every block compare of the
-//     previous step has the same outcome at the new position, the result is the previous result moved
-//     on -- neither programs nor slots are touched.  On the reference's example 5 this answers more
-//     than nine steps in ten;
+//   * REPEATED STEPS (ProgSim::replay, proven out on the host in round 1): when the set a step starts
+//     from is the set the previous step started from, moved on by the distance delta between the two,
+//     and the input it looks at equals the input the previous step looked at, its result is the
+//     previous result moved on.  The thread then only checks that the input stays PERIODIC with period
+//     delta, one aligned word per iteration of a flat loop (phase A below); programs and slots are not
+//     touched.  On the reference's example 5 this answers more than nine steps in ten;
 //   * idle steps (every configuration waiting inside a block) are skipped as in ProgSim.
-// Everything is RXM_HD: tests/hostsim runs this very code on the CPU against the golden vectors.
+// A round of a string is pre() -> phase_a() or phase_b(); the kernel (rxm_k4.cu) lets the lanes of a
+// warp run the phase most of them want.  Everything is RXM_HD: tests/hostsim runs this very code on
+// the CPU against the golden vectors.
 #ifndef RXM_K4_CORE_CUH
 #define RXM_K4_CORE_CUH
 
@@ -37,18 +42,38 @@ struct K4Prog {  // the edge programs and the per-key item lists (MfaProgram)
     uint32_t n_cells;
 };
 
-// per-thread words: word w of this thread is base[w * stride]
-struct K4Mem {
-    uint32_t *base;
-    uint32_t stride;
-    RXM_HD uint32_t &at(uint32_t w) const { return base[size_t(w) * stride]; }
-};
+constexpr uint32_t K4_LOGN = 4;      // distinct block compares remembered per step
+constexpr uint32_t K4_BURST = 64;    // iterations of the repeated-step loop per round
+constexpr uint32_t K4_POOL_MAX = 32;  // slots a thread can have at most (the set masks are 32 bits)
 
-constexpr uint32_t K4_LOGN = 4;     // distinct block compares remembered per step
-constexpr uint32_t K4_BURST = 16;   // repeated steps answered before the thread looks up again
-
+// slots for an automaton of n_states nodes: 8 hold the current set and the one being built for every forward
+// automaton of the reference's examples; the reversed ones keep more configurations waiting
+RXM_HD constexpr uint32_t k4_pool_for(uint32_t n_states) { return n_states < 8u ? 8u : (n_states > 16u ? 16u : n_states); }
+constexpr uint32_t K4_MAX_STATES = 40;  // larger automata go to K3 (one warp per string) as a whole
 RXM_HD constexpr uint32_t k4_slot_words(uint32_t nc) { return 3u + 2u * nc; }
-RXM_HD constexpr uint32_t k4_words(uint32_t nc, uint32_t maxl) { return 2u * maxl * k4_slot_words(nc) + 2u * K4_LOGN; }
+RXM_HD constexpr uint32_t k4_words(uint32_t nc, uint32_t pool) { return pool * k4_slot_words(nc) + 2u * K4_LOGN; }
+
+RXM_HD int k4_ffs(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __ffs(int(x));
+#else
+    return __builtin_ffs(int(x));
+#endif
+}
+RXM_HD int k4_ffs64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)x);
+#else
+    return __builtin_ffsll((long long)x);
+#endif
+}
+RXM_HD int k4_popc(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
 
 RXM_HD uint64_t k4_ld64(const uint8_t *p) {  // p is 8-byte aligned
 #if defined(__CUDA_ARCH__)
@@ -87,111 +112,155 @@ RXM_HD bool k4_span_equal(const uint8_t *a, const uint8_t *b, uint32_t L) {
 }
 
 template <int NC>
+RXM_HD uint32_t k4_exists_mask(uint32_t flags) {  // bit k <- flags bit 3k, k < NC
+    uint32_t m = 0;
+RXM_UNROLL
+    for (int k = 0; k < NC; k++) m |= ((flags >> (3 * k)) & 1u) << k;
+    return m;
+}
+
+enum : uint32_t { K4_WANT_NONE = 0, K4_WANT_A = 1, K4_WANT_B = 2, K4_DONE = 3 };
+
+// STRIDE: distance in words between two consecutive words of this thread (device: threads per block; host: 1)
+template <int NC, int STRIDE>
 struct K4Sim {
     typedef Cfg<NC> cfg_t;
-    static constexpr uint32_t SW = 3u + 2u * NC;
+    static constexpr uint32_t SW = 3u + 2u * NC;  // first | node, flags | born | start[NC] | len[NC]
 
-    K4Mem mem;
-    uint32_t maxl;
+    uint32_t *base;  // word 0 of this thread
+    uint32_t pool;   // slots in the pool (<= K4_POOL_MAX); the compare log follows them
     // the string in hand
     const uint8_t *s;
     uint32_t n, reversed;
     // simulation state (registers)
     uint32_t i;
-    uint32_t nb;          // buffer being filled; nb ^ 1 holds the current set
-    uint32_t cnt0, cnt1;  // configurations in buffer 0 / 1
+    uint32_t cur, nxt, prv;  // set masks: current set / set being built / set the last full step started from
     uint32_t n_log;
     uint32_t prev_i;
+    uint32_t want;        // K4_WANT_*: what the next round of this string is
+    int result;
+    // repeated steps
     uint32_t rp_delta;    // != 0: repeated steps of this distance are being answered
-    uint32_t rp_ch;
-    bool have_prev, log_bad, overflow;
+    uint32_t rp_lmax;     // the longest block the repeated step compares (>= 1: its letter)
+    uint32_t rp_vp;       // verified front: s[j] == s[j - rp_delta] for every j from the first repeated step up to here
+    uint32_t rp_vcap;     // the front need not pass this: the last step that may be answered looks up to here
+    uint32_t rp_acc;      // distance moved on so far, not yet written to the slots
+    uint64_t rp_magic;    // ceil(2^32 / rp_delta)
+    bool rp_mism;         // a byte that differs stands at rp_vp
+    bool have_prev, log_bad, overflow, near;
     // statistics (tests)
     uint32_t steps_run, steps_replayed;
 
-    RXM_HD uint32_t cnt(uint32_t b) const { return b ? cnt1 : cnt0; }
-    RXM_HD void set_cnt(uint32_t b, uint32_t v) {
-        if (b) cnt1 = v;
-        else cnt0 = v;
-    }
-    RXM_HD uint32_t slot(uint32_t b, uint32_t j) const { return (b * maxl + j) * SW; }
-    RXM_HD uint32_t log0() const { return 2u * maxl * SW; }
-
+    RXM_HD uint32_t *slotp(uint32_t j) const { return base + size_t(j) * (SW * STRIDE); }
+    RXM_HD uint32_t *logp() const { return base + size_t(pool) * (SW * STRIDE); }
     RXM_HD uint8_t at(uint32_t j) const { return reversed ? s[n - 1u - j] : s[j]; }
     RXM_HD bool span_equal(uint32_t a, uint32_t b, uint32_t L) const {  // R[a, a+L) == R[b, b+L), reading direction
         if (!reversed) return k4_span_equal(s + a, s + b, L);
         return k4_span_equal(s + (n - a - L), s + (n - b - L), L);
     }
 
-    RXM_HD void load(uint32_t b, uint32_t j, cfg_t &c) const {
-        const uint32_t o = slot(b, j);
-        c.first = mem.at(o);
-        const uint32_t nf = mem.at(o + 1);
+    RXM_HD void load(uint32_t j, cfg_t &c) const {
+        const uint32_t *sp = slotp(j);
+        c.first = sp[0];
+        const uint32_t nf = sp[STRIDE];
         c.node = nf & 0xffffu;
         c.flags = nf >> 16;
-        c.born = mem.at(o + 2);
+        c.born = sp[2 * STRIDE];
 RXM_UNROLL
         for (int k = 0; k < NC; k++) {
-            c.start[k] = mem.at(o + 3 + k);
-            c.len[k] = mem.at(o + 3 + NC + k);
+            c.start[k] = sp[(3 + k) * STRIDE];
+            c.len[k] = sp[(3 + NC + k) * STRIDE];
         }
     }
-    RXM_HD void store(uint32_t o, const cfg_t &c) const {
-        mem.at(o) = c.first;
-        mem.at(o + 1) = c.node | (c.flags << 16);
-        mem.at(o + 2) = c.born;
+    RXM_HD void store(uint32_t j, const cfg_t &c) const {
+        uint32_t *sp = slotp(j);
+        sp[0] = c.first;
+        sp[STRIDE] = c.node | (c.flags << 16);
+        sp[2 * STRIDE] = c.born;
 RXM_UNROLL
         for (int k = 0; k < NC; k++) {
-            mem.at(o + 3 + k) = c.start[k];
-            mem.at(o + 3 + NC + k) = c.len[k];
+            sp[(3 + k) * STRIDE] = c.start[k];
+            sp[(3 + NC + k) * STRIDE] = c.len[k];
         }
+    }
+
+    // set order of mfa.cpp:206 for two configurations on one node: (first, lowest cell name, creation)
+    RXM_HD static bool key_less(uint32_t fa, uint32_t fla, uint32_t ba, uint32_t fb, uint32_t flb, uint32_t bb) {
+        if (fa != fb) return fa < fb;
+        const uint32_t la = lowvar(fla), lb = lowvar(flb);
+        if (la != lb) return la < lb;
+        return la != 0 && ba < bb;  // both memories empty: equal keys, the one already there stays
+    }
+
+    // the new set's slot on `node`, or K4_POOL_MAX
+    RXM_HD uint32_t find_new(uint32_t node) const {
+        for (uint32_t m = nxt; m; m &= m - 1u) {
+            const uint32_t j = uint32_t(k4_ffs(m)) - 1u;
+            if ((slotp(j)[STRIDE] & 0xffffu) == node) return j;
+        }
+        return K4_POOL_MAX;
+    }
+    RXM_HD uint32_t alloc() {
+        const uint32_t free = ~(cur | nxt) & (pool >= 32u ? 0xffffffffu : ((1u << pool) - 1u));
+        if (!free) {
+            overflow = true;
+            return K4_POOL_MAX;
+        }
+        return uint32_t(k4_ffs(free)) - 1u;
     }
 
     // new_states.insert, reduced on the fly to the set-minimum per node (mfa.cpp:206-211)
     RXM_HD void insert(const cfg_t &c) {
-        const uint32_t m = cnt(nb);
-        for (uint32_t j = 0; j < m; j++) {
-            const uint32_t o = slot(nb, j);
-            const uint32_t nf = mem.at(o + 1);
-            if ((nf & 0xffffu) != c.node) continue;
-            const uint32_t ef = mem.at(o);
-            bool less;
-            if (c.first != ef) less = c.first < ef;
-            else {
-                const uint32_t la = lowvar(c.flags), lb = lowvar(nf >> 16);
-                if (la != lb) less = la < lb;
-                else less = la != 0 && c.born < mem.at(o + 2);
+        if (c.first < i + 2u) near = true;  // its node will hold a configuration with first <= i + 1
+        uint32_t j = find_new(c.node);
+        if (j != K4_POOL_MAX) {
+            const uint32_t *sp = slotp(j);
+            if (!key_less(c.first, c.flags, c.born, sp[0], sp[STRIDE] >> 16, sp[2 * STRIDE])) return;
+            if (!((cur >> j) & 1u)) {  // not shared with the current set: overwritten in place
+                store(j, c);
+                return;
             }
-            if (less) store(o, c);
-            return;
+            nxt &= ~(1u << j);
         }
-        if (m < maxl) {
-            store(slot(nb, m), c);
-            set_cnt(nb, m + 1);
-        } else {
-            overflow = true;
+        j = alloc();
+        if (j == K4_POOL_MAX) return;
+        store(j, c);
+        nxt |= 1u << j;
+    }
+    // the re-insertion of the configuration in slot js itself (mfa.cpp:195-197 / 138-140 on the root call):
+    // older than anything created in this step (stamp 0); its slot joins the new set, nothing is copied
+    RXM_HD void reinsert(uint32_t js, const cfg_t &root) {
+        if (root.first < i + 2u) near = true;
+        const uint32_t j = find_new(root.node);
+        if (j != K4_POOL_MAX) {
+            const uint32_t *sp = slotp(j);
+            if (!key_less(root.first, root.flags, 0u, sp[0], sp[STRIDE] >> 16, sp[2 * STRIDE])) return;
+            nxt &= ~(1u << j);  // (a slot of the new set alone: free again)
         }
+        slotp(js)[2 * STRIDE] = 0u;
+        nxt |= 1u << js;
     }
 
-    RXM_HD static uint32_t need_of(const cfg_t &c) {  // is_siffix_long_enough, mfa.cpp:116-133
+    RXM_HD static uint32_t need_of(uint32_t flags, const uint32_t *len) {  // is_siffix_long_enough, mfa.cpp:116-133
         uint32_t need = 0;
 RXM_UNROLL
         for (int k = 0; k < NC; k++) {
-            const uint32_t fl = (c.flags >> (3 * k)) & 7u;
-            if ((fl & 1u) && ((fl & 2u) || !(fl & 4u))) need += c.len[k];
+            const uint32_t fl = (flags >> (3 * k)) & 7u;
+            if ((fl & 1u) && ((fl & 2u) || !(fl & 4u))) need += len[k];
         }
         return need;
     }
 
     // one block compare of the step at i; a span already compared in this step is answered from the log
     RXM_HD bool compare_logged(uint32_t vs, uint32_t L) {
-        const uint32_t l0 = log0();
+        uint32_t *lg = logp();
         for (uint32_t e = 0; e < n_log; e++)
-            if (mem.at(l0 + 2 * e) == vs && (mem.at(l0 + 2 * e + 1) & 0x7fffffffu) == L)
-                return (mem.at(l0 + 2 * e + 1) >> 31) != 0u;
+            if (lg[(2 * e) * STRIDE] == vs && (lg[(2 * e + 1) * STRIDE] & 0x7fffffffu) == L)
+                return (lg[(2 * e + 1) * STRIDE] >> 31) != 0u;
         const bool eq = span_equal(vs, i, L);
         if (n_log < K4_LOGN) {
-            mem.at(l0 + 2 * n_log) = vs;
-            mem.at(l0 + 2 * n_log + 1) = L | (eq ? 0x80000000u : 0u);
+            lg[(2 * n_log) * STRIDE] = vs;
+            lg[(2 * n_log + 1) * STRIDE] = L | (eq ? 0x80000000u : 0u);
             n_log++;
         } else {
             log_bad = true;
@@ -199,92 +268,22 @@ RXM_UNROLL
         return eq;
     }
 
-    // evaluateState (mfa.cpp:136-200) for one configuration of the current set
-    RXM_HD void eval(const MfaView &t, const K4Prog &p, const cfg_t &root) {
-        const bool fin = (root.first == n);
-        const bool active = (i != n && i == root.first);
-        const bool waiting = (i != n && i < root.first);
-        if (!(active || waiting || fin)) return;  // behind the step: no branch of mfa.cpp:161-197 fires
-        if (!(root.node == t.finish && fin) && t.reversed) {  // mfa.cpp:141 (after the :138 test)
-            if (need_of(root) > n - i) return;
-        }
-        const uint32_t key = (root.node << p.n_cells) | (exists_mask(root.flags) & ((1u << p.n_cells) - 1u));
-        const uint32_t pb = p.begin[key];
-        if (pb == 0xffffffffu) {
-            overflow = true;
-            return;
-        }
-        const uint32_t lb = p.lbeg[key], lc = p.lcnt[key];
-        if (active) {
-            const uint32_t ch = at(i);
-            const uint32_t digit_bit = (ch >= '1' && ch <= '9') ? (1u << (ch - '1')) : 0u;
-            const uint32_t nl = lc & 0xffffu;
-            for (uint32_t q = 0; q < nl; q++) {
-                const uint32_t x = p.sel[lb + q];
-                const ProgItem it = p.items[pb + x];
-                const uint32_t kind = pi_kind(it), rc = pi_read_cell(it);
-                uint32_t L = 1;
-                bool fire = false;
-                if (kind == kEdgeAny || (kind == kEdgeLit && pi_sym(it) == ch)) {  // :171-175
-                    fire = true;
-                } else if (rc) {  // :176-193, the cell is present
-                    const int k = int(rc) - 1;
-                    const bool fresh = (pi_created(it) >> k) & 1u;
-                    uint32_t vs = 0, fl = 0;
-                    L = 0;
-RXM_UNROLL
-                    for (int kk = 0; kk < NC; kk++)
-                        if (kk == k) {
-                            L = fresh ? 0u : root.len[kk];
-                            vs = root.start[kk];
-                            fl = (root.flags >> (3 * kk)) & 7u;
-                        }
-                    if (!fresh && (fl & 2u)) log_bad = true;  // the text of an open cell changes from step to step
-                    if (n - i >= L) fire = (L == 0) || compare_logged(vs, L);
-                }
-                if (fire) {
-                    cfg_t nx;
-                    prog_working<NC>(nx, root, pi_created(it), pi_created_open(it), pi_prior_reads(it) & ~digit_bit);
-                    nx.node = pi_node(it);
-                    nx.born = prog_stamp(false, root.node, x);
-                    nx.first += L;
-                    apply_actions<NC>(nx, pi_open(it), pi_close(it), i, L);
-                    insert(nx);
-                }
-            }
-        } else {
-            const uint32_t ne = lc >> 16;
-            for (uint32_t q = 0; q < ne; q++) {
-                const uint32_t x = p.sel[lb + (lc & 0xffffu) + q];
-                const ProgItem it = p.items[pb + x];
-                if (fin && pi_skip_final(it)) continue;  // below a call that returned at mfa.cpp:138-140
-                const uint32_t v = pi_node(it);
-                if ((v == t.finish && fin) || (waiting && pi_has_leaf(it))) {  // :138-140 / :195-197
-                    cfg_t w;
-                    prog_working<NC>(w, root, pi_created(it), pi_created_open(it), 0u);
-                    w.node = v;
-                    w.born = (x != 0) ? prog_stamp(true, root.node, x) : 0u;
-                    insert(w);
-                }
-            }
-        }
-    }
-
     // the current set == the set the previous step started from, every `first` moved on by delta and every
-    // open cell grown by delta (the letters read in between)
+    // open cell grown by delta (the letters read in between).  (Creation stamps are not compared: a step
+    // never reads the stamps of the set it starts from.)
     RXM_HD bool moved_on(uint32_t delta) const {
-        const uint32_t pbuf = nb, cbuf = nb ^ 1u;
-        const uint32_t m = cnt(cbuf);
-        if (cnt(pbuf) != m) return false;
-        for (uint32_t j = 0; j < m; j++) {
+        if (k4_popc(cur) != k4_popc(prv)) return false;
+        for (uint32_t mc = cur; mc; mc &= mc - 1u) {
+            const uint32_t jc = uint32_t(k4_ffs(mc)) - 1u;
+            if ((prv >> jc) & 1u) return false;  // the very same configuration: it has not moved
             cfg_t b;
-            load(cbuf, j, b);
+            load(jc, b);
             bool found = false;
-            for (uint32_t q = 0; q < m; q++) {
-                const uint32_t o = slot(pbuf, q);
-                if ((mem.at(o + 1) & 0xffffu) != b.node) continue;
+            for (uint32_t mp = prv; mp; mp &= mp - 1u) {
+                const uint32_t jp = uint32_t(k4_ffs(mp)) - 1u;
+                if ((slotp(jp)[STRIDE] & 0xffffu) != b.node) continue;
                 cfg_t mv;
-                load(pbuf, q, mv);
+                load(jp, mv);
                 mv.first += delta;
 RXM_UNROLL
                 for (int k = 0; k < NC; k++)
@@ -292,7 +291,7 @@ RXM_UNROLL
                         if (mv.len[k] == 0) mv.start[k] = b.start[k];
                         mv.len[k] += delta;
                     }
-                found = cfg_same<NC>(mv, b) && mv.born == b.born;
+                found = cfg_same<NC>(mv, b);
                 break;
             }
             if (!found) return false;
@@ -300,157 +299,302 @@ RXM_UNROLL
         return true;
     }
 
-    RXM_HD void start(const uint8_t *str, uint32_t len, uint32_t rev, const MfaView &t) {
+    RXM_HD void start(const uint8_t *str, uint32_t len, uint32_t rev, uint32_t start_node) {
         s = str;
         n = len;
         reversed = rev;
         i = 0;
-        nb = 1;
-        cnt0 = 1;
-        cnt1 = 0;
+        cur = 1u;
+        nxt = prv = 0u;
         n_log = 0;
         prev_i = 0;
-        rp_delta = 0;
-        rp_ch = 0;
-        have_prev = false;
-        log_bad = false;
-        overflow = false;
+        want = K4_WANT_NONE;
+        result = 0;
+        rp_delta = rp_lmax = rp_vp = rp_vcap = rp_acc = 0;
+        rp_magic = 0;
+        rp_mism = false;
+        have_prev = log_bad = overflow = near = false;
         steps_run = steps_replayed = 0;
         cfg_t c0;
         c0.first = 0;
         c0.born = 0;
         c0.flags = 0;
-        c0.node = t.start;
+        c0.node = start_node;
 RXM_UNROLL
         for (int k = 0; k < NC; k++) {
             c0.start[k] = 0;
             c0.len[k] = 0;
         }
-        store(slot(0, 0), c0);
+        store(0, c0);
     }
 
-    // One round of MFA::match's loop (mfa.cpp:221-228): a burst of repeated steps answered by their block
-    // compares, or one step run in full plus the jump over the idle steps behind it.  Returns true when
-    // the string is done: result = 0 / 1, or 2 if a limit was met (never a guess).
-    RXM_HD bool advance(const MfaView &t, const K4Prog &p, int &result) {
-        bool generic = true;
-        if (rp_delta == 0) {
-            if (i < n && cnt(nb ^ 1u) == 0) {  // :224-225 -- and the pass at i == n runs on the empty set
-                result = 0;
-                return true;
-            }
-            if (have_prev && !reversed && !log_bad && i < n && i > prev_i && moved_on(i - prev_i)) {
-                rp_delta = i - prev_i;
-                rp_ch = at(prev_i);
-            }
+    // ---- what is the next round?  (dead set: done; the set has moved on from the previous step's: A; else B) ----
+    RXM_HD void pre() {
+        if (want != K4_WANT_NONE) return;
+        if (i < n && cur == 0u) {  // :224-225 -- and the pass at i == n runs on the empty set
+            result = 0;
+            want = K4_DONE;
+            return;
         }
-        if (rp_delta) {
-            const uint32_t delta = rp_delta, cbuf = nb ^ 1u, m = cnt(cbuf), l0 = log0();
+        want = K4_WANT_B;
+        if (have_prev && !reversed && !log_bad && i < n && i > prev_i && moved_on(i - prev_i)) {
+            const uint32_t delta = i - prev_i;
+            const uint32_t *lg = logp();
+            uint32_t lmax = 1;  // the letter at i
+            for (uint32_t e = 0; e < n_log; e++) {
+                const uint32_t L = lg[(2 * e + 1) * STRIDE] & 0x7fffffffu;
+                lmax = L > lmax ? L : lmax;
+            }
             uint32_t maxf = 0;
-            for (uint32_t j = 0; j < m; j++) {
-                const uint32_t f = mem.at(slot(cbuf, j));
+            for (uint32_t m = cur; m; m &= m - 1u) {
+                const uint32_t f = slotp(uint32_t(k4_ffs(m)) - 1u)[0];
                 maxf = f > maxf ? f : maxf;
             }
-            uint32_t acc = 0;
-            for (uint32_t r = 0; r < K4_BURST; r++) {
-                // everything the step and the jump after it ask about the end of the string stays as it was
-                bool same = uint64_t(i) + delta + 2 < n && uint64_t(maxf) + acc + delta < n && at(i) == rp_ch;
-                for (uint32_t e = 0; e < n_log && same; e++) {
-                    const uint32_t vs = mem.at(l0 + 2 * e), lw = mem.at(l0 + 2 * e + 1);
-                    const uint32_t L = lw & 0x7fffffffu;
-                    if (n - i < L || span_equal(vs, i, L) != ((lw >> 31) != 0u)) same = false;
-                }
-                if (!same) {
-                    rp_delta = 0;
-                    break;
-                }
-                acc += delta;
-                i += delta;
-                steps_replayed++;
+            // ProgSim::replay answers the step at p only if p + delta + 2 < n and no `first` (moved on to p) reaches
+            // n - delta: everything the step and the jump after it ask about the end of the string stays as it was
+            uint32_t d = maxf > i ? maxf - i : 0u;
+            d = d < 2u ? 2u : d;
+            if (uint64_t(i) + delta + d < n) {
+                const uint32_t p_end = n - delta - d;  // steps at p < p_end may be answered
+                const uint64_t vcap = uint64_t(p_end) - 1u + lmax;  // where the last of them looks up to
+                rp_delta = delta;
+                rp_lmax = lmax;
+                rp_vp = i;
+                rp_vcap = vcap < n ? uint32_t(vcap) : n;  // (a block that does not fit the rest is never answered)
+                rp_acc = 0;
+                rp_mism = false;
+                rp_magic = 0xffffffffull / delta + 1ull;
+                want = K4_WANT_A;
             }
-            if (acc) {  // the previous result, moved on
-                for (uint32_t j = 0; j < m; j++) {
-                    const uint32_t o = slot(cbuf, j);
-                    mem.at(o) += acc;
-                    const uint32_t fl = mem.at(o + 1) >> 16;
-RXM_UNROLL
-                    for (int k = 0; k < NC; k++)
-                        if (fl_exists(fl, k) && fl_open(fl, k)) mem.at(o + 3 + NC + k) += acc;
-                }
-            }
-            generic = (rp_delta == 0);
         }
-        if (!generic) return false;
+    }
 
-        // ---- one step in full: evaluateStates (mfa.cpp:203-213) ----
+    // ---- PHASE A: repeated steps ------------------------------------------------------------------
+    // The step at i repeats the previous one -- same letter, same outcomes of the same block compares --
+    // if the input it looks at equals the input the previous step looked at:
+    //     s[j] == s[j - delta]   for j in [i, i + lmax),   lmax = the longest block the step compared (>= 1)
+    // (a sufficient condition for ProgSim::replay's "same outcomes").  Its result is then the previous result
+    // moved on, and so on for the steps after it.  One iteration of the FLAT loop verifies one aligned word
+    // ahead of the front rp_vp and then answers every step the front has passed -- the same instructions
+    // for every lane whatever its distance, block length and position.
+    RXM_HD void phase_a() {
+        const uint32_t delta = rp_delta;
+        for (uint32_t r = 0; r < K4_BURST; r++) {
+            const bool can = !rp_mism && rp_vp < rp_vcap;
+            if (can) {  // one aligned word of the input against the input delta bytes before it
+                const uint8_t *b = s + rp_vp;
+                const uint32_t ob = uint32_t(reinterpret_cast<uintptr_t>(b) & 7u);
+                const uint8_t *b0 = b - ob;
+                const uint8_t *unit_end = (b0 + 8 < s + n) ? b0 + 8 : s + n;
+                const uint8_t *ap = b0 - delta;
+                const uint32_t oa = uint32_t(reinterpret_cast<uintptr_t>(ap) & 7u);
+                const uint8_t *a0 = ap - oa;
+                const uint32_t sh = oa * 8u;
+                // only words that hold a byte of [b - delta, unit_end - delta) are read
+                const uint64_t lo = (a0 + 8 > b - delta) ? k4_ld64(a0) : 0ull;
+                const uint64_t hi = (sh != 0u && a0 + 8 < unit_end - delta) ? k4_ld64(a0 + 8) : 0ull;
+                const uint64_t wa = sh ? ((lo >> sh) | (hi << (64u - sh))) : lo;
+                uint64_t x = wa ^ k4_ld64(b0);
+                x &= ~0ull << (8u * ob);
+                const uint32_t rem = uint32_t(unit_end - b0);
+                if (rem < 8u) x &= (1ull << (8u * rem)) - 1ull;
+                if (x) {
+                    rp_vp = uint32_t(b0 - s) + (uint32_t(k4_ffs64(x)) - 1u) / 8u;
+                    rp_mism = true;
+                } else {
+                    rp_vp = uint32_t(unit_end - s);
+                }
+            }
+            const uint32_t front = rp_vp < rp_vcap ? rp_vp : rp_vcap;
+            const uint32_t target = i + rp_lmax;
+            if (front >= target) {  // the steps at i, i + delta, ... whose blocks end at or before the front
+                uint32_t xx = front - target;
+                uint32_t k;
+                if (delta >= 4096u) {
+                    k = 1u + (xx >= delta ? 1u : 0u);
+                } else {
+                    xx = xx < (1u << 19) ? xx : (1u << 19);  // xx * delta < 2^32: the quotient below is exact
+                    k = 1u + uint32_t((xx * rp_magic) >> 32);
+                }
+                rp_acc += k * delta;
+                i += k * delta;
+                steps_replayed += k;
+            } else if (!can) {  // the front stands (a difference, or the end of what may be answered)
+                rp_delta = 0;
+                break;
+            }
+        }
+        if (rp_delta != 0) return;  // more of it in the next round
+        if (rp_acc) {               // leaving: the previous result, moved on
+            const uint32_t acc = rp_acc;
+            for (uint32_t m = cur; m; m &= m - 1u) {
+                uint32_t *sp = slotp(uint32_t(k4_ffs(m)) - 1u);
+                sp[0] += acc;
+                const uint32_t fl = sp[STRIDE] >> 16;
+RXM_UNROLL
+                for (int k = 0; k < NC; k++)
+                    if (fl_exists(fl, k) && fl_open(fl, k)) sp[(3 + NC + k) * STRIDE] += acc;
+            }
+            rp_acc = 0;
+        }
+        want = K4_WANT_B;  // the step at i is run in full
+    }
+
+    // ---- PHASE B: one step in full -- evaluateStates (mfa.cpp:203-213) over evaluateState (:136-200)
+    // -- and the jump over the idle steps behind it.  The walk over (configuration, item of its list) is one
+    // flat loop: the lanes of a warp meet in the same body whatever configuration each of them is on.
+    // Ends with want = K4_DONE (result = 0 / 1, or 2 if a limit was met -- never a guess) or K4_WANT_NONE.
+    RXM_HD void phase_b(const MfaView &t, const K4Prog &p) {
         n_log = 0;
         log_bad = false;
-        have_prev = true;
-        prev_i = i;
+        near = false;
+        prv = 0u;  // the set before this one is not needed any more
+        nxt = 0u;
         {
-            const uint32_t cbuf = nb ^ 1u, m = cnt(cbuf);
-            set_cnt(nb, 0);
-            for (uint32_t j = 0; j < m; j++) {  // any order: see prog_stamp
-                cfg_t c;
-                load(cbuf, j, c);
-                eval(t, p, c);
+            const uint32_t ch = (i < n) ? at(i) : 0u;
+            const uint32_t digit_bit = (ch >= '1' && ch <= '9') ? (1u << (ch - '1')) : 0u;
+            uint32_t todo = cur, js = 0, q = 0, nq = 0, lbase = 0, pb = 0;
+            bool active = false, waiting = false, fin = false;
+            cfg_t root;
+            for (;;) {  // any order of the configurations: see prog_stamp
+                if (q == nq) {  // next configuration of the current set
+                    if (!todo) break;
+                    js = uint32_t(k4_ffs(todo)) - 1u;
+                    todo &= todo - 1u;
+                    load(js, root);
+                    q = nq = 0;
+                    fin = (root.first == n);
+                    active = (i != n && i == root.first);
+                    waiting = (i != n && i < root.first);
+                    if (!(active || waiting || fin)) continue;  // behind the step: no branch of mfa.cpp:161-197 fires
+                    if (!(root.node == t.finish && fin) && t.reversed && need_of(root.flags, root.len) > n - i) continue;  // :141
+                    const uint32_t key = (root.node << p.n_cells) | k4_exists_mask<NC>(root.flags);
+                    pb = p.begin[key];
+                    if (pb == 0xffffffffu) {  // a (node, cells) pair the host analysis did not reach
+                        overflow = true;
+                        continue;
+                    }
+                    const uint32_t lc = p.lcnt[key];
+                    lbase = p.lbeg[key] + (active ? 0u : (lc & 0xffffu));  // LEAF items act for an active configuration,
+                    nq = active ? (lc & 0xffffu) : (lc >> 16);             // ENTER items for a waiting / final one
+                    continue;
+                }
+                const uint32_t x = p.sel[lbase + q];
+                q++;
+                const ProgItem it = p.items[pb + x];
+                if (active) {
+                    const uint32_t kind = pi_kind(it), rc = pi_read_cell(it);
+                    uint32_t L = 1;
+                    bool fire = false;
+                    if (kind == kEdgeAny || (kind == kEdgeLit && pi_sym(it) == ch)) {  // :171-175
+                        fire = true;
+                    } else if (rc) {  // :176-193, the cell is present
+                        const int k = int(rc) - 1;
+                        const bool fresh = (pi_created(it) >> k) & 1u;
+                        uint32_t vs = 0, fl = 0;
+                        L = 0;
+RXM_UNROLL
+                        for (int kk = 0; kk < NC; kk++)
+                            if (kk == k) {
+                                L = fresh ? 0u : root.len[kk];
+                                vs = root.start[kk];
+                                fl = (root.flags >> (3 * kk)) & 7u;
+                            }
+                        if (!fresh && (fl & 2u)) log_bad = true;  // the text of an open cell changes from step to step
+                        if (n - i >= L) fire = (L == 0) || compare_logged(vs, L);
+                    }
+                    if (fire) {
+                        cfg_t nx;
+                        prog_working<NC>(nx, root, pi_created(it), pi_created_open(it), pi_prior_reads(it) & ~digit_bit);
+                        nx.node = pi_node(it);
+                        nx.born = prog_stamp(false, root.node, x);
+                        nx.first += L;
+                        apply_actions<NC>(nx, pi_open(it), pi_close(it), i, L);
+                        insert(nx);
+                    }
+                } else {
+                    if (fin && pi_skip_final(it)) continue;  // below a call that returned at mfa.cpp:138-140
+                    const uint32_t v = pi_node(it);
+                    if ((v == t.finish && fin) || (waiting && pi_has_leaf(it))) {  // :138-140 / :195-197
+                        if (x == 0) {  // the root call: the configuration itself
+                            reinsert(js, root);
+                        } else {
+                            cfg_t w;
+                            prog_working<NC>(w, root, pi_created(it), pi_created_open(it), 0u);
+                            w.node = v;
+                            w.born = prog_stamp(true, root.node, x);
+                            insert(w);
+                        }
+                    }
+                }
             }
         }
         steps_run++;
-        nb ^= 1u;  // states = new_states (:212)
+        have_prev = true;
+        prev_i = i;
+        want = K4_WANT_NONE;
         if (overflow) {
             result = 2;
-            return true;
+            want = K4_DONE;
+            return;
         }
-        const uint32_t cbuf = nb ^ 1u, m = cnt(cbuf);
+        const uint32_t before = cur;  // the set this step started from
+        prv = before;
+        cur = nxt;                    // states = new_states (:212)
+        nxt = 0u;
         if (i == n) {  // the pass at i == n is the last (:227-228); :230-235
             result = 0;
-            for (uint32_t j = 0; j < m; j++)
-                if ((mem.at(slot(cbuf, j) + 1) & 0xffffu) == t.finish) result = 1;
-            return true;
+            for (uint32_t m = cur; m; m &= m - 1u)
+                if ((slotp(uint32_t(k4_ffs(m)) - 1u)[STRIDE] & 0xffffu) == t.finish) result = 1;
+            want = K4_DONE;
+            return;
         }
-        // ---- idle steps are not run (ProgSim::run) ----
-        if (m != 0 && i + 1 < n) {
-            // (a) every configuration waits (first >= i + 2) and is reproduced unchanged by a step
-            //     (kProgStable): the steps up to the first activation / reversed-mode pruning are the identity
+        // ---- idle steps are not run (ProgSim::run); a jump needs every `first` >= i + 2 ----
+        if (!near && cur != 0u && i + 1 < n) {
+            // (a) every configuration waits and is reproduced unchanged by a step (kProgStable): the steps up to
+            //     the first activation / reversed-mode pruning are the identity
             bool stable = true;
             uint32_t ev = n;
-            for (uint32_t j = 0; j < m && stable; j++) {
-                const uint32_t o = slot(cbuf, j);
-                const uint32_t f = mem.at(o), nf = mem.at(o + 1);
+            for (uint32_t m = cur; m && stable; m &= m - 1u) {
+                const uint32_t j = uint32_t(k4_ffs(m)) - 1u;
+                const uint32_t *sp = slotp(j);
+                const uint32_t f = sp[0], nf = sp[STRIDE];
                 if (f < i + 2 || f == n) stable = false;
-                const uint32_t key = ((nf & 0xffffu) << p.n_cells) | (exists_mask(nf >> 16) & ((1u << p.n_cells) - 1u));
+                const uint32_t key = ((nf & 0xffffu) << p.n_cells) | k4_exists_mask<NC>(nf >> 16);
                 if (p.begin[key] == 0xffffffffu || !(p.count[key] & kProgStable)) stable = false;
                 if (f < ev) ev = f;
                 if (t.reversed) {
                     cfg_t c;
-                    load(cbuf, j, c);
-                    const uint32_t need = need_of(c);
+                    load(j, c);
+                    const uint32_t need = need_of(c.flags, c.len);
                     const uint32_t ps = need > n ? 0u : n - need + 1u;  // fresh: not yet tested against mfa.cpp:141
                     if (ps < ev) ev = ps;
                 }
             }
             if (stable) {
                 if (ev > i + 1) i = ev - 1;  // the increment below makes the next step ev
-            } else if (m == cnt(nb)) {
+            } else if (k4_popc(cur) == k4_popc(before)) {
                 // (b) no configuration was active in the step just run and it reproduced its input set:
                 //     every further step does the same, bit for bit (prog_stamp does not depend on i)
                 bool idle = true;
                 ev = n;
-                for (uint32_t j = 0; j < m && idle; j++) {
+                for (uint32_t m = cur; m && idle; m &= m - 1u) {
+                    const uint32_t j = uint32_t(k4_ffs(m)) - 1u;
                     cfg_t c;
-                    load(cbuf, j, c);
+                    load(j, c);
                     if (c.first <= i) idle = false;
                     if (c.first < ev) ev = c.first;
                     if (t.reversed && !(c.node == t.finish && c.first == n)) {
-                        const uint32_t ps = n - need_of(c) + 1u;  // need <= n - i here
+                        const uint32_t ps = n - need_of(c.flags, c.len) + 1u;  // need <= n - i here
                         if (ps < ev) ev = ps;
                     }
+                    if ((before >> j) & 1u) continue;  // re-inserted as it was: its slot is in both sets
                     bool found = false;
-                    for (uint32_t q = 0; q < m; q++) {
-                        if ((mem.at(slot(nb, q) + 1) & 0xffffu) != c.node) continue;
+                    for (uint32_t mp = before; mp; mp &= mp - 1u) {
+                        const uint32_t jp = uint32_t(k4_ffs(mp)) - 1u;
+                        if ((slotp(jp)[STRIDE] & 0xffffu) != c.node) continue;
                         cfg_t pv;
-                        load(nb, q, pv);
+                        load(jp, pv);
                         found = cfg_same<NC>(pv, c);
                         break;
                     }
@@ -460,16 +604,20 @@ RXM_UNROLL
             }
         }
         i++;
-        return false;
     }
 
-    // MFA::match (mfa.cpp:215-236) for one string, start to end (host tests; the kernel drives advance itself)
+    // MFA::match (mfa.cpp:215-236) for one string, start to end (host tests; the kernel drives the phases
+    // itself and lets the lanes of a warp run the phase most of them want)
     RXM_HD int run(const MfaView &t, const K4Prog &p, const uint8_t *str, uint32_t len) {
-        start(str, len, t.reversed, t);
-        int r = 0;
-        while (!advance(t, p, r)) {
+        start(str, len, t.reversed, t.start);
+        for (;;) {
+            pre();
+            if (want == K4_DONE) break;
+            if (want == K4_WANT_A) phase_a();
+            else phase_b(t, p);
+            if (want == K4_DONE) break;
         }
-        return r;
+        return result;
     }
 };
 

@@ -181,9 +181,9 @@ template <int NC>
 static void run_k4_batch(const rxm::MfaView &v, const rxm::K4Prog &kp, uint32_t maxl, const uint8_t *chars,
                          const uint64_t *off, uint64_t n, uint8_t *out, uint64_t *info3) {
     std::vector<uint32_t> words(rxm::k4_words(NC, maxl));
-    rxm::K4Sim<NC> sim;
-    sim.mem = rxm::K4Mem{words.data(), 1};
-    sim.maxl = maxl;
+    rxm::K4Sim<NC, 1> sim;
+    sim.base = words.data();
+    sim.pool = maxl;
     for (uint64_t i = 0; i < n; i++) {
         const int r = sim.run(v, kp, chars + off[i], uint32_t(off[i + 1] - off[i]));
         out[i] = uint8_t(r);
@@ -210,7 +210,7 @@ extern "C" int hostsim_k4core_batch(const rxm_tables *t, const uint8_t *chars, c
     rxm::K4Prog kp{prog.items.data(), prog.begin.data(), prog.count.data(), prog.lbeg.data(), prog.lcnt.data(),
                    prog.sel.data(), prog.n_cells};
     if (info3) info3[0] = info3[1] = info3[2] = 0;
-    if (maxl == 0) maxl = t->n_states;
+    if (maxl == 0 || maxl > rxm::K4_POOL_MAX) maxl = rxm::k4_pool_for(t->n_states);  // the planner's choice
     if (t->n_cells <= 1) run_k4_batch<1>(v, kp, maxl, chars, off, n, out, info3);
     else if (t->n_cells <= 2) run_k4_batch<2>(v, kp, maxl, chars, off, n, out, info3);
     else run_k4_batch<4>(v, kp, maxl, chars, off, n, out, info3);

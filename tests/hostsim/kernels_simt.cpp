@@ -113,8 +113,8 @@ extern "C" int hostsim_k4_batch(const rxm_tables *t, const uint8_t *chars, const
     unsigned long long work[2] = {0, 0};
     std::vector<uint32_t> redo(n + 1);
     unsigned long long redo_n = 0;
-    if (maxl == 0) maxl = t->n_states < 8u ? t->n_states : 8u;
-    const bool use_redo = t->n_states > maxl;
+    if (maxl == 0 || maxl > rxm::K4_POOL_MAX) maxl = rxm::k4_pool_for(t->n_states);  // the planner's choice
+    const bool use_redo = 2 * t->n_states > maxl;  // the current set and the one being built share the pool
     Run run(limit, seed);
     int launched = 0;
     st = rxm::k4_launch(v, kp, uint32_t(prog.items.size()), uint32_t(prog.begin.size()), uint32_t(prog.sel.size()),

@@ -110,23 +110,33 @@ def test_block_compare_every_alignment_and_length():
 def test_k4_core_on_host_matches_golden(name):
     t, strings, bits = load_case(name)
     chars, off = H.make_batch(strings)
-    rc, got, info = k4_core(t, chars, off)
-    assert rc == 0 and info[2] == 0
-    assert np.array_equal(got, bits), [strings[i] for i in np.nonzero(got != bits)[0][:5]]
+    rc, got, info = k4_core(t, chars, off)  # the planner's pool: 8 .. 16 slots
+    assert rc == 0
+    ok = got != 2  # strings that outgrow the pool are REPORTED (the kernel hands them to K3), never answered wrongly
+    assert np.array_equal(got[ok], bits[ok]), [strings[i] for i in np.nonzero((got != bits) & ok)[0][:5]]
+    assert int((~ok).sum()) == info[2]
+    if name.endswith("_fwd"):
+        assert info[2] == 0  # every forward automaton of the reference's examples fits
+    rc, got, info = k4_core(t, chars, off, 32)
+    assert rc == 0 and (info[2] == 0 or name == "ex08_rev")
+    ok = got != 2
+    assert np.array_equal(got[ok], bits[ok])
 
 
 def test_k4_core_random_expression_corpus_and_replay_share():
-    n_run = replayed = 0
+    n_run = replayed = limited = 0
     for regex, flags, kind, t, strings, bits in load_fuzz_corpus():
         if kind != "mfa" or t.c.n_cells > 4:
             continue
         chars, off = H.make_batch(strings)
         rc, got, info = k4_core(t, chars, off)
-        assert rc == 0 and info[2] == 0, (regex, flags)
-        assert np.array_equal(got, bits), (regex, flags)
+        assert rc == 0, (regex, flags)
+        ok = got != 2
+        assert np.array_equal(got[ok], bits[ok]), (regex, flags)
+        limited += info[2]
         n_run += 1
         replayed += info[1]
-    assert n_run > 100 and replayed > 300
+    assert n_run > 100 and replayed > 300 and limited < 300
 
 
 def test_k4_core_small_sets_report_what_they_cannot_hold():
@@ -136,7 +146,7 @@ def test_k4_core_small_sets_report_what_they_cannot_hold():
     for name in ("ex02_rev", "ex05_rev", "ex08_rev", "ex14_rev", "ex15_rev", "ex09_fwd"):
         t, strings, bits = load_case(name)
         chars, off = H.make_batch(strings)
-        for maxl in (1, 2, 3):
+        for maxl in (1, 2, 4):
             rc, got, info = k4_core(t, chars, off, maxl)
             assert rc == 0
             ok = got != 2
@@ -161,8 +171,10 @@ def test_k4_core_config3_config4_config5_strings():
         t, _, _ = load_case(name)
         chars, off = W.attack_batch(["bbaa", "aaba", "bbaa"], "c", "", 96, 435, 65536, 5)
         rc, got, info = k4_core(t, chars, off)
-        assert rc == 0 and info[2] == 0
-        assert np.array_equal(got, H.oracle_bits(t, chars, off)), name
+        assert rc == 0
+        ok = got != 2
+        assert np.array_equal(got[ok], H.oracle_bits(t, chars, off)[ok]), name
+        assert name == "ex02_rev" or info[2] == 0
     for ex in range(1, 11):
         t, _, _ = load_case(f"ex{ex:02d}_fwd")
         chars, off = W.mixed_example_batch(ex, 1500, 77 + ex)
