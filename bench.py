@@ -349,9 +349,17 @@ ORIG_AFFINITY = None
 def bind_to_gpu_numa_node(local_rank):
     """Run this rank on the CPUs of the NUMA node its GPU hangs off (what `numactl` would do for a
     one-process-per-GPU job): pinned host buffers are then allocated next to the GPU's PCIe root,
-    which is what the host-buffer (`e2e`) path pays for when several ranks copy at once.  Returns
-    the node or None; the original affinity is kept for the CPU-baseline leg."""
+    which is what the host-buffer (`e2e`) path pays for when several ranks copy at once.  Returns what
+    was found -- {"node", "pci", "host_numa_nodes", "bound_cpus", "why"} -- so that a record says WHY a
+    rank was not bound (round 1's records only said null); the original affinity is kept for the
+    CPU-baseline leg."""
     global ORIG_AFFINITY
+    info = {"node": None, "pci": None, "host_numa_nodes": None, "bound_cpus": None, "why": None}
+    try:
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        info["host_numa_nodes"] = len(nodes)
+    except OSError as e:
+        info["why"] = f"/sys/devices/system/node: {e.strerror}"
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -360,9 +368,11 @@ def bind_to_gpu_numa_node(local_rank):
         bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
         bus = bus.decode() if isinstance(bus, bytes) else bus
         bdf = bus.lower()[-12:]  # 0000:1b:00.0
+        info["pci"] = bdf
         node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
         if node < 0:
-            return None
+            info["why"] = "the kernel reports numa_node -1 for the GPU's PCI device (no affinity exposed: a VM or a single-node host)"
+            return info
         cpus = set()
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             lo, _, hi = part.partition("-")
@@ -371,10 +381,206 @@ def bind_to_gpu_numa_node(local_rank):
         cpus &= ORIG_AFFINITY
         if cpus:
             os.sched_setaffinity(0, cpus)
-            return node
-    except Exception:
-        pass
-    return None
+            info["node"] = node
+            info["bound_cpus"] = len(cpus)
+        else:
+            info["why"] = f"node {node} has no CPU this process may run on"
+    except Exception as e:  # noqa: BLE001 -- recorded, not fatal
+        info["why"] = f"{type(e).__name__}: {e}"
+    return info
+
+
+# --------------------------------------------------------------------------------------
+# GPU arm: jobs (one matcher call each per step), timing, parity spot check
+# --------------------------------------------------------------------------------------
+
+def build_jobs(W, rxm, wl, strings, seed, dev, local_rank, host=None):
+    """The jobs of one workload on this rank: dicts with name, regex, flags, tables, chars, offsets (device
+    tensors), n, bytes, out, matcher.  `host` = precomputed list of (name, regex, flags, chars, offsets) numpy
+    batches (the sharded mode cuts one global batch); otherwise the batches are generated here."""
+    import torch
+    case, regex, flags, desc = WORKLOADS[wl]
+    jobs = []
+    if host is not None:
+        for name, rgx, fl, c_np, o_np in host:
+            jobs.append({"name": name, "regex": rgx, "flags": fl,
+                         "tables": rxm.Tables.load(os.path.join(CASES, name + ".rxt")),
+                         "chars": torch.from_numpy(np.ascontiguousarray(c_np)).to(dev),
+                         "offsets": torch.from_numpy(o_np.astype(np.int64)).to(dev)})
+    elif wl in ("config2", "config3"):
+        tables = rxm.Tables.load(os.path.join(CASES, case + ".rxt"))
+        ch, of = make_workload(W, wl, tables.text, strings, seed, dev)
+        jobs.append({"name": case, "regex": regex, "flags": flags, "tables": tables, "chars": ch, "offsets": of})
+    else:
+        for name, rgx, fl, c_np, o_np in host_batches(W, wl, strings, seed):
+            jobs.append({"name": name, "regex": rgx, "flags": fl,
+                         "tables": rxm.Tables.load(os.path.join(CASES, name + ".rxt")),
+                         "chars": torch.from_numpy(c_np).to(dev),
+                         "offsets": torch.from_numpy(o_np.astype(np.int64)).to(dev)})
+    for j in jobs:
+        j["n"] = int(j["offsets"].numel() - 1)
+        j["bytes"] = int(j["offsets"][-1]) if j["n"] else 0
+        j["out"] = torch.empty(max(j["n"], 1), dtype=torch.uint8, device=dev)[:j["n"]]
+        j["matcher"] = rxm.Matcher(j["tables"], local_rank)
+    return jobs
+
+
+def host_batches(W, wl, strings, seed):
+    """configs 4 and 5 as numpy batches: (fixture name, regex, flags, chars, offsets) per job."""
+    regex = WORKLOADS[wl][1]
+    out = []
+    if wl == "config4":
+        n4 = strings if strings != 1_000_000 else 4096
+        c_np, o_np = W.attack_batch(["bbaa", "aaba", "bbaa"], "c", "", n4, 435, 65536, seed)
+        for cname, fl in (("ex02_fwd", []), ("ex02_rev", ["-reverse"])):
+            out.append((cname, regex, fl, c_np, o_np))
+    else:  # config5
+        per = strings // 10
+        for ex in range(1, 11):
+            c_np, o_np = W.mixed_example_batch(ex, per, 1000 * ex + seed)
+            out.append((f"ex{ex:02d}_fwd", W.README_EXAMPLES[ex][0], [], c_np, o_np))
+    return out
+
+
+class JobRunner:
+    """One step = every job's rxm_match_batch once; several jobs run on streams of their own, forked from and
+    joined back into the timed stream (handles may run concurrently, include/rxm.h)."""
+
+    def __init__(self, jobs, dev, share):
+        import torch
+        self.torch = torch
+        self.jobs = jobs
+        for j in jobs:
+            j["matcher"].set_concurrency(share)
+        self.stream = torch.cuda.current_stream().cuda_stream
+        self.job_streams = [torch.cuda.Stream(device=dev) for _ in jobs] if len(jobs) > 1 else []
+        self.fork_ev = torch.cuda.Event()
+        self.join_evs = [torch.cuda.Event() for _ in self.job_streams]
+
+    def step_device(self):
+        torch = self.torch
+        if not self.job_streams:
+            j = self.jobs[0]
+            j["matcher"].match_ptrs(j["chars"].data_ptr(), j["offsets"].data_ptr(), j["n"], j["out"].data_ptr(), self.stream)
+            return
+        cur = torch.cuda.current_stream()
+        self.fork_ev.record(cur)
+        for j, st, ev_j in zip(self.jobs, self.job_streams, self.join_evs):
+            st.wait_event(self.fork_ev)
+            j["matcher"].match_ptrs(j["chars"].data_ptr(), j["offsets"].data_ptr(), j["n"], j["out"].data_ptr(), st.cuda_stream)
+            ev_j.record(st)
+        for ev_j in self.join_evs:
+            cur.wait_event(ev_j)
+
+    def launch_count(self):
+        return sum(j["matcher"].launch_count() for j in self.jobs)
+
+    def overflow_count(self):
+        return sum(j["matcher"].overflow_count() for j in self.jobs)
+
+    def close(self):
+        for j in self.jobs:
+            j["matcher"].close()
+
+    def time_steps(self, steps, total_bytes, dev):
+        """K steps with a CUDA event between them.  Inputs smaller than twice the 126 MB L2 get a 512 MB buffer
+        written between the timed steps (outside every per-step event pair); larger inputs evict themselves.
+        -> (per-step ms list, total ms over the K steps as the device saw them, flushed?)"""
+        torch = self.torch
+        flush = total_bytes < 2 * 126 * (1 << 20)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        if flush:
+            flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+            ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+            for k in range(steps):
+                flush_buf.fill_(k & 0xff)
+                ev0[k].record()
+                self.step_device()
+                ev[k + 1].record()
+            torch.cuda.synchronize()
+            step_ms = [ev0[k].elapsed_time(ev[k + 1]) for k in range(steps)]
+            return step_ms, sum(step_ms), True
+        ev[0].record()
+        for k in range(steps):
+            self.step_device()
+            ev[k + 1].record()
+        torch.cuda.synchronize()
+        step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(steps)]
+        return step_ms, ev[0].elapsed_time(ev[steps]), False
+
+
+def parity_spot_check(jobs, H):
+    """Outside every timed region: the device's bits against the C restatement on a sample that spans the WHOLE
+    length range of every job -- evenly spaced picks from the strings ordered by length, the longest included.
+    Returns the number of strings checked; raises SystemExit on any difference."""
+    checked = 0
+    for j in jobs:
+        if j["n"] == 0:
+            continue
+        off = j["offsets"].cpu().numpy().astype(np.uint64)
+        lens = np.diff(off)
+        long_strings = j["bytes"] / max(1, j["n"]) >= 5000
+        k = min(j["n"], 96 if long_strings else 3000)
+        order = np.argsort(lens, kind="stable")
+        pick = np.unique(order[np.linspace(0, j["n"] - 1, k).astype(np.int64)])
+        ch = j["chars"].cpu().numpy()
+        parts = [ch[int(off[i]):int(off[i + 1])] for i in pick]
+        so = np.zeros(len(pick) + 1, dtype=np.uint64)
+        np.cumsum([len(p) for p in parts], out=so[1:])
+        sc = np.concatenate(parts) if int(so[-1]) else np.zeros(0, dtype=np.uint8)
+        want = H.oracle_bits(j["tables"], sc, so)
+        got = j["out"].cpu().numpy()[pick]
+        if not np.array_equal(got, want):
+            bad = pick[np.nonzero(got != want)[0][:5]]
+            raise SystemExit(f"bench.py: {j['name']}: {int((got != want).sum())} of {len(pick)} bits differ from the oracle "
+                             f"(strings {bad.tolist()}, lengths {lens[bad].tolist()})")
+        checked += len(pick)
+    return checked
+
+
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+def extra_workload(W, rxm, H, wl, strings, steps, dev, local_rank, seed):
+    """A short measurement of another BASELINE config inside the default run: the same
+    timing rules as the headline (warm-up, CUDA events, L2 flush for small inputs, parity spot check)."""
+    import torch
+    jobs = build_jobs(W, rxm, wl, strings, seed, dev, local_rank)
+    share = len(jobs) if wl == "config4" else 1
+    R = JobRunner(jobs, dev, share)
+    n = sum(j["n"] for j in jobs)
+    total_bytes = sum(j["bytes"] for j in jobs)
+    for _ in range(3):
+        R.step_device()
+    torch.cuda.synchronize()
+    l0 = R.launch_count()
+    step_ms, total_ms, flushed = R.time_steps(steps, total_bytes, dev)
+    launches = R.launch_count() - l0
+    if R.overflow_count():
+        raise SystemExit(f"bench.py: {wl}: strings hit a kernel limit")
+    checked = parity_spot_check(jobs, H)
+    k_ms = statistics.mean(step_ms)
+    peak, _ = hbm_peak()
+    algo = total_bytes + 9 * n
+    res = {
+        "workload": WORKLOADS[wl][3], "strings": n, "bytes": total_bytes, "jobs_per_step": len(jobs), "steps": steps,
+        "ms_per_step": k_ms, "strings_per_sec": n / (k_ms / 1e3), "input_gb_s": total_bytes / (k_ms / 1e3) / 1e9,
+        "roofline_frac": algo / (k_ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_step": algo,
+        "engine": "+".join(sorted({rxm.ENGINE_NAMES.get(j["matcher"].plan().engine, "?") for j in jobs})),
+        "gpu_launches": int(launches), "l2_flushed_between_steps": flushed, "parity_checked": checked,
+        "match_fraction": float(sum(float(j["out"].float().sum().item()) for j in jobs) / max(1, n)),
+    }
+    eff = os.path.join(ROOT, "profiles", "mfa_kernel_efficiency.json")  # from the committed ncu captures
+    if os.path.exists(eff):
+        res["ncu"] = json.load(open(eff)).get(wl)
+    R.close()
+    del jobs, R
+    torch.cuda.empty_cache()
+    return res
 
 
 def main():
@@ -382,10 +588,14 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--strings", type=int, default=1_000_000, help="strings per GPU")
+    ap.add_argument("--strings", type=int, default=1_000_000, help="strings per GPU (weak) / in the whole batch (strong)")
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank owns a batch of --strings; strong: ONE batch of --strings is cut by bytes "
+                         "over the ranks (sharding.py), the result bits are gathered over NCCL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-workloads", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     # stdout carries exactly ONE JSON line: anything libraries print there (NCCL prints its version
@@ -409,7 +619,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
-    numa_node = bind_to_gpu_numa_node(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -434,151 +644,138 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers as H  # the oracle (checker), outside every timed region
+
     wl = args.workload
     case, regex, flags, desc = WORKLOADS[wl]
-    # a step runs every job once; single-expression workloads have one job
-    jobs = []  # dicts: name, regex, flags, tables, chars, offsets, n, bytes, out, matcher
-    if wl in ("config2", "config3"):
-        tables = rxm.Tables.load(os.path.join(CASES, case + ".rxt"))
-        ch, of = make_workload(W, wl, tables.text, args.strings, 1000 + rank, dev)
-        jobs.append({"name": case, "regex": regex, "flags": flags, "tables": tables, "chars": ch, "offsets": of})
-    elif wl == "config4":
-        n4 = args.strings if args.strings != 1_000_000 else 4096
-        c_np, o_np = W.attack_batch(["bbaa", "aaba", "bbaa"], "c", "", n4, 435, 65536, 1000 + rank)
-        ch, of = torch.from_numpy(c_np).to(dev), torch.from_numpy(o_np.astype(np.int64)).to(dev)
-        for cname, fl in (("ex02_fwd", []), ("ex02_rev", ["-reverse"])):
-            jobs.append({"name": cname, "regex": regex, "flags": fl,
-                         "tables": rxm.Tables.load(os.path.join(CASES, cname + ".rxt")), "chars": ch, "offsets": of})
-    else:  # config5
-        per = args.strings // 10 if args.strings != 1_000_000 else 100_000
-        for ex in range(1, 11):
-            c_np, o_np = W.mixed_example_batch(ex, per, 1000 * ex + rank)
-            jobs.append({"name": f"ex{ex:02d}_fwd", "regex": W.README_EXAMPLES[ex][0], "flags": [],
-                         "tables": rxm.Tables.load(os.path.join(CASES, f"ex{ex:02d}_fwd.rxt")),
-                         "chars": torch.from_numpy(c_np).to(dev),
-                         "offsets": torch.from_numpy(o_np.astype(np.int64)).to(dev)})
-    for j in jobs:
-        j["n"] = int(j["offsets"].numel() - 1)
-        j["bytes"] = int(j["offsets"][-1])
-        j["out"] = torch.empty(j["n"], dtype=torch.uint8, device=dev)
-        j["matcher"] = rxm.Matcher(j["tables"], local_rank)
+    strong = args.scaling == "strong"
+    sharded = None
+    if strong:
+        # ONE batch (every rank builds the same one from the same seed -- what reading one shared input would
+        # give), cut into byte-balanced contiguous string ranges, one per rank (sharding.py)
+        S = _load("sharding", os.path.join(PKG, "sharding.py"))
+        if wl in ("config2", "config3"):
+            tbl = rxm.Tables.load(os.path.join(CASES, case + ".rxt"))
+            ch, of = make_workload(W, wl, tbl.text, args.strings, 1000, dev)
+            whole = [(case, regex, flags, ch.cpu().numpy(), of.cpu().numpy().astype(np.uint64))]
+            del ch, of
+        else:
+            whole = host_batches(W, wl, args.strings, 0)
+        sharded = []
+        mine = []
+        for name, rgx, fl, c_np, o_np in whole:
+            bounds = S.shard_by_bytes(o_np, world)
+            lc, lo = S.local_view(c_np, o_np, bounds[rank], bounds[rank + 1])
+            mine.append((name, rgx, fl, lc, lo))
+            sharded.append({"name": name, "bounds": bounds, "n": len(o_np) - 1})
+        jobs = build_jobs(W, rxm, wl, args.strings, 0, dev, local_rank, host=mine)
+    else:
+        jobs = build_jobs(W, rxm, wl, args.strings, 1000 + rank, dev, local_rank)
     # config 4 is bounded by its longest string in each of the two automata: the handles share the
     # device (rxm_set_concurrency) so that the two launches run side by side; config 5's ten jobs are
     # throughput-bound and stay at one launch filling the device after another
     share = int(os.environ.get("RXM_BENCH_SHARE", len(jobs) if wl == "config4" else 1))
-    for j in jobs:
-        j["matcher"].set_concurrency(share)
+    R = JobRunner(jobs, dev, share)
     n = sum(j["n"] for j in jobs)
     total_bytes = sum(j["bytes"] for j in jobs)
     tables, chars, offsets, out, m = (jobs[0][k] for k in ("tables", "chars", "offsets", "out", "matcher"))
-    plan = m.plan()
-    stream = torch.cuda.current_stream().cuda_stream
+    stream = R.stream
+    step_device = R.step_device
 
-    class _AllMatchers:  # launch / overflow counters over every job's handle
-        def launch_count(self):
-            return sum(j["matcher"].launch_count() for j in jobs)
+    gathered = []
 
-        def overflow_count(self):
-            return sum(j["matcher"].overflow_count() for j in jobs)
-
-        def close(self):
-            for j in jobs:
-                j["matcher"].close()
-    M = _AllMatchers()
-
-    # one matcher (handle) per job; handles may run concurrently (include/rxm.h), so a step with
-    # several jobs puts each on its own stream, forked from and joined back into the timed stream
-    job_streams = [torch.cuda.Stream(device=dev) for _ in jobs] if len(jobs) > 1 else []
-    fork_ev = torch.cuda.Event()
-    join_evs = [torch.cuda.Event() for _ in job_streams]
-
-    def step_device():
-        if not job_streams:
-            j = jobs[0]
-            j["matcher"].match_ptrs(j["chars"].data_ptr(), j["offsets"].data_ptr(), j["n"],
-                                    j["out"].data_ptr(), stream)
-            return
-        cur = torch.cuda.current_stream()
-        fork_ev.record(cur)
-        for j, st, ev_j in zip(jobs, job_streams, join_evs):
-            st.wait_event(fork_ev)
-            j["matcher"].match_ptrs(j["chars"].data_ptr(), j["offsets"].data_ptr(), j["n"],
-                                    j["out"].data_ptr(), st.cuda_stream)
-            ev_j.record(st)
-        for ev_j in join_evs:
-            cur.wait_event(ev_j)
+    def step_sharded():
+        """strong scaling: the match on this rank's slice, then the gather of the result bits and the sum of
+        the match counts over NCCL (sharding.gather_bits / total_matches) -- the whole job's result on every rank"""
+        step_device()
+        gathered.clear()
+        for j, sh in zip(jobs, sharded):
+            gathered.append(S.gather_bits(j["out"], sh["bounds"], rank, world, dist, device=dev) if world > 1
+                            else j["out"])
+        tot = torch.stack([g.sum(dtype=torch.int64) for g in gathered]).sum()
+        return tot
 
     # ---- kernel-resident timing (inputs already in HBM) ---------------------------------
     for _ in range(args.warmup):
-        step_device()
+        step_sharded() if strong else step_device()
     barrier()
     props = torch.cuda.get_device_properties(local_rank)
     gpu_id = getattr(props, "uuid", None)
     gpu_id = f"GPU-{gpu_id}" if gpu_id and not str(gpu_id).startswith("GPU-") else (gpu_id or local_rank)
     sampler = ClockSampler(gpu_id)
-    launches0 = M.launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     # the timed region is padded so nvidia-smi (100 ms period) sees it
     t_pad = time.perf_counter()
     while time.perf_counter() - t_pad < 0.5:
         step_device()
         torch.cuda.synchronize()
-    launches0 = M.launch_count()
-    # inputs smaller than twice the 126 MB L2: write a 512 MB buffer between the timed steps (the
-    # flush is outside every per-step event pair); larger inputs evict themselves
-    flush = total_bytes < 2 * 126 * (1 << 20)
-    if flush:
-        flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-        ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-        for k in range(args.steps):
-            flush_buf.fill_(k & 0xff)
-            ev0[k].record()
-            step_device()
-            ev[k + 1].record()
+    launches0 = R.launch_count()
+    if strong:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            total_matches = step_sharded()
+        e1.record()
+        barrier()
+        total_ms = max_over_ranks(e0.elapsed_time(e1))
+        step_ms = [e0.elapsed_time(e1) / args.steps] * args.steps
+        flush = False
+        total_matches = int(total_matches.item())
     else:
-        ev[0].record()
-        for k in range(args.steps):
-            step_device()
-            ev[k + 1].record()
-    barrier()
-    launches = M.launch_count() - launches0
+        step_ms, local_total, flush = R.time_steps(args.steps, total_bytes, dev)
+        barrier()
+        total_ms = max_over_ranks(local_total)
+    launches = R.launch_count() - launches0
     while time.perf_counter() - t_pad < 1.2:
         step_device()
         torch.cuda.synchronize()
     clocks = sampler.stop()
-    if flush:
-        step_ms = [ev0[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
-        total_ms = max_over_ranks(sum(step_ms))
-        del flush_buf
-    else:
-        step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
-        total_ms = max_over_ranks(ev[0].elapsed_time(ev[args.steps]))
     ms_per_step = total_ms / args.steps
     n_all = sum_over_ranks(float(n))
     bytes_all = sum_over_ranks(float(total_bytes))
     value = n_all / (ms_per_step / 1e3)
-    if M.overflow_count():
+    if R.overflow_count():
         raise SystemExit("bench.py: strings hit a kernel limit")
 
     # ---- parity spot check against the oracle (outside every timed region) ---------------
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import helpers as H
-    k_chk = 0
-    for j in jobs:
-        kj = min(j["n"], 3000 if j["bytes"] / max(1, j["n"]) < 5000 else 64)
-        off_h = j["offsets"][:kj + 1].cpu().numpy().astype(np.uint64)
-        chars_h = j["chars"][:int(off_h[-1])].cpu().numpy()
-        want = H.oracle_bits(j["tables"], chars_h, off_h)
-        got = j["out"][:kj].cpu().numpy()
-        if not np.array_equal(got, want):
-            raise SystemExit(f"bench.py: {j['name']}: {int((got != want).sum())} of {kj} bits differ from the oracle")
-        k_chk += kj
+    k_chk = parity_spot_check(jobs, H)
     match_frac = float(sum(float(j["out"].float().sum().item()) for j in jobs) / max(1, n))
+    extra = {}
+    if strong:
+        # the gathered vector (every rank holds it) against this rank's own bits and, on rank 0, against the
+        # bits of the WHOLE batch matched on one GPU (what N = 1 gives)
+        ok = True
+        for j, sh, g in zip(jobs, sharded, gathered):
+            lo_, hi_ = sh["bounds"][rank], sh["bounds"][rank + 1]
+            ok = ok and bool(torch.equal(g[lo_:hi_], j["out"]))
+        whole_equal = None
+        if rank == 0 and world > 1:
+            whole_equal = True
+            for (name, rgx, fl, c_np, o_np), g in zip(whole, gathered):
+                mt = rxm.Matcher(rxm.Tables.load(os.path.join(CASES, name + ".rxt")), local_rank)
+                dc = torch.from_numpy(np.ascontiguousarray(c_np)).to(dev)
+                do = torch.from_numpy(o_np.astype(np.int64)).to(dev)
+                o1 = torch.empty(len(o_np) - 1, dtype=torch.uint8, device=dev)
+                mt.match_ptrs(dc.data_ptr(), do.data_ptr(), len(o_np) - 1, o1.data_ptr(), stream)
+                torch.cuda.synchronize()
+                whole_equal = whole_equal and bool(torch.equal(o1, g))
+                mt.close()
+                del dc, do, o1
+        if not ok or whole_equal is False:
+            raise SystemExit("bench.py: gathered result vector differs from the single-GPU bits")
+        extra["sharded"] = {
+            "note": "ONE batch cut by bytes over the ranks (sharding.shard_by_bytes); the timed step is the match of "
+                    "each rank's slice + all_gather of the result bits + sum of match counts over NCCL",
+            "strings_total": int(sum(sh["n"] for sh in sharded)), "total_matches": total_matches,
+            "bounds": {sh["name"]: [int(b) for b in sh["bounds"]] for sh in sharded} if world <= 8 else None,
+            "gathered_equals_local": ok, "gathered_equals_single_gpu": whole_equal,
+        }
 
     # ---- end to end through the C ABI with HOST buffers -----------------------------------
     for j in jobs:
         j["h_chars"] = torch.empty(j["bytes"], dtype=torch.uint8, pin_memory=True)
-        j["h_chars"].copy_(j["chars"])
+        j["h_chars"].copy_(j["chars"][:j["bytes"]])
         j["h_off"] = torch.empty(j["n"] + 1, dtype=torch.int64, pin_memory=True)
         j["h_off"].copy_(j["offsets"])
         j["h_out"] = torch.empty(j["n"], dtype=torch.uint8, pin_memory=True)
@@ -603,9 +800,40 @@ def main():
             raise SystemExit("bench.py: host-buffer path and device-pointer path disagree")
     e2e_value = n_all * e2e_steps / e2e_s
 
+    # ---- host -> device copies alone: each rank by itself, then all ranks at once ----
+    h2d = {}
+    if jobs and jobs[0]["bytes"] > (64 << 20):
+        hb, db = jobs[0]["h_chars"], jobs[0]["chars"][:jobs[0]["bytes"]]
+
+        def copy_ms(reps=3):
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                db.copy_(hb, non_blocking=True)
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+        copy_ms(1)
+        alone = []
+        for r in range(world):  # one rank at a time
+            barrier()
+            alone.append(copy_ms() if r == rank else 0.0)
+            barrier()
+        barrier()
+        together = copy_ms()
+        barrier()
+        gb = jobs[0]["bytes"] / 1e9
+        mine_alone = max(alone)
+        h2d = {"bytes": jobs[0]["bytes"],
+               "alone_gb_s": sum_over_ranks(gb / (mine_alone / 1e3)) / world,
+               "together_gb_s_per_gpu": sum_over_ranks(gb / (together / 1e3)) / world,
+               "together_gb_s_slowest_gpu": gb / (max_over_ranks(together) / 1e3),
+               "note": "pinned host buffer -> device, cudaMemcpyAsync of the whole chars array; alone = one rank "
+                       "copying while the others wait, together = all ranks at once (what the e2e step pays)"}
+
     # ---- uniform i.i.d. variant of config 2 (early exit) -----------------------------------
-    extra = {}
-    if wl == "config2":
+    if wl == "config2" and not strong:
         del jobs[0]["h_chars"]
         u_chars, u_off = make_workload(W, wl, tables.text, n, 2000 + rank, dev, uniform=True)
         for _ in range(3):
@@ -628,7 +856,7 @@ def main():
         del u_chars, u_off
 
     # ---- raw-text route (config 2): tokenise on the device, then match ------------------------
-    if wl == "config2":
+    if wl == "config2" and not strong:
         nt = min(n, 250_000)
         t_off = jobs[0]["offsets"][:nt + 1]
         t_bytes = int(t_off[-1])
@@ -678,13 +906,16 @@ def main():
         }
         del text, h_text
 
+    engines = "+".join(sorted({rxm.ENGINE_NAMES.get(j["matcher"].plan().engine, "?") for j in jobs}))
+    dfa_stride = int(jobs[0]["matcher"].plan().dfa_stride)
+    n_jobs, n_streams = len(jobs), max(1, len(R.job_streams))
+
+    def device_bits(chars_np, offsets_np):  # the device's answer for the CPU baseline's sample (same handle)
+        return m.match_host(chars_np, offsets_np)
+
+    line = None
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak = float(json.load(open(peaks_path))["hbm_gbs"])
-            peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
-        else:
-            peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+        peak, peak_src = hbm_peak()
         algo_bytes = total_bytes + 9 * n  # per launch on this rank: len + 8 B offset + 1 B result
         k_ms = statistics.mean(step_ms)
         achieved = algo_bytes / (k_ms / 1e3) / 1e9
@@ -695,18 +926,18 @@ def main():
         line = {
             "metric": "strings_per_sec", "value": value, "unit": "strings/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": desc, "strings_per_gpu": n, "bytes_per_gpu": total_bytes,
-                       "mean_len": total_bytes / n, "match_fraction": match_frac,
-                       "engine": "+".join(sorted({rxm.ENGINE_NAMES.get(j["matcher"].plan().engine, "?") for j in jobs})),
-                       "dfa_stride": int(jobs[0]["matcher"].plan().dfa_stride),
-                       "jobs_per_step": len(jobs),
-                       "handles_sharing_device": share, "job_streams": max(1, len(job_streams)),
-                       "numa_node": numa_node,
+                       "mean_len": total_bytes / max(1, n), "match_fraction": match_frac,
+                       "engine": engines, "dfa_stride": dfa_stride, "jobs_per_step": n_jobs,
+                       "handles_sharing_device": share, "job_streams": n_streams,
+                       "numa": numa,
                        "l2": ("L2 flushed between timed steps (512 MB written; inputs are %.2f GB per GPU)" if flush else
                               "inputs (%.2f GB per GPU) are larger than the 126 MB L2") % (total_bytes / 1e9),
-                       "sharding": "by string index, one rank per GPU, no data-path collective"},
+                       "sharding": ("ONE batch of %d strings cut by bytes over the ranks, result bits gathered over NCCL"
+                                    % args.strings) if strong else
+                                   "by string index, one rank per GPU, no data-path collective"},
             "input_gb_s": bytes_all / (ms_per_step / 1e3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -714,9 +945,9 @@ def main():
                          "algorithmic_bytes_per_launch": algo_bytes,
                          "frac_of_nominal_8_tb_s": achieved / 8000.0},  # both denominators
             "e2e": {"value": e2e_value, "unit": "strings/s",
-                    "h2d_bytes_per_step": total_bytes + 8 * (n + len(jobs)), "d2h_bytes_per_step": n + 8 * len(jobs),
+                    "h2d_bytes_per_step": total_bytes + 8 * (n + n_jobs), "d2h_bytes_per_step": n + 8 * n_jobs,
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-                    "input_gb_s": bytes_all * e2e_steps / e2e_s / 1e9},
+                    "input_gb_s": bytes_all * e2e_steps / e2e_s / 1e9, "h2d_copy_alone_vs_together": h2d},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "parity_checked": k_chk,
@@ -726,11 +957,22 @@ def main():
             os.sched_setaffinity(0, ORIG_AFFINITY)  # the CPU baseline uses every host core
         if world == 1 and not args.no_cpu_baseline:
             if wl in ("config2", "config3"):
-                line["cpu_baseline"] = cpu_baseline(W, rxm, wl, tables, regex, flags)
+                line["cpu_baseline"] = cpu_baseline(W, rxm, wl, tables, regex, flags, device_bits)
             else:
                 line["cpu_baseline"] = cpu_baseline_jobs(jobs, wl)
+    R.close()
+    for j in jobs:
+        j.clear()
+    del jobs, chars, offsets, out
+    torch.cuda.empty_cache()
+    if rank == 0:
+        # ---- the other BASELINE configs, briefly, in the default run (config 2 stays the headline) ----
+        if world == 1 and wl == "config2" and not strong and not args.no_extra_workloads:
+            wk = {}
+            for xwl, xs, xn in (("config3", 3, 1_000_000), ("config4", 2, 4096), ("config5", 3, 1_000_000)):
+                wk[xwl] = extra_workload(W, rxm, H, xwl, xn, xs, dev, local_rank, 1000)
+            line["workloads"] = wk
         print(json.dumps(line), file=RESULT_OUT, flush=True)
-    M.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

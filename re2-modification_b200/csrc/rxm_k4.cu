@@ -53,6 +53,7 @@ k4_mfa_thread_kernel(MfaView v, K4Prog gp, uint32_t n_items, uint32_t n_keys, ui
     K4Sim<NC, K4_THREADS> sim;
     sim.base = reinterpret_cast<uint32_t *>(smem + o) + threadIdx.x;
     sim.pool = maxl;
+    sim.use_map = v.n_states <= K4_MAP_STATES && maxl <= 15u;
     sim.want = K4_WANT_NONE;
 
     // tickets: with the tile sort's records, ticket t is record (t mod 32) of group g of tile tl, group g

@@ -30,6 +30,10 @@
 
 #include "rxm_mfa_core.cuh"
 
+#ifndef K4_STAT
+#define K4_STAT(x)  // host statistics (tools), compiled out
+#endif
+
 namespace rxm {
 
 struct K4Prog {  // the edge programs and the per-key item lists (MfaProgram)
@@ -48,7 +52,8 @@ constexpr uint32_t K4_POOL_MAX = 32;  // slots a thread can have at most (the se
 
 // slots for an automaton of n_states nodes: 8 hold the current set and the one being built for every forward
 // automaton of the reference's examples; the reversed ones keep more configurations waiting
-RXM_HD constexpr uint32_t k4_pool_for(uint32_t n_states) { return n_states < 8u ? 8u : (n_states > 16u ? 16u : n_states); }
+RXM_HD constexpr uint32_t k4_pool_for(uint32_t n_states) { return n_states < 8u ? 8u : (n_states > 15u ? 15u : n_states); }
+constexpr uint32_t K4_MAP_STATES = 16;  // up to this many nodes the new set's slot of a node is kept in a 64-bit map (4 bits each)
 constexpr uint32_t K4_MAX_STATES = 40;  // larger automata go to K3 (one warp per string) as a whole
 RXM_HD constexpr uint32_t k4_slot_words(uint32_t nc) { return 3u + 2u * nc; }
 RXM_HD constexpr uint32_t k4_words(uint32_t nc, uint32_t pool) { return pool * k4_slot_words(nc) + 2u * K4_LOGN; }
@@ -83,6 +88,16 @@ RXM_HD uint64_t k4_ld64(const uint8_t *p) {  // p is 8-byte aligned
 #endif
 }
 
+// L2 prefetch of the line at p (if it still holds a byte of the string): the thread's stream is read ahead of its compares
+RXM_HD void k4_prefetch_l2(const uint8_t *p, const uint8_t *end) {
+#if defined(__CUDA_ARCH__)
+    if (p < end) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+    (void)end;
+#endif
+}
+
 // a[0, L) == b[0, L) ?  Only aligned 8-byte words that hold at least one byte of a span are read.
 RXM_HD bool k4_span_equal(const uint8_t *a, const uint8_t *b, uint32_t L) {
     if (a == b || L == 0) return true;
@@ -112,6 +127,14 @@ RXM_HD bool k4_span_equal(const uint8_t *a, const uint8_t *b, uint32_t L) {
 }
 
 template <int NC>
+RXM_HD uint32_t k4_open_mask(uint32_t flags) {  // bit k <- cell k exists and is open
+    uint32_t m = 0;
+RXM_UNROLL
+    for (int k = 0; k < NC; k++) m |= (((flags >> (3 * k)) & 3u) == 3u ? 1u : 0u) << k;
+    return m;
+}
+
+template <int NC>
 RXM_HD uint32_t k4_exists_mask(uint32_t flags) {  // bit k <- flags bit 3k, k < NC
     uint32_t m = 0;
 RXM_UNROLL
@@ -129,6 +152,7 @@ struct K4Sim {
 
     uint32_t *base;  // word 0 of this thread
     uint32_t pool;   // slots in the pool (<= K4_POOL_MAX); the compare log follows them
+    bool use_map;    // the automaton has <= K4_MAP_STATES nodes and the pool <= 15 slots
     // the string in hand
     const uint8_t *s;
     uint32_t n, reversed;
@@ -141,7 +165,10 @@ struct K4Sim {
     int result;
     // repeated steps
     uint32_t rp_delta;    // != 0: repeated steps of this distance are being answered
-    uint32_t rp_lmax;     // the longest block the repeated step compares (>= 1: its letter)
+    uint32_t rp_lmax;     // the longest block the repeated step must see again (>= 1: its letter)
+    uint32_t log_open;    // bit e: log entry e is a block of a cell that is still OPEN
+    uint32_t unsafe;      // bit j: the new set's configuration in slot j does not move on with the step (see phase_a)
+    uint64_t nmap;        // (automata of <= K4_MAP_STATES nodes) 4 bits per node: slot + 1 of the new set's configuration on it
     uint32_t rp_vp;       // verified front: s[j] == s[j - rp_delta] for every j from the first repeated step up to here
     uint32_t rp_vcap;     // the front need not pass this: the last step that may be answered looks up to here
     uint32_t rp_acc;      // distance moved on so far, not yet written to the slots
@@ -187,15 +214,22 @@ RXM_UNROLL
     // set order of mfa.cpp:206 for two configurations on one node: (first, lowest cell name, creation)
     RXM_HD static bool key_less(uint32_t fa, uint32_t fla, uint32_t ba, uint32_t fb, uint32_t flb, uint32_t bb) {
         if (fa != fb) return fa < fb;
-        const uint32_t la = lowvar(fla), lb = lowvar(flb);
+        // lowest cell name present: the lowest `exists` bit (flag bit 3k for cell k); no bit = empty memory, smallest
+        const uint32_t ea = fla & 0x1249249u, eb = flb & 0x1249249u;
+        const uint32_t la = ea & (0u - ea), lb = eb & (0u - eb);
         if (la != lb) return la < lb;
         return la != 0 && ba < bb;  // both memories empty: equal keys, the one already there stays
     }
 
     // the new set's slot on `node`, or K4_POOL_MAX
     RXM_HD uint32_t find_new(uint32_t node) const {
+        if (use_map) {
+            const uint32_t e = uint32_t(nmap >> (4u * node)) & 15u;
+            return e ? e - 1u : K4_POOL_MAX;
+        }
         for (uint32_t m = nxt; m; m &= m - 1u) {
             const uint32_t j = uint32_t(k4_ffs(m)) - 1u;
+            K4_STAT(g_find++);
             if ((slotp(j)[STRIDE] & 0xffffu) == node) return j;
         }
         return K4_POOL_MAX;
@@ -210,7 +244,9 @@ RXM_UNROLL
     }
 
     // new_states.insert, reduced on the fly to the set-minimum per node (mfa.cpp:206-211)
-    RXM_HD void insert(const cfg_t &c) {
+    // (bad: the candidate is not the previous step's candidate moved on -- see phase_a; it may lose here, not stand)
+    RXM_HD void insert(const cfg_t &c, bool bad) {
+        K4_STAT(g_ins++);
         if (c.first < i + 2u) near = true;  // its node will hold a configuration with first <= i + 1
         uint32_t j = find_new(c.node);
         if (j != K4_POOL_MAX) {
@@ -218,6 +254,7 @@ RXM_UNROLL
             if (!key_less(c.first, c.flags, c.born, sp[0], sp[STRIDE] >> 16, sp[2 * STRIDE])) return;
             if (!((cur >> j) & 1u)) {  // not shared with the current set: overwritten in place
                 store(j, c);
+                unsafe = (unsafe & ~(1u << j)) | (bad ? 1u << j : 0u);
                 return;
             }
             nxt &= ~(1u << j);
@@ -226,10 +263,13 @@ RXM_UNROLL
         if (j == K4_POOL_MAX) return;
         store(j, c);
         nxt |= 1u << j;
+        unsafe = (unsafe & ~(1u << j)) | (bad ? 1u << j : 0u);
+        if (use_map) nmap = (nmap & ~(15ull << (4u * c.node))) | (uint64_t(j + 1u) << (4u * c.node));
     }
     // the re-insertion of the configuration in slot js itself (mfa.cpp:195-197 / 138-140 on the root call):
     // older than anything created in this step (stamp 0); its slot joins the new set, nothing is copied
     RXM_HD void reinsert(uint32_t js, const cfg_t &root) {
+        K4_STAT(g_reins++);
         if (root.first < i + 2u) near = true;
         const uint32_t j = find_new(root.node);
         if (j != K4_POOL_MAX) {
@@ -239,6 +279,8 @@ RXM_UNROLL
         }
         slotp(js)[2 * STRIDE] = 0u;
         nxt |= 1u << js;
+        unsafe &= ~(1u << js);
+        if (use_map) nmap = (nmap & ~(15ull << (4u * root.node))) | (uint64_t(js + 1u) << (4u * root.node));
     }
 
     RXM_HD static uint32_t need_of(uint32_t flags, const uint32_t *len) {  // is_siffix_long_enough, mfa.cpp:116-133
@@ -252,15 +294,20 @@ RXM_UNROLL
     }
 
     // one block compare of the step at i; a span already compared in this step is answered from the log
-    RXM_HD bool compare_logged(uint32_t vs, uint32_t L) {
+    // (open: the cell is still open -- its text, and with it this block, grows with every step)
+    RXM_HD bool compare_logged(uint32_t vs, uint32_t L, bool open) {
         uint32_t *lg = logp();
         for (uint32_t e = 0; e < n_log; e++)
-            if (lg[(2 * e) * STRIDE] == vs && (lg[(2 * e + 1) * STRIDE] & 0x7fffffffu) == L)
+            if (lg[(2 * e) * STRIDE] == vs && (lg[(2 * e + 1) * STRIDE] & 0x7fffffffu) == L) {
+                if ((((log_open >> e) & 1u) != 0u) != open) log_bad = true;  // one span, two cells that part ways
                 return (lg[(2 * e + 1) * STRIDE] >> 31) != 0u;
+            }
+        K4_STAT(g_cmp++; g_cmpbytes += L);
         const bool eq = span_equal(vs, i, L);
         if (n_log < K4_LOGN) {
             lg[(2 * n_log) * STRIDE] = vs;
             lg[(2 * n_log + 1) * STRIDE] = L | (eq ? 0x80000000u : 0u);
+            if (open) log_open |= 1u << n_log;
             n_log++;
         } else {
             log_bad = true;
@@ -310,7 +357,8 @@ RXM_UNROLL
         prev_i = 0;
         want = K4_WANT_NONE;
         result = 0;
-        rp_delta = rp_lmax = rp_vp = rp_vcap = rp_acc = 0;
+        rp_delta = rp_lmax = rp_vp = rp_vcap = rp_acc = log_open = unsafe = 0;
+        nmap = 0;
         rp_magic = 0;
         rp_mism = false;
         have_prev = log_bad = overflow = near = false;
@@ -342,7 +390,11 @@ RXM_UNROLL
             const uint32_t *lg = logp();
             uint32_t lmax = 1;  // the letter at i
             for (uint32_t e = 0; e < n_log; e++) {
-                const uint32_t L = lg[(2 * e + 1) * STRIDE] & 0x7fffffffu;
+                const uint32_t lw = lg[(2 * e + 1) * STRIDE];
+                // a block of an OPEN cell that matched made a candidate that lost (phase_b): whether it matches again
+                // does not matter.  Every other block must be seen again as it was.
+                if (((log_open >> e) & 1u) && (lw >> 31)) continue;
+                const uint32_t L = lw & 0x7fffffffu;
                 lmax = L > lmax ? L : lmax;
             }
             uint32_t maxf = 0;
@@ -350,8 +402,8 @@ RXM_UNROLL
                 const uint32_t f = slotp(uint32_t(k4_ffs(m)) - 1u)[0];
                 maxf = f > maxf ? f : maxf;
             }
-            // ProgSim::replay answers the step at p only if p + delta + 2 < n and no `first` (moved on to p) reaches
-            // n - delta: everything the step and the jump after it ask about the end of the string stays as it was
+            // the step at p is only answered if p + delta + 2 < n and no `first` (moved on to p) reaches n - delta:
+            // everything the step and the jump after it ask about the end of the string stays as it was
             uint32_t d = maxf > i ? maxf - i : 0u;
             d = d < 2u ? 2u : d;
             if (uint64_t(i) + delta + d < n) {
@@ -370,40 +422,64 @@ RXM_UNROLL
     }
 
     // ---- PHASE A: repeated steps ------------------------------------------------------------------
-    // The step at i repeats the previous one -- same letter, same outcomes of the same block compares --
-    // if the input it looks at equals the input the previous step looked at:
-    //     s[j] == s[j - delta]   for j in [i, i + lmax),   lmax = the longest block the step compared (>= 1)
-    // (a sufficient condition for ProgSim::replay's "same outcomes").  Its result is then the previous result
-    // moved on, and so on for the steps after it.  One iteration of the FLAT loop verifies one aligned word
-    // ahead of the front rp_vp and then answers every step the front has passed -- the same instructions
-    // for every lane whatever its distance, block length and position.
+    // sigma(c) = configuration c moved on by delta: first + delta, every OPEN cell longer by delta (an open cell
+    // ends where its configuration reads: start + len == first), closed cells as they are.  Let the step at
+    // p = i - delta have turned the set Q into the set P in hand, and P == sigma(Q) (moved_on).  The step at i
+    // then walks the same programs from sources with the same flags; if the letter is the same and every block
+    // compare comes out as before, the same items fire, and a candidate is sigma of the previous step's
+    // candidate -- first + 1 or + L, open cells appended to, closed cells untouched -- UNLESS its item
+    //   * opens a cell (open action, or a cell created open on the way down: anchored at i, not at i - delta),
+    //   * closes a cell that is open (what it freezes is delta longer than before), or
+    //   * reads a cell that is still open (the block, hence the candidate's first, is delta longer).
+    // Such a candidate's key never moves by less than delta, so where it LOST the per-node minimum to a
+    // candidate that does move on it loses again; phase_b refuses the repetition only if one of them STANDS in
+    // the result.  Then step(sigma(Q)) == sigma(step(Q)), and by induction for every following step, as long as
+    //     s[j] == s[j - delta]   for j in [i, i + lmax),   lmax = the longest block to be seen again (>= 1: the letter)
+    // -- equal windows give equal outcomes for blocks of closed cells, and a block of an open cell that did
+    // NOT match keeps its differing letter (one that matched made a losing candidate: it does not matter).
+    // (This is ProgSim::replay with its conditions made sufficient: the host study of round 1 refused every
+    // step that reads an open cell -- the reference's examples 1, 3, 4 and 8 never repeated -- and did not look
+    // at open / close actions.)  One iteration of the FLAT loop verifies aligned words ahead of the front rp_vp
+    // and then answers every step the front has passed -- the same instructions for every lane whatever its
+    // distance, block length and position.
     RXM_HD void phase_a() {
         const uint32_t delta = rp_delta;
         for (uint32_t r = 0; r < K4_BURST; r++) {
             const bool can = !rp_mism && rp_vp < rp_vcap;
-            if (can) {  // one aligned word of the input against the input delta bytes before it
-                const uint8_t *b = s + rp_vp;
+            if (can) {
+                // four aligned words of the input from the front on against the input delta bytes before them; the
+                // nine loads are issued together (one memory round trip per 32 bytes), and only words that hold a
+                // byte of the string are read
+                const uint8_t *b = s + rp_vp, *end = s + n;
                 const uint32_t ob = uint32_t(reinterpret_cast<uintptr_t>(b) & 7u);
                 const uint8_t *b0 = b - ob;
-                const uint8_t *unit_end = (b0 + 8 < s + n) ? b0 + 8 : s + n;
                 const uint8_t *ap = b0 - delta;
                 const uint32_t oa = uint32_t(reinterpret_cast<uintptr_t>(ap) & 7u);
                 const uint8_t *a0 = ap - oa;
                 const uint32_t sh = oa * 8u;
-                // only words that hold a byte of [b - delta, unit_end - delta) are read
-                const uint64_t lo = (a0 + 8 > b - delta) ? k4_ld64(a0) : 0ull;
-                const uint64_t hi = (sh != 0u && a0 + 8 < unit_end - delta) ? k4_ld64(a0 + 8) : 0ull;
-                const uint64_t wa = sh ? ((lo >> sh) | (hi << (64u - sh))) : lo;
-                uint64_t x = wa ^ k4_ld64(b0);
-                x &= ~0ull << (8u * ob);
-                const uint32_t rem = uint32_t(unit_end - b0);
-                if (rem < 8u) x &= (1ull << (8u * rem)) - 1ull;
-                if (x) {
-                    rp_vp = uint32_t(b0 - s) + (uint32_t(k4_ffs64(x)) - 1u) / 8u;
-                    rp_mism = true;
-                } else {
-                    rp_vp = uint32_t(unit_end - s);
+                uint64_t w[4], a[5];
+RXM_UNROLL
+                for (int u = 0; u < 4; u++) w[u] = (b0 + 8 * u < end) ? k4_ld64(b0 + 8 * u) : 0ull;
+RXM_UNROLL
+                for (int u = 0; u < 5; u++)  // word u of the past: read iff it holds a byte of [b - delta, end - delta)
+                    a[u] = (a0 + 8 * u + 8 > b - delta && a0 + 8 * u < end - delta) ? k4_ld64(a0 + 8 * u) : 0ull;
+                k4_prefetch_l2(b0 + 512, end);
+                uint32_t nvp = uint32_t((b0 + 32 < end ? b0 + 32 : end) - s);
+                bool mism = false;
+RXM_UNROLL
+                for (int u = 3; u >= 0; u--) {  // the FIRST word that differs decides: walk backwards, keep the earliest
+                    uint64_t x = (sh ? ((a[u] >> sh) | (a[u + 1] << (64u - sh))) : a[u]) ^ w[u];
+                    if (u == 0) x &= ~0ull << (8u * ob);
+                    const uint8_t *ub = b0 + 8 * u;
+                    if (ub >= end) x = 0;
+                    else if (ub + 8 > end) x &= (1ull << (8u * uint32_t(end - ub))) - 1ull;
+                    if (x) {
+                        nvp = uint32_t(ub - s) + (uint32_t(k4_ffs64(x)) - 1u) / 8u;
+                        mism = true;
+                    }
                 }
+                rp_vp = nvp;
+                rp_mism = mism;
             }
             const uint32_t front = rp_vp < rp_vcap ? rp_vp : rp_vcap;
             const uint32_t target = i + rp_lmax;
@@ -446,10 +522,13 @@ RXM_UNROLL
     // Ends with want = K4_DONE (result = 0 / 1, or 2 if a limit was met -- never a guess) or K4_WANT_NONE.
     RXM_HD void phase_b(const MfaView &t, const K4Prog &p) {
         n_log = 0;
+        log_open = 0;
+        unsafe = 0;
         log_bad = false;
         near = false;
         prv = 0u;  // the set before this one is not needed any more
         nxt = 0u;
+        nmap = 0;
         {
             const uint32_t ch = (i < n) ? at(i) : 0u;
             const uint32_t digit_bit = (ch >= '1' && ch <= '9') ? (1u << (ch - '1')) : 0u;
@@ -466,6 +545,7 @@ RXM_UNROLL
                     fin = (root.first == n);
                     active = (i != n && i == root.first);
                     waiting = (i != n && i < root.first);
+                    K4_STAT(g_src++; g_active += active; g_waiting += (waiting || fin) && !active);
                     if (!(active || waiting || fin)) continue;  // behind the step: no branch of mfa.cpp:161-197 fires
                     if (!(root.node == t.finish && fin) && t.reversed && need_of(root.flags, root.len) > n - i) continue;  // :141
                     const uint32_t key = (root.node << p.n_cells) | k4_exists_mask<NC>(root.flags);
@@ -481,11 +561,12 @@ RXM_UNROLL
                 }
                 const uint32_t x = p.sel[lbase + q];
                 q++;
+                K4_STAT(g_items++);
                 const ProgItem it = p.items[pb + x];
                 if (active) {
                     const uint32_t kind = pi_kind(it), rc = pi_read_cell(it);
                     uint32_t L = 1;
-                    bool fire = false;
+                    bool fire = false, grows = false;
                     if (kind == kEdgeAny || (kind == kEdgeLit && pi_sym(it) == ch)) {  // :171-175
                         fire = true;
                     } else if (rc) {  // :176-193, the cell is present
@@ -500,17 +581,21 @@ RXM_UNROLL
                                 vs = root.start[kk];
                                 fl = (root.flags >> (3 * kk)) & 7u;
                             }
-                        if (!fresh && (fl & 2u)) log_bad = true;  // the text of an open cell changes from step to step
-                        if (n - i >= L) fire = (L == 0) || compare_logged(vs, L);
+                        grows = !fresh && (fl & 2u);  // the text of an open cell grows from step to step
+                        if (n - i >= L) fire = (L == 0) || compare_logged(vs, L, grows);
                     }
                     if (fire) {
+                        K4_STAT(g_fire++);
+                        // does the candidate move on with the step?  (see phase_a)
+                        const bool bad = grows || (pi_open(it) | pi_created_open(it)) != 0u ||
+                                         (pi_close(it) & k4_open_mask<NC>(root.flags)) != 0u;
                         cfg_t nx;
                         prog_working<NC>(nx, root, pi_created(it), pi_created_open(it), pi_prior_reads(it) & ~digit_bit);
                         nx.node = pi_node(it);
                         nx.born = prog_stamp(false, root.node, x);
                         nx.first += L;
                         apply_actions<NC>(nx, pi_open(it), pi_close(it), i, L);
-                        insert(nx);
+                        insert(nx, bad);
                     }
                 } else {
                     if (fin && pi_skip_final(it)) continue;  // below a call that returned at mfa.cpp:138-140
@@ -523,7 +608,7 @@ RXM_UNROLL
                             prog_working<NC>(w, root, pi_created(it), pi_created_open(it), 0u);
                             w.node = v;
                             w.born = prog_stamp(true, root.node, x);
-                            insert(w);
+                            insert(w, pi_created_open(it) != 0u);
                         }
                     }
                 }
@@ -533,6 +618,7 @@ RXM_UNROLL
         have_prev = true;
         prev_i = i;
         want = K4_WANT_NONE;
+        if (nxt & unsafe) log_bad = true;  // a configuration that does not move on with the step stands in the result
         if (overflow) {
             result = 2;
             want = K4_DONE;

@@ -184,6 +184,7 @@ static void run_k4_batch(const rxm::MfaView &v, const rxm::K4Prog &kp, uint32_t 
     rxm::K4Sim<NC, 1> sim;
     sim.base = words.data();
     sim.pool = maxl;
+    sim.use_map = v.n_states <= rxm::K4_MAP_STATES && maxl <= 15u;
     for (uint64_t i = 0; i < n; i++) {
         const int r = sim.run(v, kp, chars + off[i], uint32_t(off[i + 1] - off[i]));
         out[i] = uint8_t(r);

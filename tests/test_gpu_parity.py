@@ -680,7 +680,8 @@ def test_k4_hands_outgrown_strings_to_k3_on_the_device(name):
     extra = [bytes(rng.choice(np.frombuffer(b"aaabbc", dtype=np.uint8), size=int(L))) for L in rng.integers(0, 120, size=20000)]
     chars, off = H.make_batch(strings + extra)
     m = rxm.Matcher(t, 0)
-    assert rxm.ENGINE_NAMES[m.plan().engine] == "K4_THREAD"
+    # (the planner sends automata above 40 nodes -- example 8 reversed has 77 -- to K3 as a whole)
+    assert rxm.ENGINE_NAMES[m.plan().engine] == ("K3_WARP" if t.c.n_states > 40 else "K4_THREAD")
     got = m.match_host(chars, off)
     assert m.overflow_count() == 0
     assert np.array_equal(got[:len(bits)], bits)
