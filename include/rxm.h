@@ -107,7 +107,7 @@ enum {
     RXM_ENGINE_K1_DFA = 1,     /* memory-free automaton, determinised with the reference's exact step */
     RXM_ENGINE_K1_BITSET = 2,  /* memory-free automaton too large to determinise: the active set
                                   itself on the device (follow masks, or an edge walk)             */
-    RXM_ENGINE_K2_THREAD = 3,  /* MFA, one thread per string                                        */
+    RXM_ENGINE_K2_THREAD = 3,  /* MFA, one thread per string, recursive walk (automata with more than 4 cells) */
     RXM_ENGINE_K3_WARP = 4,    /* MFA, one warp per string (large automata; takes over the strings that
                                   outgrow K4's per-thread sets)                                     */
     RXM_ENGINE_K4_THREAD = 5   /* MFA, one thread per string over host-compiled edge programs, repeated
@@ -134,6 +134,23 @@ typedef struct rxm_plan_info {
 
 /* Copies `host_tables` (caller keeps ownership), plans, uploads to `device`. */
 int rxm_tables_upload(const rxm_tables *host_tables, int device, rxm_handle *out);
+
+/*
+ * The same with the planner's choices overridden -- for tests and for comparing the engines; no reference
+ * counterpart (the reference has one matcher per automaton kind).  `opts` may be NULL (= rxm_tables_upload).
+ * An engine that cannot run the automaton is RXM_ERR_UNSUPPORTED, never a silent substitute.
+ */
+#define RXM_OPT_K1_NO_QUAD 1u   /* K1: one input byte per table lookup even where four would do          */
+#define RXM_OPT_K1B_WALK 2u     /* K1 bit-set engine: the edge-walking step instead of the follow masks   */
+#define RXM_OPT_INDEX_ORDER 4u  /* hand strings out by index, not in the tile sort's order                */
+typedef struct rxm_upload_opts {
+    uint32_t abi_version;  /* RXM_ABI_VERSION                                                             */
+    uint32_t engine;       /* 0: the planner's choice; RXM_ENGINE_*: that engine                          */
+    uint32_t flags;        /* RXM_OPT_*                                                                   */
+    uint32_t k3_tile;      /* 0: the planner's choice; 8 / 16 / 32 lanes per string for K3                */
+    uint32_t reserved[4];
+} rxm_upload_opts;
+int rxm_tables_upload_opts(const rxm_tables *host_tables, int device, const rxm_upload_opts *opts, rxm_handle *out);
 int rxm_plan_query(rxm_handle h, rxm_plan_info *info);
 int rxm_free(rxm_handle h);
 
@@ -144,9 +161,22 @@ int rxm_free(rxm_handle h);
  * (on the handle's device) or a host pointer (pageable or pinned); host
  * buffers are staged through the handle's device workspace inside the call.
  * `stream` is a cudaStream_t (NULL = default stream).  With device pointers the
- * call is asynchronous on `stream`; with any host pointer it returns after the
- * results are in `out_bits`.  Calls on one handle must be serialised by the
- * caller; different handles may be used concurrently.
+ * call is asynchronous on `stream` -- nothing is read back, every choice that
+ * depends on the batch (string order, lanes per string) is made on the device;
+ * with any host pointer it returns after the results are in `out_bits`.  Calls on
+ * one handle must be serialised by the caller; different handles may be used
+ * concurrently.  Workspace the handle owns (per-string records, lists) grows on
+ * demand inside the call (cudaMalloc when a batch is larger than any before).
+ *
+ * Device buffers -- readable slack.  The kernels read whole ALIGNED words around a
+ * string's bytes: the 32-byte-aligned blocks that hold its first and last byte
+ * (K1, tokeniser) or the 8-byte ones (K3, K4).  So the device memory from
+ * (chars + offsets[0]) rounded DOWN to 32 bytes up to (chars + offsets[n])
+ * rounded UP to 32 bytes must be readable.  Any cudaMalloc'ed / pool-allocated
+ * buffer satisfies this when `chars` is its start or 32-byte aligned inside it
+ * (allocations are 256-byte granular); a sub-buffer that starts at an odd offset
+ * must have its neighbours inside the same allocation.  Bytes outside the strings
+ * never influence a result.
  */
 int rxm_match_batch(rxm_handle h, const uint8_t *chars, const uint64_t *offsets, uint64_t n,
                     uint8_t *out_bits, void *stream);

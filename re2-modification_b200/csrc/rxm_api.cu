@@ -77,7 +77,9 @@ struct rxm_matcher {
     uint32_t *d_redo_list = nullptr;
     size_t cap_redo = 0;
     unsigned long long *d_redo_n = nullptr;
+    uint32_t *d_pick = nullptr;  // [0] 1: the batch in hand is one of long strings (decided on the device)
     uint32_t sharing = 1;  // rxm_set_concurrency: handles that run at once on this device
+    bool index_order = false;  // RXM_OPT_INDEX_ORDER
 
     // staging workspace for host buffers
     uint8_t *d_chars = nullptr;
@@ -116,8 +118,20 @@ static bool is_device_ptr(const void *p) {
 extern "C" const char *rxm_last_cuda_error(void) { return g_cuda_err; }
 
 extern "C" int rxm_tables_upload(const rxm_tables *host_tables, int device, rxm_handle *out) {
+    return rxm_tables_upload_opts(host_tables, device, nullptr, out);
+}
+
+extern "C" int rxm_tables_upload_opts(const rxm_tables *host_tables, int device, const rxm_upload_opts *opts,
+                                      rxm_handle *out) {
     if (!out) return RXM_ERR_INVALID;
     *out = nullptr;
+    rxm_upload_opts o{};
+    if (opts) {
+        if (opts->abi_version != RXM_ABI_VERSION) return RXM_ERR_INVALID;
+        o = *opts;
+        if (o.engine > RXM_ENGINE_K4_THREAD || (o.k3_tile != 0 && o.k3_tile != 8 && o.k3_tile != 16 && o.k3_tile != 32))
+            return RXM_ERR_INVALID;
+    }
     int st = rxm_tables_validate(host_tables);
     if (st != RXM_OK) return st;
     int ndev = 0;
@@ -151,11 +165,19 @@ extern "C" int rxm_tables_upload(const rxm_tables *host_tables, int device, rxm_
         return code;
     };
 
+    m->index_order = (o.flags & RXM_OPT_INDEX_ORDER) != 0;
+    if (o.engine != 0 &&
+        (t.kind == RXM_KIND_NFA) != (o.engine == RXM_ENGINE_K1_DFA || o.engine == RXM_ENGINE_K1_BITSET)) {
+        err = "the requested engine does not run this kind of automaton";
+        return fail(RXM_ERR_UNSUPPORTED);
+    }
     if (t.kind == RXM_KIND_NFA) {
-        const char *nfa_force = getenv("RXM_NFA_ENGINE");  // "bitset": tuning and tests
-        const bool force_bitset = nfa_force && std::strcmp(nfa_force, "bitset") == 0;
+        const bool force_bitset = o.engine == RXM_ENGINE_K1_BITSET;
+        std::vector<uint8_t> table, accept;
         st = force_bitset ? RXM_ERR_UNSUPPORTED : rxm::plan_dfa(t, m->dfa, &err);
-        if (st == RXM_ERR_UNSUPPORTED) {
+        // (a determinisation whose tables do not fit shared memory goes to the bit-set engine as well)
+        if (st == RXM_OK) st = rxm::k1_build_tables(m->dfa, m->k1, table, accept, &err, (o.flags & RXM_OPT_K1_NO_QUAD) != 0);
+        if (st == RXM_ERR_UNSUPPORTED && o.engine != RXM_ENGINE_K1_DFA) {
             // too many active sets for a table (or forced): simulate the set itself (K1B)
             std::string berr;
             if (rxm::check_nfa_bitset(t, &berr) != RXM_OK) {
@@ -169,9 +191,10 @@ extern "C" int rxm_tables_upload(const rxm_tables *host_tables, int device, rxm_
             rxm::k1b_build_tables(t, eb, ed);
             if ((st = upload_vec(eb, &m->d_edge_begin)) != RXM_OK) return fail(st);
             if ((st = upload_vec(ed, &m->d_k1b_edges)) != RXM_OK) return fail(st);
-            const char *walk = getenv("RXM_K1B_WALK");  // "1": force the edge-walking step (tests)
             rxm::plan_bitset_masks(t, m->bmasks);
-            if (walk && walk[0] == '1') m->bmasks.ok = false;
+            if (o.flags & RXM_OPT_K1B_WALK) m->bmasks.ok = false;  // the edge-walking step
+            if (m->bmasks.ok && size_t(m->bmasks.n_classes) * t.n_states * 16 + 256 > 96 * 1024)
+                m->bmasks.ok = false;  // the follow masks would not fit shared memory: decided here, not per batch
             if (m->bmasks.ok) {
                 std::vector<uint8_t> cls(m->bmasks.byte_class, m->bmasks.byte_class + 256);
                 if ((st = upload_vec(m->bmasks.ls, &m->d_k1b_ls)) != RXM_OK) return fail(st);
@@ -181,9 +204,6 @@ extern "C" int rxm_tables_upload(const rxm_tables *host_tables, int device, rxm_
             m->info.engine = RXM_ENGINE_K1_BITSET;
             goto planned;
         }
-        if (st != RXM_OK) return fail(st);
-        std::vector<uint8_t> table, accept;
-        st = rxm::k1_build_tables(m->dfa, m->k1, table, accept, &err);
         if (st != RXM_OK) return fail(st);
         if ((st = upload_vec(table, &m->d_k1_table)) != RXM_OK) return fail(st);
         if ((st = upload_vec(accept, &m->d_k1_accept)) != RXM_OK) return fail(st);
@@ -214,8 +234,7 @@ extern "C" int rxm_tables_upload(const rxm_tables *host_tables, int device, rxm_
         m->info.engine = RXM_ENGINE_K2_THREAD;
         // K3 (warp per string) needs the edge programs; automata they cannot express stay on K2
         std::string perr;
-        const char *force = getenv("RXM_MFA_ENGINE");  // "k2" / "k3": tuning and tests
-        if (!(force && std::strcmp(force, "k2") == 0) && rxm::compile_programs(t, m->prog, &perr) == RXM_OK) {
+        if (o.engine != RXM_ENGINE_K2_THREAD && rxm::compile_programs(t, m->prog, &perr) == RXM_OK) {
             if ((st = upload_vec(m->prog.items, &m->d_items)) != RXM_OK) return fail(st);
             if ((st = upload_vec(m->prog.begin, &m->d_prog_begin)) != RXM_OK) return fail(st);
             if ((st = upload_vec(m->prog.count, &m->d_prog_count)) != RXM_OK) return fail(st);
@@ -225,19 +244,16 @@ extern "C" int rxm_tables_upload(const rxm_tables *host_tables, int device, rxm_
             m->k4_maxl = rxm::k4_pool_for(t.n_states);  // slots per thread: the current set and the one being built share them
             // K4 (one thread per string) unless the automaton is large: its sets outgrow a thread's slots, K3 (one
             // warp per string, one slot per node) runs the whole batch
-            const bool big = t.n_states > rxm::K4_MAX_STATES && !(force && std::strcmp(force, "k4") == 0);
-            m->info.engine = ((force && std::strcmp(force, "k3") == 0) || big) ? RXM_ENGINE_K3_WARP : RXM_ENGINE_K4_THREAD;
+            const bool big = t.n_states > rxm::K4_MAX_STATES && o.engine != RXM_ENGINE_K4_THREAD;
+            m->info.engine = (o.engine == RXM_ENGINE_K3_WARP || big) ? RXM_ENGINE_K3_WARP : RXM_ENGINE_K4_THREAD;
             // short programs: several strings per warp (a step's items fit one pass of the tile)
             m->k3_tile = m->prog.max_count <= 8 ? 8 : (m->prog.max_count <= 16 ? 16 : 32);
-            if (const char *tl = getenv("RXM_K3_TILE")) {
-                const int x = atoi(tl);
-                if (x == 8 || x == 16 || x == 32) {
-                    m->k3_tile = uint32_t(x);
-                    m->k3_tile_forced = true;
-                }
+            if (o.k3_tile) {
+                m->k3_tile = o.k3_tile;
+                m->k3_tile_forced = true;
             }
-        } else if (force && (std::strcmp(force, "k3") == 0 || std::strcmp(force, "k4") == 0)) {
-            err = "RXM_MFA_ENGINE=k3/k4 but the edge programs cannot be built: " + perr;
+        } else if (o.engine == RXM_ENGINE_K3_WARP || o.engine == RXM_ENGINE_K4_THREAD) {
+            err = "the requested engine needs the edge programs, which cannot be built: " + perr;
             return fail(RXM_ERR_UNSUPPORTED);
         }
     }
@@ -245,7 +261,8 @@ planned:
     // [0] strings that hit a kernel limit, [1] K2/K3 work counter
     if (cudaMalloc(reinterpret_cast<void **>(&m->d_overflow), 2 * sizeof(unsigned long long)) != cudaSuccess)
         return fail(cuda_fail(cudaGetLastError(), "cudaMalloc overflow counter"));
-    CU(cudaMemset(m->d_overflow, 0, 2 * sizeof(unsigned long long)));
+    if (cudaMemset(m->d_overflow, 0, 2 * sizeof(unsigned long long)) != cudaSuccess)
+        return fail(cuda_fail(cudaGetLastError(), "cudaMemset overflow counter"));
     *out = m;
     return RXM_OK;
 }
@@ -274,6 +291,7 @@ extern "C" int rxm_free(rxm_handle h) {
     cudaFree(h->d_prog_sel);
     cudaFree(h->d_redo_list);
     cudaFree(h->d_redo_n);
+    cudaFree(h->d_pick);
     cudaFree(h->d_chars);
     cudaFree(h->d_offsets);
     cudaFree(h->d_bits);
@@ -320,9 +338,8 @@ extern "C" int rxm_overflow_count(rxm_handle h, uint64_t *count) {
 static int prepare_order(rxm_matcher *m, rxm::Spans spans, uint64_t n, cudaStream_t stream,
                          const rxm::K1Rec **order, int *launched, bool long_strings = false) {
     *order = nullptr;
-    const char *lpt = getenv("RXM_K3_ORDER");  // "index": tuning
     const uint64_t least = long_strings ? 512 : 4 * rxm::K1_TILE_STRINGS;
-    if (n < least || n > 0xfffffff0ull || (lpt && std::strcmp(lpt, "index") == 0)) return RXM_OK;
+    if (n < least || n > 0xfffffff0ull || m->index_order) return RXM_OK;
     if (n > m->cap_recs) {
         cudaFree(m->d_recs);
         m->d_recs = nullptr;
@@ -376,57 +393,91 @@ static int launch_on_device(rxm_matcher *m, const uint8_t *d_chars, rxm::Spans s
                        m->tables.finish, m->tables.reversed};
         rxm::K4Prog kp{m->d_items, m->d_prog_begin, m->d_prog_count, m->d_prog_lbeg, m->d_prog_lcnt, m->d_prog_sel,
                        m->prog.n_cells};
-        const rxm::K1Rec *order = nullptr;
-        if ((st = prepare_order(m, spans, n, stream, &order, &launched_extra)) != RXM_OK) return st;
-        // automata with more nodes than a thread has slots: strings that outgrow them are run by K3
-        const bool redo = 2 * m->tables.n_states() > m->k4_maxl;
-        if (redo) {
-            if (n > 0xfffffff0ull) return RXM_ERR_UNSUPPORTED;
-            if (n > m->cap_redo) {
-                cudaFree(m->d_redo_list);
-                m->d_redo_list = nullptr;
-                m->cap_redo = 0;
-                const size_t want = size_t(n + (n >> 3) + 32);
-                CU(cudaMalloc(reinterpret_cast<void **>(&m->d_redo_list), want * sizeof(uint32_t)));
-                m->cap_redo = want;
-            }
-            if (!m->d_redo_n) CU(cudaMalloc(reinterpret_cast<void **>(&m->d_redo_n), sizeof(unsigned long long)));
-            CU(cudaMemsetAsync(m->d_redo_n, 0, sizeof(unsigned long long), stream));
+        rxm::ProgView gp{m->d_items, m->d_prog_begin, m->d_prog_count, m->prog.n_cells};
+        // Batches of long strings (mean length above 4096: few strings, each bounded by its own length) are
+        // K3's, 32 lanes per string; everything else is K4's.  With host buffers the lengths are known here;
+        // with device buffers the choice is made ON THE DEVICE (mfa_pick_kernel) and both kernels are launched
+        // gated on it, so the call stays asynchronous on `stream`.
+        const bool known = total_chars != ~0ull;
+        const bool is_long = known && total_chars / n > rxm::kMfaLongMean;
+        const uint32_t *gate = nullptr;
+        if (!known) {
+            if (!m->d_pick) CU(cudaMalloc(reinterpret_cast<void **>(&m->d_pick), 2 * sizeof(uint32_t)));
+            if ((st = rxm::mfa_pick_launch(spans, n, m->d_pick, stream)) != RXM_OK) return st;
+            launched_extra++;
+            gate = m->d_pick;
         }
-        st = rxm::k4_launch(v, kp, uint32_t(m->prog.items.size()), uint32_t(m->prog.begin.size()),
-                            uint32_t(m->prog.sel.size()), m->tables.n_cells, m->k4_maxl, d_chars, spans, order, n, d_out,
-                            m->d_overflow, m->d_overflow + 1, redo ? m->d_redo_list : nullptr, m->d_redo_n, m->sm_count,
-                            m->sharing, stream, &launched);
-        if (st == RXM_OK && redo) {
+        const rxm::K1Rec *order = nullptr;
+        if ((st = prepare_order(m, spans, n, stream, &order, &launched_extra, is_long || !known)) != RXM_OK) return st;
+        if (!is_long) {
+            // strings that outgrow a thread's slots (the current set and the one being built share them) are run by K3
+            const bool redo = 2 * m->tables.n_states() > m->k4_maxl;
+            if (redo) {
+                if (n > 0xfffffff0ull) return RXM_ERR_UNSUPPORTED;
+                if (n > m->cap_redo) {
+                    cudaFree(m->d_redo_list);
+                    m->d_redo_list = nullptr;
+                    m->cap_redo = 0;
+                    const size_t want = size_t(n + (n >> 3) + 32);
+                    CU(cudaMalloc(reinterpret_cast<void **>(&m->d_redo_list), want * sizeof(uint32_t)));
+                    m->cap_redo = want;
+                }
+                if (!m->d_redo_n) CU(cudaMalloc(reinterpret_cast<void **>(&m->d_redo_n), sizeof(unsigned long long)));
+                CU(cudaMemsetAsync(m->d_redo_n, 0, sizeof(unsigned long long), stream));
+            }
+            st = rxm::k4_launch(v, kp, uint32_t(m->prog.items.size()), uint32_t(m->prog.begin.size()),
+                                uint32_t(m->prog.sel.size()), m->tables.n_cells, m->k4_maxl, d_chars, spans, order, n, d_out,
+                                m->d_overflow, m->d_overflow + 1, redo ? m->d_redo_list : nullptr, m->d_redo_n, m->sm_count,
+                                m->sharing, stream, &launched, gate);
+            if (st == RXM_OK && redo) {
+                int l3 = 0;
+                st = rxm::k3_launch(v, gp, uint32_t(m->prog.items.size()), uint32_t(m->prog.begin.size()), m->tables.n_cells,
+                                    m->k3_tile, d_chars, spans, nullptr, n, d_out, m->d_overflow, m->d_overflow + 1,
+                                    m->sm_count, m->sharing, stream, &l3, m->d_redo_list, m->d_redo_n);
+                launched_extra += l3;
+            }
+        }
+        if (st == RXM_OK && (is_long || !known)) {
             int l3 = 0;
-            rxm::ProgView gp{m->d_items, m->d_prog_begin, m->d_prog_count, m->prog.n_cells};
             st = rxm::k3_launch(v, gp, uint32_t(m->prog.items.size()), uint32_t(m->prog.begin.size()), m->tables.n_cells,
-                                m->k3_tile, d_chars, spans, nullptr, n, d_out, m->d_overflow, m->d_overflow + 1,
-                                m->sm_count, m->sharing, stream, &l3, m->d_redo_list, m->d_redo_n);
-            launched_extra += l3;
+                                32, d_chars, spans, order, n, d_out, m->d_overflow, m->d_overflow + 1, m->sm_count,
+                                m->sharing, stream, &l3, nullptr, nullptr, gate, 1u);
+            if (is_long) launched = l3;
+            else launched_extra += l3;
         }
     } else if (m->info.engine == RXM_ENGINE_K3_WARP) {
         rxm::MfaView v{m->d_edge_begin, m->d_edges, m->tables.n_states(), m->tables.start,
                        m->tables.finish, m->tables.reversed};
         rxm::ProgView gp{m->d_items, m->d_prog_begin, m->d_prog_count, m->prog.n_cells};
-        // Lanes per string: short programs let 2 or 4 strings share a warp, which pays for
-        // many short strings; long strings want the whole warp (per-string latency, wide
-        // block compares).  The mean length decides; with device buffers it costs one 8-byte
-        // read-back of offsets[n].
+        // Lanes per string: short programs let 2 or 4 strings share a warp, which pays for many short
+        // strings; long strings want the whole warp (per-string latency, wide block compares).  With host
+        // buffers the mean length decides here; with device buffers it is decided on the device and the two
+        // tile widths are launched gated on it (no read-back: the call stays asynchronous on `stream`).
         uint32_t tile = m->k3_tile;
-        if (total_chars == ~0ull && ((tile < 32 && !m->k3_tile_forced) || n < 4 * rxm::K1_TILE_STRINGS)) {
-            uint64_t ends[1] = {0};  // (small batches: the hand-out order below wants the mean length too)
-            CU(cudaMemcpyAsync(ends, spans.end + (n - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
-            CU(cudaStreamSynchronize(stream));
-            total_chars = ends[0];
+        const bool known = total_chars != ~0ull;
+        const bool long_strings = known && total_chars / n > rxm::kMfaLongMean;
+        const bool two_widths = !known && tile < 32 && !m->k3_tile_forced;
+        if (long_strings && !m->k3_tile_forced) tile = 32;
+        const uint32_t *gate = nullptr;
+        if (two_widths) {
+            if (!m->d_pick) CU(cudaMalloc(reinterpret_cast<void **>(&m->d_pick), 2 * sizeof(uint32_t)));
+            if ((st = rxm::mfa_pick_launch(spans, n, m->d_pick, stream)) != RXM_OK) return st;
+            launched_extra++;
+            gate = m->d_pick;
         }
-        if (tile < 32 && !m->k3_tile_forced && total_chars / n > 4096) tile = 32;
         const rxm::K1Rec *order = nullptr;
-        const bool long_strings = (total_chars != ~0ull && total_chars / n > 4096);
-        if ((st = prepare_order(m, spans, n, stream, &order, &launched_extra, long_strings)) != RXM_OK) return st;
+        if ((st = prepare_order(m, spans, n, stream, &order, &launched_extra, long_strings || !known)) != RXM_OK) return st;
+        if (two_widths) {
+            int l3 = 0;
+            st = rxm::k3_launch(v, gp, uint32_t(m->prog.items.size()), uint32_t(m->prog.begin.size()), m->tables.n_cells,
+                                32, d_chars, spans, order, n, d_out, m->d_overflow, m->d_overflow + 1, m->sm_count,
+                                m->sharing, stream, &l3, nullptr, nullptr, gate, 1u);
+            launched_extra += l3;
+            if (st != RXM_OK) return st;
+        }
         st = rxm::k3_launch(v, gp, uint32_t(m->prog.items.size()), uint32_t(m->prog.begin.size()),
                             m->tables.n_cells, tile, d_chars, spans, order, n, d_out, m->d_overflow, m->d_overflow + 1,
-                            m->sm_count, m->sharing, stream, &launched);
+                            m->sm_count, m->sharing, stream, &launched, nullptr, nullptr, gate, 0u);
     } else {
         rxm::MfaView v{m->d_edge_begin, m->d_edges, m->tables.n_states(), m->tables.start,
                        m->tables.finish, m->tables.reversed};

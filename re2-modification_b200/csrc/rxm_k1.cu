@@ -25,7 +25,7 @@
 namespace rxm {
 
 int k1_build_tables(const DfaPlan &p, K1Tables &kt, std::vector<uint8_t> &table,
-                    std::vector<uint8_t> &accept, std::string *err) {
+                    std::vector<uint8_t> &accept, std::string *err, bool no_quad) {
     kt = K1Tables();
     kt.n_states = p.n_states;
     kt.n_classes = p.n_classes;
@@ -57,8 +57,7 @@ int k1_build_tables(const DfaPlan &p, K1Tables &kt, std::vector<uint8_t> &table,
                 lit_hi = std::max(lit_hi, b);
             }
         if (lit_hi < 0) lit_lo = lit_hi = 'a';
-        const char *noquad = getenv("RXM_K1_NOQUAD");
-        if (p.n_states <= 64 && lit_hi - lit_lo <= 3 && !(noquad && noquad[0] == '1')) {
+        if (p.n_states <= 64 && lit_hi - lit_lo <= 3 && !no_quad) {
             const uint32_t lo = uint32_t(std::min(lit_lo, 252));
             kt.quad = 1;
             kt.quad_lo = lo;
@@ -574,8 +573,15 @@ k1_dfa_classed_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict
                                                   ring0 + (threadIdx.x >> 5) * (STAGES * 32 * (CH + 16)));
 }
 
-// ring geometry variants (RXM_K1_VARIANT=0..2 selects one for tuning; default 0)
+// Ring geometry.  The product library holds ONE geometry per kernel (V0 / 64-byte chunks, 2 stages, 8 warps:
+// the fastest measured); the others exist only in tuning builds (make EXTRA=-DRXM_TUNING),
+// selected there with RXM_K1_VARIANT=0..7.
+// The dynamic shared-memory limit is a per-FUNCTION attribute: it is always set to the same value, so that
+// handles sharing a kernel instantiation may launch from several host threads (the size a launch needs is
+// checked against it).
+constexpr int K1_MAX_DYN_SMEM = 200 * 1024;
 struct V0 { static constexpr int CH = 64, STAGES = 2, NS = 1; };
+#ifdef RXM_TUNING
 struct V1 { static constexpr int CH = 32, STAGES = 2, NS = 2; };
 struct V2 { static constexpr int CH = 64, STAGES = 2, NS = 2; };
 struct V3 { static constexpr int CH = 32, STAGES = 3, NS = 2; };
@@ -590,6 +596,9 @@ inline int k1_variant() {
     }
     return v;
 }
+#else
+inline int k1_variant() { return 0; }
+#endif
 
 template <class Kern>
 int blocks_per_sm(Kern kern, size_t smem) {
@@ -602,7 +611,7 @@ template <bool REV, int L, class V>
 int launch_direct_v(const K1Tables &kt, const K1Launch &a) {
     const size_t smem = size_t(K1_WARPS) * V::STAGES * V::NS * 32 * (V::CH + 16);
     auto kern = k1_dfa_direct_kernel<REV, L, V::CH, V::STAGES, V::NS>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_MAX_DYN_SMEM) != cudaSuccess)
         return RXM_ERR_CUDA;
     int nb = blocks_per_sm(kern, smem);
     if (nb <= 0) return RXM_ERR_CUDA;
@@ -617,10 +626,12 @@ int launch_direct_v(const K1Tables &kt, const K1Launch &a) {
 template <bool REV, int L>
 int launch_direct(const K1Tables &kt, const K1Launch &a) {
     switch (k1_variant()) {
+#ifdef RXM_TUNING
         case 1: return launch_direct_v<REV, L, V1>(kt, a);
         case 2: return launch_direct_v<REV, L, V2>(kt, a);
         case 3: return launch_direct_v<REV, L, V3>(kt, a);
         case 4: return launch_direct_v<REV, L, V4>(kt, a);
+#endif
         default: return launch_direct_v<REV, L, V0>(kt, a);
     }
 }
@@ -629,7 +640,7 @@ template <bool REV, int L, int CH, int STAGES, int WARPS>
 int launch_quad_w(const K1Tables &kt, const K1Launch &a) {
     const size_t smem = size_t(WARPS) * STAGES * 32 * (CH + 16);
     auto kern = k1_dfa_quad_kernel<REV, L, CH, STAGES, WARPS>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_MAX_DYN_SMEM) != cudaSuccess)
         return RXM_ERR_CUDA;
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, WARPS * 32, smem) != cudaSuccess || nb <= 0)
@@ -645,6 +656,7 @@ int launch_quad_w(const K1Tables &kt, const K1Launch &a) {
 template <bool REV, int L>
 int launch_quad(const K1Tables &kt, const K1Launch &a) {
     switch (k1_variant()) {  // tuning: CTA width / ring geometry
+#ifdef RXM_TUNING
         case 1: return launch_quad_w<REV, L, 64, 2, 16>(kt, a);
         case 2: return launch_quad_w<REV, L, 64, 3, 10>(kt, a);
         case 3: return launch_quad_w<REV, L, 128, 2, 11>(kt, a);
@@ -652,6 +664,7 @@ int launch_quad(const K1Tables &kt, const K1Launch &a) {
         case 5: return launch_quad_w<REV, L, 256, 2, 6>(kt, a);
         case 6: return launch_quad_w<REV, L, 128, 3, 7>(kt, a);
         case 7: return launch_quad_w<REV, L, 64, 4, 10>(kt, a);
+#endif
         default: return launch_quad_w<REV, L, 64, 2, 8>(kt, a);
     }
 }
@@ -679,7 +692,7 @@ template <bool REV>
 int launch_classed(const K1Tables &kt, const K1Launch &a) {
     const size_t smem = size_t(kt.table_bytes) + kt.accept_bytes + 128 + size_t(K1_WARPS) * V0::STAGES * 32 * (V0::CH + 16);
     auto kern = k1_dfa_classed_kernel<REV, V0::CH, V0::STAGES>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_MAX_DYN_SMEM) != cudaSuccess)
         return RXM_ERR_CUDA;
     int nb = blocks_per_sm(kern, smem);
     if (nb <= 0) return RXM_ERR_CUDA;

@@ -134,7 +134,7 @@ int k1b_mask_launch(const uint64_t *d_ls, const uint8_t *d_class, uint32_t n_sta
     *launched = 0;
     const size_t smem = size_t(n_classes) * n_states * 16 + 256;
     if (smem > 96 * 1024) return RXM_ERR_UNSUPPORTED;
-    if (cudaFuncSetAttribute(k1b_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+    if (cudaFuncSetAttribute(k1b_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 /* one value per function: launches may come from several threads */) != cudaSuccess)
         return RXM_ERR_CUDA;
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k1b_mask_kernel, K1B_THREADS, smem) != cudaSuccess || nb <= 0)
@@ -162,7 +162,7 @@ int k1b_launch(const uint16_t *d_eb, const uint32_t *d_ed, uint32_t n_states, ui
     *launched = 0;
     const size_t smem = ((size_t(n_edges) * 4 + (size_t(n_states) + 1) * 2) + 15) & ~size_t(15);
     if (smem > 96 * 1024) return RXM_ERR_UNSUPPORTED;
-    if (cudaFuncSetAttribute(k1b_bitset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+    if (cudaFuncSetAttribute(k1b_bitset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 /* one value per function: launches may come from several threads */) != cudaSuccess)
         return RXM_ERR_CUDA;
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k1b_bitset_kernel, K1B_THREADS, smem) != cudaSuccess || nb <= 0)

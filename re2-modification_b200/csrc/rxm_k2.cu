@@ -87,7 +87,7 @@ int launch_k2(const MfaView &v, uint32_t n_edges, const uint8_t *d_chars, Spans 
         smem = tab_bytes;
     }
     auto kern = local ? k2_mfa_thread_kernel<NC, CAP, DMAX, true> : k2_mfa_thread_kernel<NC, CAP, DMAX, false>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 /* one value per function: launches may come from several threads */) != cudaSuccess)
         return RXM_ERR_CUDA;
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, K2_THREADS, smem) != cudaSuccess || nb <= 0)

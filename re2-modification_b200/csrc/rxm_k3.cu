@@ -166,8 +166,11 @@ k3_mfa_warp_kernel(MfaView v, ProgView gp, uint32_t n_items, uint32_t n_keys, ui
                    const uint8_t *__restrict__ chars, const Spans sp, const K1Rec *__restrict__ recs, uint64_t n,
                    uint8_t *__restrict__ out, unsigned long long *__restrict__ overflow,
                    unsigned long long *__restrict__ next_string, const uint32_t *__restrict__ list,
-                   const unsigned long long *__restrict__ list_n) {
+                   const unsigned long long *__restrict__ list_n, const uint32_t *__restrict__ gate, uint32_t gate_want) {
     RXM_DYN_SMEM(smem);
+    // gate != null: this launch only runs if the batch is (gate_want = 1) / is not (0) one of long strings -- decided
+    // on the device (mfa_pick_kernel), so that the call stays asynchronous when only the device knows the lengths
+    if (gate && (*gate != 0u) != (gate_want != 0u)) return;
     // list != null: the strings to run are list[0 .. *list_n) (K4 hands over the strings that outgrew its
     // per-thread sets; the count is only known on the device)
     if (list) n = *list_n;
@@ -535,7 +538,7 @@ template <int NC, int TILE>
 int launch_k3(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n_keys, const uint8_t *d_chars,
               Spans spans, const K1Rec *d_recs, uint64_t n, uint8_t *d_out, unsigned long long *d_overflow,
               unsigned long long *d_next, int sm_count, uint32_t sharing, cudaStream_t stream, const uint32_t *d_list,
-              const unsigned long long *d_list_n) {
+              const unsigned long long *d_list_n, const uint32_t *d_gate, uint32_t gate_want) {
     constexpr int TILES = K3_WARPS * 32 / TILE;  // strings in flight per block
     const uint32_t SP = (v.n_states + TILE - 1u) & ~uint32_t(TILE - 1);
     const size_t per_tile = size_t(SP) * 2 * (8 + 4 + 8 * NC) + size_t(SP) * 12 + 16;
@@ -557,7 +560,7 @@ int launch_k3(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n
     if (blocks > need) blocks = need;
     if (cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), stream) != cudaSuccess) return RXM_ERR_CUDA;
     RXM_LAUNCH(kern, unsigned(blocks), K3_WARPS * 32, smem, stream, v, gp, n_items, n_keys, in_smem ? 1u : 0u, d_chars, spans,
-               d_recs, n, d_out, d_overflow, d_next, d_list, d_list_n);
+               d_recs, n, d_out, d_overflow, d_next, d_list, d_list_n, d_gate, gate_want);
     return RXM_OK;
 }
 
@@ -565,29 +568,46 @@ template <int NC>
 int launch_k3_tile(uint32_t tile, const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n_keys,
                    const uint8_t *d_chars, Spans spans, const K1Rec *d_recs, uint64_t n, uint8_t *d_out,
                    unsigned long long *d_overflow, unsigned long long *d_next, int sm_count, uint32_t sharing, cudaStream_t stream,
-                   const uint32_t *d_list, const unsigned long long *d_list_n) {
+                   const uint32_t *d_list, const unsigned long long *d_list_n, const uint32_t *d_gate, uint32_t gate_want) {
     // the per-string state (two buffers of one slot per node) of all strings of a block must fit
     // shared memory: automata with many nodes move to wider tiles (fewer strings per block)
     int st = RXM_ERR_UNSUPPORTED;
-    if (tile <= 8) st = launch_k3<NC, 8>(v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream, d_list, d_list_n);
+    if (tile <= 8) st = launch_k3<NC, 8>(v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream, d_list, d_list_n, d_gate, gate_want);
     if (st == RXM_ERR_UNSUPPORTED && tile <= 16)
-        st = launch_k3<NC, 16>(v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream, d_list, d_list_n);
+        st = launch_k3<NC, 16>(v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream, d_list, d_list_n, d_gate, gate_want);
     if (st == RXM_ERR_UNSUPPORTED)
-        st = launch_k3<NC, 32>(v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream, d_list, d_list_n);
+        st = launch_k3<NC, 32>(v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream, d_list, d_list_n, d_gate, gate_want);
     return st;
 }
 
 }  // namespace
 
+namespace {
+// "long strings": mean length above 4096 -- the regime where one string per warp (K3, 32 lanes) beats one per
+// thread (K4): few strings, each bounded by its own length.  One thread; flag[0] <- 1 / 0.
+__global__ void mfa_pick_kernel(const Spans sp, uint64_t n, uint32_t *__restrict__ flag) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const uint64_t total = n ? sp.end[n - 1] - sp.begin[0] : 0;
+        flag[0] = (n && total / n > kMfaLongMean) ? 1u : 0u;
+    }
+}
+}  // namespace
+
+int mfa_pick_launch(Spans spans, uint64_t n, uint32_t *d_flag, cudaStream_t stream) {
+    RXM_LAUNCH(mfa_pick_kernel, 1u, 32, 0, stream, spans, n, d_flag);
+    return RXM_OK;
+}
+
 int k3_launch(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n_keys, uint32_t n_cells,
               uint32_t tile, const uint8_t *d_chars, Spans spans, const K1Rec *d_recs, uint64_t n, uint8_t *d_out,
               unsigned long long *d_overflow, unsigned long long *d_next, int sm_count, uint32_t sharing,
-              cudaStream_t stream, int *launched, const uint32_t *d_list, const unsigned long long *d_list_n) {
+              cudaStream_t stream, int *launched, const uint32_t *d_list, const unsigned long long *d_list_n,
+              const uint32_t *d_gate, uint32_t gate_want) {
     *launched = 0;
     int st;
-    if (n_cells <= 1) st = launch_k3_tile<1>(tile, v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream, d_list, d_list_n);
-    else if (n_cells <= 2) st = launch_k3_tile<2>(tile, v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream, d_list, d_list_n);
-    else if (n_cells <= 4) st = launch_k3_tile<4>(tile, v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream, d_list, d_list_n);
+    if (n_cells <= 1) st = launch_k3_tile<1>(tile, v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream, d_list, d_list_n, d_gate, gate_want);
+    else if (n_cells <= 2) st = launch_k3_tile<2>(tile, v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream, d_list, d_list_n, d_gate, gate_want);
+    else if (n_cells <= 4) st = launch_k3_tile<4>(tile, v, gp, n_items, n_keys, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, sm_count, sharing, stream, d_list, d_list_n, d_gate, gate_want);
     else return RXM_ERR_UNSUPPORTED;
     if (st == RXM_OK) *launched = 1;
     return st;

@@ -22,8 +22,9 @@ k4_mfa_thread_kernel(MfaView v, K4Prog gp, uint32_t n_items, uint32_t n_keys, ui
                      uint32_t maxl, const uint8_t *__restrict__ chars, const Spans sp, const K1Rec *__restrict__ recs,
                      uint64_t n, uint8_t *__restrict__ out, unsigned long long *__restrict__ overflow,
                      unsigned long long *__restrict__ next_string, uint32_t *__restrict__ redo_list,
-                     unsigned long long *__restrict__ redo_n) {
+                     unsigned long long *__restrict__ redo_n, const uint32_t *__restrict__ gate) {
     RXM_DYN_SMEM(smem);
+    if (gate && *gate != 0u) return;  // a batch of long strings: K3 runs it (mfa_pick_kernel decided on the device)
     constexpr uint32_t ALL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u;
     // ---- block-shared program tables ----
@@ -135,7 +136,7 @@ template <int NC>
 int launch_k4(const MfaView &v, const K4Prog &gp, uint32_t n_items, uint32_t n_keys, uint32_t n_sel, uint32_t maxl,
               const uint8_t *d_chars, Spans spans, const K1Rec *d_recs, uint64_t n, uint8_t *d_out,
               unsigned long long *d_overflow, unsigned long long *d_next, uint32_t *d_redo_list,
-              unsigned long long *d_redo_n, int sm_count, uint32_t sharing, cudaStream_t stream) {
+              unsigned long long *d_redo_n, int sm_count, uint32_t sharing, cudaStream_t stream, const uint32_t *d_gate) {
     const size_t tab = (size_t(n_keys) * 16 + size_t(n_sel) * 2 + 15) & ~size_t(15);
     const bool in_smem = size_t(n_items) * sizeof(ProgItem) <= 24 * 1024;
     const size_t smem = tab + (in_smem ? size_t(n_items) * sizeof(ProgItem) : 0) +
@@ -153,7 +154,7 @@ int launch_k4(const MfaView &v, const K4Prog &gp, uint32_t n_items, uint32_t n_k
     if (blocks > need) blocks = need;
     if (cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), stream) != cudaSuccess) return RXM_ERR_CUDA;
     RXM_LAUNCH(kern, unsigned(blocks), K4_THREADS, smem, stream, v, gp, n_items, n_keys, n_sel, in_smem ? 1u : 0u, maxl,
-               d_chars, spans, d_recs, n, d_out, d_overflow, d_next, d_redo_list, d_redo_n);
+               d_chars, spans, d_recs, n, d_out, d_overflow, d_next, d_redo_list, d_redo_n, d_gate);
     return RXM_OK;
 }
 
@@ -162,12 +163,13 @@ int launch_k4(const MfaView &v, const K4Prog &gp, uint32_t n_items, uint32_t n_k
 int k4_launch(const MfaView &v, const K4Prog &gp, uint32_t n_items, uint32_t n_keys, uint32_t n_sel, uint32_t n_cells,
               uint32_t maxl, const uint8_t *d_chars, Spans spans, const K1Rec *d_recs, uint64_t n, uint8_t *d_out,
               unsigned long long *d_overflow, unsigned long long *d_next, uint32_t *d_redo_list,
-              unsigned long long *d_redo_n, int sm_count, uint32_t sharing, cudaStream_t stream, int *launched) {
+              unsigned long long *d_redo_n, int sm_count, uint32_t sharing, cudaStream_t stream, int *launched,
+              const uint32_t *d_gate) {
     *launched = 0;
     int st;
-    if (n_cells <= 1) st = launch_k4<1>(v, gp, n_items, n_keys, n_sel, maxl, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, d_redo_list, d_redo_n, sm_count, sharing, stream);
-    else if (n_cells <= 2) st = launch_k4<2>(v, gp, n_items, n_keys, n_sel, maxl, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, d_redo_list, d_redo_n, sm_count, sharing, stream);
-    else if (n_cells <= 4) st = launch_k4<4>(v, gp, n_items, n_keys, n_sel, maxl, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, d_redo_list, d_redo_n, sm_count, sharing, stream);
+    if (n_cells <= 1) st = launch_k4<1>(v, gp, n_items, n_keys, n_sel, maxl, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, d_redo_list, d_redo_n, sm_count, sharing, stream, d_gate);
+    else if (n_cells <= 2) st = launch_k4<2>(v, gp, n_items, n_keys, n_sel, maxl, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, d_redo_list, d_redo_n, sm_count, sharing, stream, d_gate);
+    else if (n_cells <= 4) st = launch_k4<4>(v, gp, n_items, n_keys, n_sel, maxl, d_chars, spans, d_recs, n, d_out, d_overflow, d_next, d_redo_list, d_redo_n, sm_count, sharing, stream, d_gate);
     else return RXM_ERR_UNSUPPORTED;
     if (st == RXM_OK) *launched = 1;
     return st;

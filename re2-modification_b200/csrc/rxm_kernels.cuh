@@ -51,7 +51,7 @@ struct K1Tables {
 };
 
 int k1_build_tables(const DfaPlan &p, K1Tables &kt, std::vector<uint8_t> &table,
-                    std::vector<uint8_t> &accept, std::string *err);
+                    std::vector<uint8_t> &accept, std::string *err, bool no_quad = false);
 
 // One record per string, written by the tile sort: descending length bucket within each tile.
 struct __align__(16) K1Rec {
@@ -108,7 +108,15 @@ int k3_launch(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n
               uint32_t sharing /* handles running at once on the device: the grid takes 1/sharing of the block slots */,
               cudaStream_t stream, int *launched,
               const uint32_t *d_list = nullptr /* run strings d_list[0 .. *d_list_n) instead of 0 .. n (n = the list's capacity) */,
-              const unsigned long long *d_list_n = nullptr);
+              const unsigned long long *d_list_n = nullptr,
+              const uint32_t *d_gate = nullptr /* run only if (*d_gate != 0) == (gate_want != 0): mfa_pick_launch */,
+              uint32_t gate_want = 0);
+
+// Batches of long strings (mean length above kMfaLongMean) go to K3 with 32 lanes per string, the others to
+// K4.  When only the device knows the lengths the choice is made there: d_flag[0] <- 1 (long) / 0, and both
+// kernels are launched gated on it -- no read-back, the call stays asynchronous.
+constexpr uint64_t kMfaLongMean = 4096;
+int mfa_pick_launch(Spans spans, uint64_t n, uint32_t *d_flag, cudaStream_t stream);
 
 // ---- K4: MFA, one thread per string, over the same edge programs (rxm_k4_core.cuh) ------------
 // maxl = live configurations a thread keeps per set; a string that needs more is appended to
@@ -116,7 +124,8 @@ int k3_launch(const MfaView &v, const ProgView &gp, uint32_t n_items, uint32_t n
 int k4_launch(const MfaView &v, const K4Prog &gp, uint32_t n_items, uint32_t n_keys, uint32_t n_sel, uint32_t n_cells,
               uint32_t maxl, const uint8_t *d_chars, Spans spans, const K1Rec *d_recs, uint64_t n, uint8_t *d_out,
               unsigned long long *d_overflow, unsigned long long *d_next, uint32_t *d_redo_list,
-              unsigned long long *d_redo_n, int sm_count, uint32_t sharing, cudaStream_t stream, int *launched);
+              unsigned long long *d_redo_n, int sm_count, uint32_t sharing, cudaStream_t stream, int *launched,
+              const uint32_t *d_gate = nullptr /* skip the launch's work if *d_gate != 0 (a batch of long strings) */);
 
 // ---- tokeniser: whitespace-delimited text -> spans (rxm_tok.cu) ------------------------------
 // Same token boundaries as `cin >> text` (matchers/match.cpp:22-23): whitespace is

@@ -31,7 +31,7 @@ ENGINE_NAMES = {1: "K1_DFA", 2: "K1_BITSET", 3: "K2_THREAD", 4: "K3_WARP", 5: "K
 # every symbol include/rxm.h declares (tests check that the library exports them all)
 ABI_SYMBOLS = [
     "rxm_tables_format", "rxm_tables_parse", "rxm_tables_release", "rxm_tables_validate",
-    "rxm_tables_upload", "rxm_plan_query", "rxm_free", "rxm_match_batch", "rxm_match_text",
+    "rxm_tables_upload", "rxm_tables_upload_opts", "rxm_plan_query", "rxm_free", "rxm_match_batch", "rxm_match_text",
     "rxm_launch_count", "rxm_overflow_count", "rxm_set_concurrency", "rxm_strerror", "rxm_last_cuda_error",
 ]
 
@@ -45,6 +45,15 @@ class RxmTables(C.Structure):
         ("edge_sym", C.POINTER(C.c_uint8)), ("edge_to", C.POINTER(C.c_uint16)),
         ("edge_open", C.POINTER(C.c_uint16)), ("edge_close", C.POINTER(C.c_uint16)),
     ]
+
+
+class RxmUploadOpts(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("engine", C.c_uint32), ("flags", C.c_uint32), ("k3_tile", C.c_uint32),
+                ("reserved", C.c_uint32 * 4)]
+
+
+OPT_K1_NO_QUAD, OPT_K1B_WALK, OPT_INDEX_ORDER = 1, 2, 4
+ENGINE_IDS = {"k1": 1, "bitset": 2, "k2": 3, "k3": 4, "k4": 5}
 
 
 class RxmPlanInfo(C.Structure):
@@ -85,6 +94,8 @@ def lib() -> C.CDLL:
         L.rxm_tables_validate.restype = C.c_int
         L.rxm_tables_upload.argtypes = [C.POINTER(RxmTables), C.c_int, C.POINTER(C.c_void_p)]
         L.rxm_tables_upload.restype = C.c_int
+        L.rxm_tables_upload_opts.argtypes = [C.POINTER(RxmTables), C.c_int, C.POINTER(RxmUploadOpts), C.POINTER(C.c_void_p)]
+        L.rxm_tables_upload_opts.restype = C.c_int
         L.rxm_plan_query.argtypes = [C.c_void_p, C.POINTER(RxmPlanInfo)]
         L.rxm_plan_query.restype = C.c_int
         L.rxm_free.argtypes = [C.c_void_p]
@@ -158,12 +169,18 @@ class Tables:
 class Matcher:
     """Device matcher for one automaton: rxm_tables_upload / rxm_match_batch / rxm_free."""
 
-    def __init__(self, tables: Tables, device: int = 0):
+    def __init__(self, tables: Tables, device: int = 0, engine=None, flags: int = 0, k3_tile: int = 0):
+        """engine: None (the planner's choice) or "k1" / "bitset" / "k2" / "k3" / "k4" (rxm_tables_upload_opts);
+        flags: OPT_*; k3_tile: 0 or 8 / 16 / 32."""
         self.tables = tables
         self.device = device
         self._h = C.c_void_p()
         self.saw_exit = C.c_int(0)  # set by the last match_text_* call
-        st = lib().rxm_tables_upload(tables.ptr, device, C.byref(self._h))
+        if engine is None and not flags and not k3_tile:
+            st = lib().rxm_tables_upload(tables.ptr, device, C.byref(self._h))
+        else:
+            o = RxmUploadOpts(abi_version=1, engine=ENGINE_IDS[engine] if engine else 0, flags=flags, k3_tile=k3_tile)
+            st = lib().rxm_tables_upload_opts(tables.ptr, device, C.byref(o), C.byref(self._h))
         if st != RXM_OK:
             raise RxmError(st, "rxm_tables_upload: " + lib().rxm_last_cuda_error().decode())
 

@@ -11,15 +11,12 @@ rxm = H.rxm
 bad = 0
 for regex, flags, kind, t, strings, bits in load_fuzz_corpus(sys.argv[1] if len(sys.argv) > 1 else None):
     chars, off = H.make_batch(strings)
-    variants = [{}] + ([{"RXM_MFA_ENGINE": "k2"}] if kind == "mfa" and t.c.n_cells > 4 else
-                       [{"RXM_MFA_ENGINE": "k2"}, {"RXM_MFA_ENGINE": "k3"}] if kind == "mfa" else
-                       [{"RXM_NFA_ENGINE": "bitset"}, {"RXM_NFA_ENGINE": "bitset", "RXM_K1B_WALK": "1"}])
+    variants = [{}] + ([{"engine": "k2"}] if kind == "mfa" and t.c.n_cells > 4 else
+                       [{"engine": "k2"}, {"engine": "k3"}, {"engine": "k4"}] if kind == "mfa" else
+                       [{"engine": "bitset"}, {"engine": "bitset", "flags": 2}])
     for env in variants:
-        for k in ("RXM_MFA_ENGINE", "RXM_NFA_ENGINE", "RXM_K1B_WALK"):
-            os.environ.pop(k, None)
-        os.environ.update(env)
         try:
-            m = rxm.Matcher(t, 0)
+            m = rxm.Matcher(t, 0, **env)
         except rxm.RxmError as e:
             print("UPLOAD", regex, flags, env, e, "states", t.c.n_states, "edges", t.c.n_edges, "cells", t.c.n_cells); bad += 1
             continue

@@ -106,12 +106,9 @@ def main():
                 strings.append(s.encode())
         chars, off = H.make_batch(strings)
         want = H.oracle_bits(t, chars, off)
-        variants = [{}] + ([{"RXM_MFA_ENGINE": "k2"}] if kind == "mfa" else [{"RXM_NFA_ENGINE": "bitset"}, {"RXM_K1_NOQUAD": "1"}])
+        variants = [{}] + ([{"engine": "k2"}] if kind == "mfa" else [{"engine": "bitset"}, {"flags": 1}])
         for env in variants:
-            for k in ("RXM_MFA_ENGINE", "RXM_NFA_ENGINE", "RXM_K1B_WALK", "RXM_K1_NOQUAD"):
-                os.environ.pop(k, None)
-            os.environ.update(env)
-            m = rxm.Matcher(t, 0)
+            m = rxm.Matcher(t, 0, **env)
             got = m.match_host(chars, off)
             if not np.array_equal(got, want):
                 bad += 1

@@ -69,14 +69,11 @@ def main():
             strings.append(u * int(nprng.integers(2, 60)))
         chars, off = H.make_batch(strings)
         want = H.oracle_bits(t, chars, off)
-        variants = [{}] + ([{"RXM_MFA_ENGINE": "k2"}, {"RXM_MFA_ENGINE": "k3"}] if mfa else
-                           [{"RXM_NFA_ENGINE": "bitset"}, {"RXM_NFA_ENGINE": "bitset", "RXM_K1B_WALK": "1"}, {"RXM_K1_NOQUAD": "1"}])
+        variants = [{}] + ([{"engine": "k2"}, {"engine": "k3"}, {"engine": "k4"}] if mfa else
+                           [{"engine": "bitset"}, {"engine": "bitset", "flags": 2}, {"flags": 1}])
         for env in variants:
-            for k in ("RXM_MFA_ENGINE", "RXM_NFA_ENGINE", "RXM_K1B_WALK", "RXM_K1_NOQUAD"):
-                os.environ.pop(k, None)
-            os.environ.update(env)
             try:
-                m = rxm.Matcher(t, 0)
+                m = rxm.Matcher(t, 0, **env)
             except rxm.RxmError as e:
                 if e.status == rxm.RXM_ERR_UNSUPPORTED:
                     declined += 1

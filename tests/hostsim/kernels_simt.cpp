@@ -134,8 +134,10 @@ extern "C" int hostsim_k4_batch(const rxm_tables *t, const uint8_t *chars, const
 }
 
 // K1 through rxm::plan_dfa, rxm::k1_build_tables and rxm::k1_launch: the tile sort, then the scan
-// kernel the tables select (quad stride / direct / two-lookup; RXM_K1_NOQUAD and RXM_K1_VARIANT are
+// kernel the tables select (quad stride / direct / two-lookup; hostsim_k1_no_quad stands for RXM_OPT_K1_NO_QUAD, RXM_K1_VARIANT is
 // read as on the device).  info3 (may be null) <- sets, byte classes, bytes per lookup.
+static bool g_k1_no_quad = false;  // RXM_OPT_K1_NO_QUAD for the next hostsim_k1_batch calls
+extern "C" void hostsim_k1_no_quad(int on) { g_k1_no_quad = on != 0; }
 extern "C" int hostsim_k1_batch(const rxm_tables *t, const uint8_t *chars, const uint64_t *off, uint64_t n,
                                 uint8_t *out, uint64_t limit, unsigned long long *overflow_out, uint32_t *info3,
                                 char *msg_out, uint32_t msg_cap, uint64_t seed) {
@@ -145,7 +147,7 @@ extern "C" int hostsim_k1_batch(const rxm_tables *t, const uint8_t *chars, const
     if (st != RXM_OK) return st;
     rxm::K1Tables kt;
     std::vector<uint8_t> table, accept;
-    st = rxm::k1_build_tables(p, kt, table, accept, &err);
+    st = rxm::k1_build_tables(p, kt, table, accept, &err, g_k1_no_quad);
     if (st != RXM_OK) return st;
     if (info3) {
         info3[0] = p.n_states;

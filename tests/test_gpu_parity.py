@@ -24,19 +24,8 @@ def _engine_cases():
 
 
 def _matcher(t, engine):
-    """engine: None (planner's choice) or "k2"/"k3"/"k4" (RXM_MFA_ENGINE override at upload)."""
-    import os
-    old = os.environ.get("RXM_MFA_ENGINE")
-    if engine:
-        os.environ["RXM_MFA_ENGINE"] = engine
-    try:
-        m = rxm.Matcher(t, 0)
-    finally:
-        if engine:
-            if old is None:
-                del os.environ["RXM_MFA_ENGINE"]
-            else:
-                os.environ["RXM_MFA_ENGINE"] = old
+    """engine: None (planner's choice) or "k2"/"k3"/"k4" (rxm_tables_upload_opts)."""
+    m = rxm.Matcher(t, 0, engine=engine)
     if engine:
         assert rxm.ENGINE_NAMES[m.plan().engine] == {"k2": "K2_THREAD", "k3": "K3_WARP", "k4": "K4_THREAD"}[engine]
     return m
@@ -205,9 +194,9 @@ def test_k1_every_length_and_alignment(name):
 
 
 @pytest.mark.parametrize("name", ["nfa_config2", "nfa_quirk", "nfa_abb", "nfa_dots", "nfa_third"])
-def test_k1_quad_stride_and_bytes_outside_the_window(name, monkeypatch):
+def test_k1_quad_stride_and_bytes_outside_the_window(name):
     """The four-bytes-per-lookup interior (dfa_stride 4) against the oracle and against the
-    one-byte scan (RXM_K1_NOQUAD=1), on long strings that stay alive and carry bytes outside
+    one-byte scan (RXM_OPT_K1_NO_QUAD), on long strings that stay alive and carry bytes outside
     the 4-letter window -- singly, in every position of a 16-byte vector, and in runs."""
     t, _, _ = load_case(name)
     rng = np.random.default_rng(5)
@@ -237,8 +226,7 @@ def test_k1_quad_stride_and_bytes_outside_the_window(name, monkeypatch):
     stride = m.plan().dfa_stride
     got = m.match_host(chars, off)
     m.close()
-    monkeypatch.setenv("RXM_K1_NOQUAD", "1")
-    m1 = rxm.Matcher(t, 0)
+    m1 = rxm.Matcher(t, 0, flags=rxm.OPT_K1_NO_QUAD)
     assert m1.plan().dfa_stride == 1
     got1 = m1.match_host(chars, off)
     m1.close()
@@ -250,16 +238,13 @@ def test_k1_quad_stride_and_bytes_outside_the_window(name, monkeypatch):
 
 @pytest.mark.parametrize("mode", ["masks", "walk"])
 @pytest.mark.parametrize("name", [n for n in CASE_NAMES if BY_NAME[n]["kind"] == "nfa"])
-def test_bitset_engine_on_every_memory_free_fixture(name, mode, monkeypatch):
+def test_bitset_engine_on_every_memory_free_fixture(name, mode):
     """K1B (the active set as a 128-bit mask, the reference's exact step per letter) in both of its
     forms -- bit-parallel follow masks and the edge walk: forced on every memory-free fixture,
     golden bits + random batches against the oracle; forward, right-to-left, Thompson, the
     visited quirk."""
-    monkeypatch.setenv("RXM_NFA_ENGINE", "bitset")
-    if mode == "walk":
-        monkeypatch.setenv("RXM_K1B_WALK", "1")
     t, strings, bits = load_case(name)
-    m = rxm.Matcher(t, 0)
+    m = rxm.Matcher(t, 0, engine="bitset", flags=rxm.OPT_K1B_WALK if mode == "walk" else 0)
     assert rxm.ENGINE_NAMES[m.plan().engine] == "K1_BITSET"
     assert (m.plan().dfa_classes > 0) == (mode == "masks")
     chars, off = H.make_batch(strings)
@@ -490,7 +475,7 @@ def test_sharded_1_2_4_8_ways_gives_the_identical_bit_vector(name):
     m.close()
 
 
-def test_random_expression_corpus_on_device(monkeypatch):
+def test_random_expression_corpus_on_device():
     """The 280 random expressions of tests/golden/fuzz (bits from the reference's own code) through
     every device engine that can take them: the planner's choice, K2 and K3 for the MFAs, the
     bit-set engine in both forms for the memory-free ones, and the raw-text route."""
@@ -502,16 +487,13 @@ def test_random_expression_corpus_on_device(monkeypatch):
         tag = (regex, flags)
         variants = [{}]
         if kind == "mfa" and t.c.n_cells > 4:
-            variants += [{"RXM_MFA_ENGINE": "k2"}]  # more than 4 cells: the planner's choice is K2 as well
+            variants += [{"engine": "k2"}]  # more than 4 cells: the planner's choice is K2 as well
         elif kind == "mfa":
-            variants += [{"RXM_MFA_ENGINE": "k2"}, {"RXM_MFA_ENGINE": "k3"}, {"RXM_MFA_ENGINE": "k4"}]
+            variants += [{"engine": "k2"}, {"engine": "k3"}, {"engine": "k4"}]
         else:
-            variants += [{"RXM_NFA_ENGINE": "bitset"}, {"RXM_NFA_ENGINE": "bitset", "RXM_K1B_WALK": "1"}]
+            variants += [{"engine": "bitset"}, {"engine": "bitset", "flags": rxm.OPT_K1B_WALK}]
         for env in variants:
-            with monkeypatch.context() as mp:
-                for k, v in env.items():
-                    mp.setenv(k, v)
-                m = rxm.Matcher(t, 0)
+            m = rxm.Matcher(t, 0, **env)
             engines_seen.add((rxm.ENGINE_NAMES[m.plan().engine], tuple(sorted(env.items()))))
             got = m.match_host(chars, off)
             assert np.array_equal(got, bits), (tag, env, [strings[i] for i in np.nonzero(got != bits)[0][:3]])

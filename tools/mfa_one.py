@@ -20,8 +20,7 @@ def _load(name):
 
 rxm, W = _load("rxm"), _load("workloads")
 case, what, n = sys.argv[1], sys.argv[2], int(sys.argv[3])
-if len(sys.argv) > 4:
-    os.environ["RXM_MFA_ENGINE"] = sys.argv[4]
+engine = sys.argv[4] if len(sys.argv) > 4 and sys.argv[4] != "auto" else None
 steps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
 dev = torch.device("cuda:0")
 if what == "config3":
@@ -29,7 +28,7 @@ if what == "config3":
 else:
     c_np, o_np = W.mixed_example_batch(int(what), n, 1000 * int(what))
     ch, of = torch.from_numpy(c_np).to(dev), torch.from_numpy(o_np.astype(np.int64)).to(dev)
-m = rxm.Matcher(rxm.Tables.load(os.path.join(ROOT, "tests", "golden", "cases", case + ".rxt")), 0)
+m = rxm.Matcher(rxm.Tables.load(os.path.join(ROOT, "tests", "golden", "cases", case + ".rxt")), 0, engine=engine)
 out = torch.empty(n, dtype=torch.uint8, device=dev)
 s = torch.cuda.current_stream().cuda_stream
 for _ in range(2):

@@ -1,5 +1,5 @@
 """Tuning helper (GPU; not part of the product or the tests): the MFA engines timed on the bench
-workloads with device-resident buffers.  RXM_MFA_ENGINE is read at upload, so the engines are compared
+workloads with device-resident buffers.  The engines (rxm_tables_upload_opts; "auto" = the planner's choice) are compared
 inside one process:  python tools/mfa_time.py [config3|config4|config5] [engines, e.g. k4,k3] [n] [steps]"""
 import importlib.util
 import os
@@ -41,11 +41,10 @@ else:
 s = torch.cuda.current_stream().cuda_stream
 ref = {}
 for eng in engines:
-    os.environ["RXM_MFA_ENGINE"] = eng
     total = 0.0
     for name, ch, of in jobs:
         nn = of.numel() - 1
-        m = rxm.Matcher(case(name), 0)
+        m = rxm.Matcher(case(name), 0, engine=None if eng == "auto" else eng)
         out = torch.empty(nn, dtype=torch.uint8, device=dev)
         for _ in range(2):
             m.match_ptrs(ch.data_ptr(), of.data_ptr(), nn, out.data_ptr(), s)
