@@ -127,8 +127,9 @@ typedef struct rxm_plan_info {
     uint32_t n_cells;
     uint32_t reversed;
     uint32_t sm_count;
-    uint32_t dfa_stride;    /* K1_DFA: input bytes per table lookup in the scan's interior (1, or 4
-                               when all literals lie in one 4-letter window and there are <= 64 sets) */
+    uint32_t dfa_stride;    /* K1_DFA: input bytes per table lookup in the scan's interior: 1; 4 when all
+                               literals lie in one 4-letter window and there are <= 64 sets; 8 when the
+                               window has two letters                                                  */
     uint32_t reserved[6];
 } rxm_plan_info;
 
@@ -143,6 +144,7 @@ int rxm_tables_upload(const rxm_tables *host_tables, int device, rxm_handle *out
 #define RXM_OPT_K1_NO_QUAD 1u   /* K1: one input byte per table lookup even where four would do          */
 #define RXM_OPT_K1B_WALK 2u     /* K1 bit-set engine: the edge-walking step instead of the follow masks   */
 #define RXM_OPT_INDEX_ORDER 4u  /* hand strings out by index, not in the tile sort's order                */
+#define RXM_OPT_K1_NO_OCT 8u    /* K1: at most four input bytes per lookup even where eight would do      */
 typedef struct rxm_upload_opts {
     uint32_t abi_version;  /* RXM_ABI_VERSION                                                             */
     uint32_t engine;       /* 0: the planner's choice; RXM_ENGINE_*: that engine                          */

@@ -176,7 +176,8 @@ extern "C" int rxm_tables_upload_opts(const rxm_tables *host_tables, int device,
         std::vector<uint8_t> table, accept;
         st = force_bitset ? RXM_ERR_UNSUPPORTED : rxm::plan_dfa(t, m->dfa, &err);
         // (a determinisation whose tables do not fit shared memory goes to the bit-set engine as well)
-        if (st == RXM_OK) st = rxm::k1_build_tables(m->dfa, m->k1, table, accept, &err, (o.flags & RXM_OPT_K1_NO_QUAD) != 0);
+        if (st == RXM_OK) st = rxm::k1_build_tables(m->dfa, m->k1, table, accept, &err, (o.flags & RXM_OPT_K1_NO_QUAD) != 0,
+                                                        (o.flags & RXM_OPT_K1_NO_OCT) != 0);
         if (st == RXM_ERR_UNSUPPORTED && o.engine != RXM_ENGINE_K1_DFA) {
             // too many active sets for a table (or forced): simulate the set itself (K1B)
             std::string berr;
@@ -210,7 +211,7 @@ extern "C" int rxm_tables_upload_opts(const rxm_tables *host_tables, int device,
         m->info.engine = RXM_ENGINE_K1_DFA;
         m->info.dfa_states = m->dfa.n_states;
         m->info.dfa_classes = m->dfa.n_classes;
-        m->info.dfa_stride = m->k1.quad ? 4 : 1;
+        m->info.dfa_stride = m->k1.quad == 2 ? 8 : (m->k1.quad ? 4 : 1);
         m->info.exact_step_differs = m->dfa.exact_step_differs;
     } else {
         st = rxm::check_mfa(t, &err);

@@ -25,7 +25,7 @@
 namespace rxm {
 
 int k1_build_tables(const DfaPlan &p, K1Tables &kt, std::vector<uint8_t> &table,
-                    std::vector<uint8_t> &accept, std::string *err, bool no_quad) {
+                    std::vector<uint8_t> &accept, std::string *err, bool no_quad, bool no_oct) {
     kt = K1Tables();
     kt.n_states = p.n_states;
     kt.n_classes = p.n_classes;
@@ -57,7 +57,22 @@ int k1_build_tables(const DfaPlan &p, K1Tables &kt, std::vector<uint8_t> &table,
                 lit_hi = std::max(lit_hi, b);
             }
         if (lit_hi < 0) lit_lo = lit_hi = 'a';
-        if (p.n_states <= 64 && lit_hi - lit_lo <= 3 && !no_quad) {
+        // Oct stride: with all literals in a TWO-letter window [lo, lo+1] a letter is one bit, and the
+        // interior takes EIGHT input bytes per lookup: O[q][code], bit i of code = (byte i of the aligned
+        // 8-byte group, memory order) - lo; composed in reading order like Q.
+        if (p.n_states <= 64 && lit_hi - lit_lo <= 1 && !no_quad && !no_oct) {
+            const uint32_t lo = uint32_t(std::min(lit_lo, 254));
+            kt.quad = 2;
+            kt.quad_lo = lo;
+            const size_t base = table.size();
+            table.resize(base + size_t(256) * sp, 0);
+            for (uint32_t q = 0; q < p.n_states; q++)
+                for (uint32_t code = 0; code < 256; code++) {
+                    uint32_t r = q;
+                    for (int k = 0; k < 8; k++) r = table[size_t(lo + ((code >> (p.reversed ? 7 - k : k)) & 1u)) * sp + r];
+                    table[base + size_t(q) * 256 + code] = uint8_t(r);
+                }
+        } else if (p.n_states <= 64 && lit_hi - lit_lo <= 3 && !no_quad) {
             const uint32_t lo = uint32_t(std::min(lit_lo, 252));
             kt.quad = 1;
             kt.quad_lo = lo;
@@ -313,6 +328,41 @@ struct QuadStep {
     }
 };
 
+// Oct stride (eight bytes per lookup; letters of a two-letter window are one bit each).  x = word - lo4
+// leaves 0 / 1 in every byte (anything else shows under 0xFE in its own or a lower byte position);
+// x0 * (2^3 + 2^10 + 2^17 + 2^24) puts the four bits of the first word at 24..27, x1 * (2^7 + 2^14 + 2^21 + 2^28)
+// those of the second at 28..31, and no two partial products of the SUM share a bit position, so nothing
+// carries: one IMAD with the other product as its addend.  Per 8 bytes: 2 IADD, 2 LOP, 2 IMAD, SHF off the
+// dependent chain, IMAD + LDS.U8 on it.
+struct OctStep {
+    static constexpr bool on = true;
+    const uint8_t *Q;   // shared-memory table O[q][code]
+    uint32_t neg_lo4;
+    __device__ __forceinline__ uint32_t pair(uint32_t q, uint32_t w0, uint32_t w1, uint32_t &bad) const {
+        const uint32_t x0 = w0 + neg_lo4, x1 = w1 + neg_lo4;
+        bad |= x0 | x1;
+        const uint32_t code = mad_lo(x1, 0x10204080u, x0 * 0x01020408u) >> 24;
+        return Q[mad_lo(q, 256u, code)];
+    }
+    template <bool REV>
+    __device__ __forceinline__ uint32_t vec(uint32_t q, const uint32_t (&w)[4], uint32_t &bad) const {
+        uint32_t b = 0;
+#ifdef RXM_K1_PROBE  // tuning builds only: the staging path without the lookups
+        bad = 0;
+        return q ^ ((w[0] ^ w[1] ^ w[2] ^ w[3]) & 1u);
+#endif
+        if (!REV) {
+            q = pair(q, w[0], w[1], b);
+            q = pair(q, w[2], w[3], b);
+        } else {
+            q = pair(q, w[2], w[3], b);
+            q = pair(q, w[0], w[1], b);
+        }
+        bad = b & 0xfefefefeu;
+        return q;
+    }
+};
+
 template <bool REV>
 __device__ __forceinline__ uint32_t vec_byte(const uint32_t (&w)[4], int k) {  // k-th byte in READING order
     const int mb = REV ? 15 - k : k;
@@ -507,31 +557,224 @@ __device__ __forceinline__ void k1_scan_body(const Step st, const Quad qd, const
     }
 }
 
-constexpr int K1_WARPS = 8;
+// ---- row-staged scan (the product's scan for direct / quad / oct tables) ---------------------------------------
+// What bounds the chunk-staged scan above is the shared-memory / L1 pipe, twice over (ncu): a
+// cp.async instruction whose 32 lanes serve 8 strings touches 8-16 different 128-byte lines, and L1 works
+// through one line per ~2 cycles; and 32 lanes looking up 32 unrelated table bytes meet in ~3.7 banks-deep
+// conflicts.  The second is the stride's business (oct: half the lookups).  The first is this body's:
+//   * a string is fetched in whole 128-byte LINES: 8 consecutive lanes copy the 8 16-byte pieces of one line,
+//     one cp.async instruction serves 4 strings = 4 lines -- the least L1 can be asked for per 512 bytes --
+//     and every sector crosses L2 -> SM once;
+//   * a lane owns a ROW of STAGES lines in shared memory, used as a ring of 16-byte vectors.  Line k of its
+//     string lands at ring vectors 8k .. 8k+7, rotated by a per-lane constant chosen so that the vector the
+//     lane reads at step v sits in bank group (lane + v) mod 8: the eight lanes of an LDS.128 phase always
+//     read eight different bank groups whatever the alignment of their strings (rows are a multiple of
+//     128 bytes apart, no padding), and the 8 pieces of a line are written to 8 different groups;
+//   * a string's first byte may stand anywhere in its first line, so a round of 8 vectors straddles lines
+//     r and r+1: line r+1 must have landed before round r is walked, lines up to r+STAGES-1 are in flight.
+// Reads: only 16-byte aligned pieces that hold at least one byte of the string.
+template <bool REV, class Step, int STAGES, class Quad>
+__device__ __forceinline__ void k1_rows_body(const Step st, const Quad qd, const uint8_t *__restrict__ chars,
+                                             const K1Rec *__restrict__ recs, uint64_t n,
+                                             uint8_t *__restrict__ out, const uint8_t *accept,
+                                             uint32_t start_state, uint32_t *__restrict__ task_counter,
+                                             uint32_t ring_base /* this warp's 32 rows, smem address */) {
+    static_assert(STAGES >= 3 && STAGES <= 8, "a round reads two lines while at least one more is in flight");
+    constexpr uint32_t RING = STAGES * 128u;  // bytes per row
+    constexpr uint32_t R16 = RING / 16u;      // vectors per row
+    constexpr int AHEAD = STAGES - 1;         // lines issued before the first round
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t sub = lane & 7u;                  // the 16-byte piece of a line this lane copies (ascending address)
+    const uint32_t msub = REV ? 7u - sub : sub;      // ... counted in reading order
+    const uint32_t row0 = ring_base + (lane >> 3) * RING;  // row of the string instruction 0 serves for this lane
+    const uint32_t my_row = ring_base + lane * RING;
+    const uint32_t ntiles = uint32_t((n + K1_TILE_STRINGS - 1) / K1_TILE_STRINGS);
 
-template <bool REV, int L, int CH, int STAGES, int NS>
-__global__ void __launch_bounds__(K1_WARPS * 32)
-k1_dfa_direct_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict__ recs, uint64_t n,
-                     uint8_t *__restrict__ out, const uint8_t *__restrict__ g_table,
-                     const uint8_t *__restrict__ g_accept, uint32_t start,
-                     uint32_t *__restrict__ task_counter) {
+    for (;;) {
+        uint32_t task = 0;
+        if (lane == 0) task = atomicAdd(task_counter, 1u);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        const uint32_t grp = task / ntiles, tile = task - grp * ntiles;  // group g of every tile before group g+1 of any
+        if (grp >= K1_TILE_STRINGS / 32u) break;
+        const uint64_t first = uint64_t(tile) * K1_TILE_STRINGS + grp * 32u;
+        const uint64_t tile_end = min(n, uint64_t(tile + 1u) * K1_TILE_STRINGS);
+        if (first >= tile_end) continue;
+
+        K1Rec rec;
+        rec.start = 0;
+        rec.len = 0;
+        rec.idx = 0xffffffffu;
+        if (first + lane < tile_end) rec = recs[first + lane];
+        uint32_t q = start_state;
+        // The lane's stream: 16-byte vectors in reading order, vector 0 the aligned one that holds the first
+        // byte read (hb pad bytes in front of it); `lead` vectors of line 0 come before vector 0.
+        // org: forward the address of line 0, reversed the END of line 0 (lines then run downwards).
+        uint64_t org;
+        uint32_t lead, hb;
+        {
+            const uint64_t a = uint64_t(reinterpret_cast<uintptr_t>(chars + rec.start));
+            if (!REV) {
+                org = a & ~uint64_t(127);
+                lead = uint32_t(a & 127u) >> 4;
+                hb = uint32_t(a & 15u);
+            } else {
+                const uint64_t e = a + rec.len;
+                org = (e + 127u) & ~uint64_t(127);
+                const uint32_t d = uint32_t(org - e);
+                lead = d >> 4;
+                hb = d & 15u;
+            }
+        }
+        const uint32_t nbytes = rec.len ? hb + rec.len : 0u;  // stream length incl. the front pad
+        const uint32_t nvec = (nbytes + 15u) >> 4;
+        const uint32_t rot = (lane - lead) & 7u;  // vector v of the stream lives at ring vector (rot + lead + v) mod R16
+        // vectors [vlo, vhi) are complete (no pad, no tail) in EVERY stream of the warp
+        const uint32_t vlo = __reduce_max_sync(0xffffffffu, hb ? 1u : 0u);
+        const uint32_t vhi = __reduce_min_sync(0xffffffffu, nbytes >> 4);
+        const uint32_t nvmax = __reduce_max_sync(0xffffffffu, nvec);
+
+        // loader state: instruction g of a round serves string 4g + lane/8
+        const uint8_t *src[8];  // this lane's piece of the next line to issue
+        uint32_t hi[8];         // pieces (reading order, counted from line 0) below this index hold bytes of the string
+        uint32_t pos[8];        // ring vector the piece goes to
+        uint32_t lo_first[8];   // line 0 only: pieces below this index lie before the string
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+            const int t = g * 4 + int(lane >> 3);
+            const uint64_t o = __shfl_sync(0xffffffffu, org, t);
+            const uint32_t ld = __shfl_sync(0xffffffffu, lead, t);
+            const uint32_t nv = __shfl_sync(0xffffffffu, nvec, t);
+            const uint32_t rt = __shfl_sync(0xffffffffu, rot, t);
+            lo_first[g] = ld;
+            hi[g] = nv ? ld + nv : 0u;
+            pos[g] = rt + msub;  // < 15 <= R16
+            src[g] = reinterpret_cast<const uint8_t *>(uintptr_t(!REV ? o + sub * 16u : o - 128u + sub * 16u));
+        }
+        uint32_t m = msub;  // reading-order index of this lane's piece in the next line to issue
+        auto issue_line = [&](bool first_line) {
+#pragma unroll
+            for (int g = 0; g < 8; g++) {
+                const bool want = m < hi[g] && (!first_line || m >= lo_first[g]);
+                cp_async16(row0 + uint32_t(g) * (4u * RING) + pos[g] * 16u, src[g], want);
+                src[g] = !REV ? src[g] + 128 : src[g] - 128;
+                pos[g] = pos[g] + 8u >= R16 ? pos[g] + 8u - R16 : pos[g] + 8u;
+            }
+            cp_async_commit();
+            m += 8u;
+        };
+
+        issue_line(true);
+#pragma unroll
+        for (int s = 1; s < AHEAD; s++) issue_line(false);
+        const uint32_t nrounds = (nvmax + 7u) >> 3;
+        uint32_t pr = rot + lead;  // ring vector of the round's first vector
+        for (uint32_t r = 0; r < nrounds; r++) {
+            issue_line(false);  // line r + AHEAD (predicated off beyond each string's end; always commits)
+            cp_async_wait<AHEAD - 1>();  // lines <= r + 1 have landed
+            __syncwarp();
+            const uint32_t v0 = r * 8u;
+            if (v0 >= vlo && v0 + 8u <= vhi) {
+                // interior round: every vector complete in every stream
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    uint32_t pj = pr + uint32_t(j);
+                    pj = pj >= R16 ? pj - R16 : pj;
+                    const uint4 v = lds128(my_row + pj * 16u);
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                    if constexpr (Quad::on) {
+                        uint32_t bad = 0;
+                        const uint32_t qf = qd.template vec<REV>(q, w, bad);
+                        if (bad) {  // a byte outside the window: this vector goes byte by byte
+#pragma unroll
+                            for (int k = 0; k < 16; k++) q = st(q, vec_byte<REV>(w, k));
+                        } else {
+                            q = qf;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 16; k++) q = st(q, vec_byte<REV>(w, k));
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t lo = (v0 + uint32_t(j)) * 16u;  // stream offset of this vector
+                    if (lo >= nbytes) continue;
+                    uint32_t pj = pr + uint32_t(j);
+                    pj = pj >= R16 ? pj - R16 : pj;
+                    const uint4 v = lds128(my_row + pj * 16u);
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                    if (lo >= hb && lo + 16u <= nbytes) {
+                        bool done = false;
+                        if constexpr (Quad::on) {
+                            uint32_t bad = 0;
+                            const uint32_t qf = qd.template vec<REV>(q, w, bad);
+                            if (!bad) {
+                                q = qf;
+                                done = true;
+                            }
+                        }
+                        if (!done) {
+#pragma unroll
+                            for (int k = 0; k < 16; k++) q = st(q, vec_byte<REV>(w, k));
+                        }
+                    } else {
+                        // boundary vector: byte k in READING order sits at stream offset lo + k
+#pragma unroll
+                        for (int k = 0; k < 16; k++) {
+                            const uint32_t at = lo + uint32_t(k);
+                            const uint32_t byte = vec_byte<REV>(w, k);
+                            if (at >= hb && at < nbytes) q = st(q, byte);
+                        }
+                    }
+                }
+            }
+            pr = pr + 8u >= R16 ? pr + 8u - R16 : pr + 8u;
+            __syncwarp();
+            // every live stream's active set is empty (automata.cpp:186-188)
+            if (__all_sync(0xffffffffu, q == 0u || (r + 1u) * 128u >= nbytes)) break;
+        }
+        cp_async_wait<0>();
+        __syncwarp();
+        if (rec.idx != 0xffffffffu) out[rec.idx] = accept[q];
+    }
+}
+
+// MODE 0: one byte per lookup (table T), 1: quad stride (T then Q), 2: oct stride (T then O)
+template <bool REV, int L, int STAGES, int WARPS, int MODE>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+k1_rows_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict__ recs, uint64_t n,
+               uint8_t *__restrict__ out, const uint8_t *__restrict__ g_table,
+               const uint8_t *__restrict__ g_accept, uint32_t start, uint32_t quad_lo,
+               uint32_t *__restrict__ task_counter) {
     constexpr uint32_t TB = 256u << L;
-    __shared__ __align__(16) uint8_t s_table[TB];   // static: its offset folds into the LDS
+    constexpr uint32_t TABLES = MODE ? 2u * TB : TB;
+    __shared__ __align__(16) uint8_t s_table[TABLES];  // static: offsets fold into the LDS
     __shared__ __align__(16) uint8_t s_accept[256];
     RXM_DYN_SMEM_128(ring);
     const uint4 *s4 = reinterpret_cast<const uint4 *>(g_table);
     uint4 *d4 = reinterpret_cast<uint4 *>(s_table);
-    for (uint32_t i = threadIdx.x; i < TB / 16; i += blockDim.x) d4[i] = s4[i];
+    for (uint32_t i = threadIdx.x; i < TABLES / 16; i += blockDim.x) d4[i] = s4[i];
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_accept[i] = g_accept[i];
     __syncthreads();
-    const uint32_t ring0 = uint32_t(__cvta_generic_to_shared(ring));
+    const uint32_t ring0 = uint32_t(__cvta_generic_to_shared(ring)) + (threadIdx.x >> 5) * (32u * STAGES * 128u);
     const DirectStep<L> st{s_table};
-    k1_scan_body<REV, DirectStep<L>, CH, STAGES, NS>(st, NoQuad(), chars, recs, n, out, s_accept, start, task_counter,
-                                                     ring0 + (threadIdx.x >> 5) * (STAGES * NS * 32 * (CH + 16)));
+    if constexpr (MODE == 2) {
+        const OctStep qd{s_table + TB, 0u - quad_lo * 0x01010101u};
+        k1_rows_body<REV, DirectStep<L>, STAGES, OctStep>(st, qd, chars, recs, n, out, s_accept, start, task_counter, ring0);
+    } else if constexpr (MODE == 1) {
+        const QuadStep qd{s_table + TB, 0u - quad_lo * 0x01010101u};
+        k1_rows_body<REV, DirectStep<L>, STAGES, QuadStep>(st, qd, chars, recs, n, out, s_accept, start, task_counter, ring0);
+    } else {
+        k1_rows_body<REV, DirectStep<L>, STAGES, NoQuad>(st, NoQuad(), chars, recs, n, out, s_accept, start, task_counter, ring0);
+    }
 }
 
-// Quad-stride variant: g_table = T[256][SP] followed by Q[SP][256].
-template <bool REV, int L, int CH, int STAGES, int WARPS>
+constexpr int K1_WARPS = 8;
+
+#ifdef RXM_TUNING
+// Chunk-staged ring with a multi-byte stride (round 1's scan): g_table = T[256][SP] followed by Q / O [SP][256].
+template <bool REV, int L, int CH, int STAGES, int WARPS, class Multi>
 __global__ void __launch_bounds__(WARPS * 32)
 k1_dfa_quad_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict__ recs, uint64_t n,
                    uint8_t *__restrict__ out, const uint8_t *__restrict__ g_table,
@@ -548,11 +791,12 @@ k1_dfa_quad_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict__ 
     __syncthreads();
     const uint32_t ring0 = uint32_t(__cvta_generic_to_shared(ring));
     const DirectStep<L> st{s_table};
-    const QuadStep qd{s_table + TB, 0u - quad_lo * 0x01010101u};
-    k1_scan_body<REV, DirectStep<L>, CH, STAGES, 1, QuadStep>(
+    const Multi qd{s_table + TB, 0u - quad_lo * 0x01010101u};
+    k1_scan_body<REV, DirectStep<L>, CH, STAGES, 1, Multi>(
         st, qd, chars, recs, n, out, s_accept, start, task_counter,
         ring0 + (threadIdx.x >> 5) * (STAGES * 32 * (CH + 16)));
 }
+#endif
 
 template <bool REV, int CH, int STAGES>
 __global__ void __launch_bounds__(K1_WARPS * 32)
@@ -573,26 +817,22 @@ k1_dfa_classed_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict
                                                   ring0 + (threadIdx.x >> 5) * (STAGES * 32 * (CH + 16)));
 }
 
-// Ring geometry.  The product library holds ONE geometry per kernel (V0 / 64-byte chunks, 2 stages, 8 warps:
-// the fastest measured); the others exist only in tuning builds (make EXTRA=-DRXM_TUNING),
-// selected there with RXM_K1_VARIANT=0..7.
+// Geometry.  The product library holds ONE geometry per kernel: rows of 3 lines, 16 warps per CTA (one CTA per SM:
+// 192 KB of rows) for the direct / quad / oct tables; the chunk-staged ring (64-byte chunks, 2 stages, 8 warps)
+// for the two-lookup tables, whose size varies.  The others exist only in tuning builds (make EXTRA=-DRXM_TUNING),
+// selected there with RXM_K1_VARIANT.
 // The dynamic shared-memory limit is a per-FUNCTION attribute: it is always set to the same value, so that
 // handles sharing a kernel instantiation may launch from several host threads (the size a launch needs is
 // checked against it).
 constexpr int K1_MAX_DYN_SMEM = 200 * 1024;
 struct V0 { static constexpr int CH = 64, STAGES = 2, NS = 1; };
 #ifdef RXM_TUNING
-struct V1 { static constexpr int CH = 32, STAGES = 2, NS = 2; };
-struct V2 { static constexpr int CH = 64, STAGES = 2, NS = 2; };
-struct V3 { static constexpr int CH = 32, STAGES = 3, NS = 2; };
-struct V4 { static constexpr int CH = 32, STAGES = 2, NS = 1; };
-
 inline int k1_variant() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("RXM_K1_VARIANT");
         v = e ? atoi(e) : 0;
-        if (v < 0 || v > 7) v = 0;
+        if (v < 0 || v > 15) v = 0;
     }
     return v;
 }
@@ -601,50 +841,21 @@ inline int k1_variant() { return 0; }
 #endif
 
 template <class Kern>
-int blocks_per_sm(Kern kern, size_t smem) {
+int blocks_per_sm(Kern kern, int threads, size_t smem) {
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, K1_WARPS * 32, smem) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem) != cudaSuccess) return 0;
     return nb;
 }
 
-template <bool REV, int L, class V>
-int launch_direct_v(const K1Tables &kt, const K1Launch &a) {
-    const size_t smem = size_t(K1_WARPS) * V::STAGES * V::NS * 32 * (V::CH + 16);
-    auto kern = k1_dfa_direct_kernel<REV, L, V::CH, V::STAGES, V::NS>;
+template <bool REV, int L, int MODE, int STAGES, int WARPS>
+int launch_rows_g(const K1Tables &kt, const K1Launch &a) {
+    const size_t smem = size_t(WARPS) * 32 * STAGES * 128;
+    static_assert(size_t(WARPS) * 32 * STAGES * 128 <= size_t(K1_MAX_DYN_SMEM), "rows fit the per-function limit");
+    auto kern = k1_rows_kernel<REV, L, STAGES, WARPS, MODE>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_MAX_DYN_SMEM) != cudaSuccess)
         return RXM_ERR_CUDA;
-    int nb = blocks_per_sm(kern, smem);
+    const int nb = blocks_per_sm(kern, WARPS * 32, smem);
     if (nb <= 0) return RXM_ERR_CUDA;
-    const uint64_t tasks = (a.n + 32 * V::NS - 1) / (32 * V::NS);
-    uint64_t blocks = uint64_t(a.sm_count) * nb;
-    const uint64_t need = (tasks + K1_WARPS - 1) / K1_WARPS;
-    if (blocks > need) blocks = need;
-    RXM_LAUNCH(kern, unsigned(blocks), K1_WARPS * 32, smem, a.stream, a.d_chars, a.d_recs, a.n, a.d_out, a.d_table, a.d_accept, kt.start, a.d_task_counter);
-    return RXM_OK;
-}
-
-template <bool REV, int L>
-int launch_direct(const K1Tables &kt, const K1Launch &a) {
-    switch (k1_variant()) {
-#ifdef RXM_TUNING
-        case 1: return launch_direct_v<REV, L, V1>(kt, a);
-        case 2: return launch_direct_v<REV, L, V2>(kt, a);
-        case 3: return launch_direct_v<REV, L, V3>(kt, a);
-        case 4: return launch_direct_v<REV, L, V4>(kt, a);
-#endif
-        default: return launch_direct_v<REV, L, V0>(kt, a);
-    }
-}
-
-template <bool REV, int L, int CH, int STAGES, int WARPS>
-int launch_quad_w(const K1Tables &kt, const K1Launch &a) {
-    const size_t smem = size_t(WARPS) * STAGES * 32 * (CH + 16);
-    auto kern = k1_dfa_quad_kernel<REV, L, CH, STAGES, WARPS>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_MAX_DYN_SMEM) != cudaSuccess)
-        return RXM_ERR_CUDA;
-    int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, WARPS * 32, smem) != cudaSuccess || nb <= 0)
-        return RXM_ERR_CUDA;
     const uint64_t tasks = (a.n + 31) / 32;
     uint64_t blocks = uint64_t(a.sm_count) * nb;
     const uint64_t need = (tasks + WARPS - 1) / WARPS;
@@ -653,37 +864,70 @@ int launch_quad_w(const K1Tables &kt, const K1Launch &a) {
     return RXM_OK;
 }
 
-template <bool REV, int L>
-int launch_quad(const K1Tables &kt, const K1Launch &a) {
-    switch (k1_variant()) {  // tuning: CTA width / ring geometry
 #ifdef RXM_TUNING
-        case 1: return launch_quad_w<REV, L, 64, 2, 16>(kt, a);
-        case 2: return launch_quad_w<REV, L, 64, 3, 10>(kt, a);
-        case 3: return launch_quad_w<REV, L, 128, 2, 11>(kt, a);
-        case 4: return launch_quad_w<REV, L, 128, 2, 8>(kt, a);
-        case 5: return launch_quad_w<REV, L, 256, 2, 6>(kt, a);
-        case 6: return launch_quad_w<REV, L, 128, 3, 7>(kt, a);
-        case 7: return launch_quad_w<REV, L, 64, 4, 10>(kt, a);
+template <bool REV, int L, int CH, int STAGES, int WARPS, class Multi>
+int launch_chunks_w(const K1Tables &kt, const K1Launch &a) {
+    const size_t smem = size_t(WARPS) * STAGES * 32 * (CH + 16);
+    auto kern = k1_dfa_quad_kernel<REV, L, CH, STAGES, WARPS, Multi>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_MAX_DYN_SMEM) != cudaSuccess)
+        return RXM_ERR_CUDA;
+    const int nb = blocks_per_sm(kern, WARPS * 32, smem);
+    if (nb <= 0) return RXM_ERR_CUDA;
+    const uint64_t tasks = (a.n + 31) / 32;
+    uint64_t blocks = uint64_t(a.sm_count) * nb;
+    const uint64_t need = (tasks + WARPS - 1) / WARPS;
+    if (blocks > need) blocks = need;
+    RXM_LAUNCH(kern, unsigned(blocks), WARPS * 32, smem, a.stream, a.d_chars, a.d_recs, a.n, a.d_out, a.d_table, a.d_accept, kt.start, kt.quad_lo, a.d_task_counter);
+    return RXM_OK;
+}
 #endif
-        default: return launch_quad_w<REV, L, 64, 2, 8>(kt, a);
+
+template <bool REV, int L, int MODE>
+int launch_rows(const K1Tables &kt, const K1Launch &a) {
+    switch (k1_variant()) {
+#ifdef RXM_TUNING
+        case 1: return launch_rows_g<REV, L, MODE, 4, 12>(kt, a);
+        case 2: return launch_rows_g<REV, L, MODE, 4, 8>(kt, a);
+        case 3: return launch_rows_g<REV, L, MODE, 3, 12>(kt, a);
+        case 4: return launch_rows_g<REV, L, MODE, 3, 8>(kt, a);
+        case 5: return launch_rows_g<REV, L, MODE, 5, 9>(kt, a);
+        case 6: return launch_rows_g<REV, L, MODE, 6, 8>(kt, a);
+        case 8:  // the chunk-staged ring of round 1 with this table's stride
+            if constexpr (MODE == 2) return launch_chunks_w<REV, L, 64, 2, 8, OctStep>(kt, a);
+            else if constexpr (MODE == 1) return launch_chunks_w<REV, L, 64, 2, 8, QuadStep>(kt, a);
+            else return RXM_ERR_INVALID;
+        case 9:
+            if constexpr (MODE == 2) return launch_chunks_w<REV, L, 128, 2, 8, OctStep>(kt, a);
+            else if constexpr (MODE == 1) return launch_chunks_w<REV, L, 128, 2, 8, QuadStep>(kt, a);
+            else return RXM_ERR_INVALID;
+#endif
+        default: return launch_rows_g<REV, L, MODE, 3, 16>(kt, a);
     }
 }
 
 template <bool REV>
 int launch_direct_l(const K1Tables &kt, const K1Launch &a) {
-    if (kt.quad) {
+    if (kt.quad == 2) {
         switch (kt.log2sp) {
-            case 4: return launch_quad<REV, 4>(kt, a);
-            case 5: return launch_quad<REV, 5>(kt, a);
-            case 6: return launch_quad<REV, 6>(kt, a);
+            case 4: return launch_rows<REV, 4, 2>(kt, a);
+            case 5: return launch_rows<REV, 5, 2>(kt, a);
+            case 6: return launch_rows<REV, 6, 2>(kt, a);
+            default: return RXM_ERR_INVALID;
+        }
+    }
+    if (kt.quad == 1) {
+        switch (kt.log2sp) {
+            case 4: return launch_rows<REV, 4, 1>(kt, a);
+            case 5: return launch_rows<REV, 5, 1>(kt, a);
+            case 6: return launch_rows<REV, 6, 1>(kt, a);
             default: return RXM_ERR_INVALID;
         }
     }
     switch (kt.log2sp) {
-        case 4: return launch_direct<REV, 4>(kt, a);
-        case 5: return launch_direct<REV, 5>(kt, a);
-        case 6: return launch_direct<REV, 6>(kt, a);
-        case 7: return launch_direct<REV, 7>(kt, a);
+        case 4: return launch_rows<REV, 4, 0>(kt, a);
+        case 5: return launch_rows<REV, 5, 0>(kt, a);
+        case 6: return launch_rows<REV, 6, 0>(kt, a);
+        case 7: return launch_rows<REV, 7, 0>(kt, a);
         default: return RXM_ERR_INVALID;
     }
 }
@@ -694,7 +938,7 @@ int launch_classed(const K1Tables &kt, const K1Launch &a) {
     auto kern = k1_dfa_classed_kernel<REV, V0::CH, V0::STAGES>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_MAX_DYN_SMEM) != cudaSuccess)
         return RXM_ERR_CUDA;
-    int nb = blocks_per_sm(kern, smem);
+    int nb = blocks_per_sm(kern, K1_WARPS * 32, smem);
     if (nb <= 0) return RXM_ERR_CUDA;
     const uint64_t tasks = (a.n + 31) / 32;
     uint64_t blocks = uint64_t(a.sm_count) * nb;

@@ -46,12 +46,14 @@ struct K1Tables {
     uint32_t reversed;
     uint32_t table_bytes;  // bytes of the device table blob (copied to shared memory)
     uint32_t accept_bytes;
-    uint32_t quad;         // K1_DIRECT with SP <= 64: the quad table Q[SP][256] follows T in the blob
-    uint32_t quad_lo;      // lowest byte value of the quad table's 4-letter window
+    uint32_t quad;         // K1_DIRECT with SP <= 64: 1 = the quad table Q[SP][256] (four bytes per lookup, 4-letter
+                           // window) follows T in the blob, 2 = the oct table O[SP][256] (eight bytes, 2-letter window)
+    uint32_t quad_lo;      // lowest byte value of the window
 };
 
 int k1_build_tables(const DfaPlan &p, K1Tables &kt, std::vector<uint8_t> &table,
-                    std::vector<uint8_t> &accept, std::string *err, bool no_quad = false);
+                    std::vector<uint8_t> &accept, std::string *err, bool no_quad = false,
+                    bool no_oct = false);
 
 // One record per string, written by the tile sort: descending length bucket within each tile.
 struct __align__(16) K1Rec {

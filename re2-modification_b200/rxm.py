@@ -52,7 +52,7 @@ class RxmUploadOpts(C.Structure):
                 ("reserved", C.c_uint32 * 4)]
 
 
-OPT_K1_NO_QUAD, OPT_K1B_WALK, OPT_INDEX_ORDER = 1, 2, 4
+OPT_K1_NO_QUAD, OPT_K1B_WALK, OPT_INDEX_ORDER, OPT_K1_NO_OCT = 1, 2, 4, 8
 ENGINE_IDS = {"k1": 1, "bitset": 2, "k2": 3, "k3": 4, "k4": 5}
 
 

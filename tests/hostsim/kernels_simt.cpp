@@ -136,8 +136,8 @@ extern "C" int hostsim_k4_batch(const rxm_tables *t, const uint8_t *chars, const
 // K1 through rxm::plan_dfa, rxm::k1_build_tables and rxm::k1_launch: the tile sort, then the scan
 // kernel the tables select (quad stride / direct / two-lookup; hostsim_k1_no_quad stands for RXM_OPT_K1_NO_QUAD, RXM_K1_VARIANT is
 // read as on the device).  info3 (may be null) <- sets, byte classes, bytes per lookup.
-static bool g_k1_no_quad = false;  // RXM_OPT_K1_NO_QUAD for the next hostsim_k1_batch calls
-extern "C" void hostsim_k1_no_quad(int on) { g_k1_no_quad = on != 0; }
+static bool g_k1_no_quad = false, g_k1_no_oct = false;  // RXM_OPT_K1_NO_QUAD / _NO_OCT for the next hostsim_k1_batch calls
+extern "C" void hostsim_k1_no_quad(int on) { g_k1_no_quad = (on & 1) != 0; g_k1_no_oct = (on & 2) != 0; }
 extern "C" int hostsim_k1_batch(const rxm_tables *t, const uint8_t *chars, const uint64_t *off, uint64_t n,
                                 uint8_t *out, uint64_t limit, unsigned long long *overflow_out, uint32_t *info3,
                                 char *msg_out, uint32_t msg_cap, uint64_t seed) {
@@ -147,12 +147,12 @@ extern "C" int hostsim_k1_batch(const rxm_tables *t, const uint8_t *chars, const
     if (st != RXM_OK) return st;
     rxm::K1Tables kt;
     std::vector<uint8_t> table, accept;
-    st = rxm::k1_build_tables(p, kt, table, accept, &err, g_k1_no_quad);
+    st = rxm::k1_build_tables(p, kt, table, accept, &err, g_k1_no_quad, g_k1_no_oct);
     if (st != RXM_OK) return st;
     if (info3) {
         info3[0] = p.n_states;
         info3[1] = p.n_classes;
-        info3[2] = kt.quad ? 4 : 1;
+        info3[2] = kt.quad == 2 ? 8 : (kt.quad ? 4 : 1);
     }
     table.resize(table.size() + 64);  // the kernels copy whole 16-byte vectors
     accept.resize(accept.size() + 256);

@@ -28,7 +28,8 @@ text = open(os.path.join(ROOT, "tests", "golden", "cases", "nfa_config2.rxt")).r
 t = rxm.Tables(text)
 chars, off = W.alive_strings(text, n, 64, 4096, 5, "cuda")
 out = torch.empty(n, dtype=torch.uint8, device="cuda")
-m = rxm.Matcher(t, 0)
+flags = int(os.environ.get("RXM_K1_FLAGS", "0"))  # rxm.OPT_K1_NO_OCT = 8, OPT_K1_NO_QUAD = 1
+m = rxm.Matcher(t, 0, flags=flags)
 s = torch.cuda.current_stream().cuda_stream
 for _ in range(5):
     m.match_ptrs(chars.data_ptr(), off.data_ptr(), n, out.data_ptr(), s)
@@ -41,5 +42,6 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
 nbytes = int(off[-1].item())
-print(f"variant={os.environ.get('RXM_K1_VARIANT', '0')} stride={m.plan().dfa_stride} ms/step={ms:.4f} "
-      f"input_GB/s={nbytes / ms / 1e6:.0f} match_frac={float(out.float().mean()):.4f}")
+w = torch.arange(1, n + 1, device="cuda", dtype=torch.int64) % 1000003
+print(f"lib={os.path.basename(rxm.LIB_PATH)} variant={os.environ.get('RXM_K1_VARIANT', '0')} stride={m.plan().dfa_stride} ms/step={ms:.4f} "
+      f"input_GB/s={nbytes / ms / 1e6:.0f} match_frac={float(out.float().mean()):.4f} checksum={int((out.to(torch.int64) * w).sum())}")
