@@ -121,10 +121,26 @@ extern "C" int rxm_tables_upload(const rxm_tables *host_tables, int device, rxm_
     return rxm_tables_upload_opts(host_tables, device, nullptr, out);
 }
 
+static int upload_impl(const rxm_tables *host_tables, int device, const rxm_upload_opts *opts, rxm_handle *out,
+                       rxm_matcher **in_flight);
+
+// never throws: an allocation failure inside the planner's containers is RXM_ERR_NOMEM, nothing leaks
 extern "C" int rxm_tables_upload_opts(const rxm_tables *host_tables, int device, const rxm_upload_opts *opts,
                                       rxm_handle *out) {
     if (!out) return RXM_ERR_INVALID;
     *out = nullptr;
+    rxm_matcher *in_flight = nullptr;
+    try {
+        return upload_impl(host_tables, device, opts, out, &in_flight);
+    } catch (...) {
+        if (in_flight) rxm_free(in_flight);
+        *out = nullptr;
+        return RXM_ERR_NOMEM;
+    }
+}
+
+static int upload_impl(const rxm_tables *host_tables, int device, const rxm_upload_opts *opts, rxm_handle *out,
+                       rxm_matcher **in_flight) {
     rxm_upload_opts o{};
     if (opts) {
         if (opts->abi_version != RXM_ABI_VERSION) return RXM_ERR_INVALID;
@@ -148,6 +164,7 @@ extern "C" int rxm_tables_upload_opts(const rxm_tables *host_tables, int device,
 
     rxm_matcher *m = new (std::nothrow) rxm_matcher();
     if (!m) return RXM_ERR_NOMEM;
+    *in_flight = m;
     m->device = device;
     m->sm_count = prop.multiProcessorCount;
     m->tables.assign(*host_tables);
@@ -161,6 +178,7 @@ extern "C" int rxm_tables_upload_opts(const rxm_tables *host_tables, int device,
 
     auto fail = [&](int code) {
         if (!err.empty()) std::snprintf(g_cuda_err, sizeof g_cuda_err, "%s", err.c_str());
+        *in_flight = nullptr;
         rxm_free(m);
         return code;
     };
@@ -264,6 +282,7 @@ planned:
         return fail(cuda_fail(cudaGetLastError(), "cudaMalloc overflow counter"));
     if (cudaMemset(m->d_overflow, 0, 2 * sizeof(unsigned long long)) != cudaSuccess)
         return fail(cuda_fail(cudaGetLastError(), "cudaMemset overflow counter"));
+    *in_flight = nullptr;
     *out = m;
     return RXM_OK;
 }

@@ -118,7 +118,9 @@ __host__ __device__ __forceinline__ uint32_t len_bucket(uint32_t len) {
     return 128u + (e - 7u) * 64u + ((len >> (e - 6u)) & 63u);
 }
 
-__device__ __forceinline__ uint32_t clamp_len(uint64_t len) { return len >= 0x7fffffffull ? 0u : uint32_t(len); }
+// strings of 2^31-1 bytes and more are not scanned: their record carries this length, their bit is 0 (rxm.h)
+constexpr uint32_t K1_LEN_OVERFLOW = 0x7fffffffu;
+__device__ __forceinline__ uint32_t clamp_len(uint64_t len) { return len >= 0x7fffffffull ? K1_LEN_OVERFLOW : uint32_t(len); }
 
 // One kernel: every tile of K1_TILE consecutive strings is counting-sorted by DESCENDING length
 // bucket inside shared memory and written out as K1_TILE records (strings are not moved).
@@ -210,6 +212,47 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gsrc, 
         "l"(gsrc), "r"(int(pred))
         : "memory");
 }
+// The same with an L2 eviction policy.  The row-staged scan reads every byte once: evict_first lets the streamed
+// lines leave L2 ahead of the 256-byte blocks two neighbouring strings share (measured: -2.5 % per step).
+__device__ __forceinline__ void cp_async16_pol(uint32_t smem_dst, const void *gsrc, bool pred, uint64_t pol) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t"
+        "@p cp.async.cg.shared.global.L2::cache_hint.L2::256B [%0], [%1], 16, %3;\n\t}\n" ::"r"(smem_dst),
+        "l"(gsrc), "r"(int(pred)), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+#ifdef RXM_TUNING  // tuning builds: the other L2 fetch granules, and an L2 prefetch of the line at p
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void cp_async16_128(uint32_t smem_dst, const void *gsrc, bool pred) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t"
+        "@p cp.async.cg.shared.global.L2::128B [%0], [%1], 16;\n\t}\n" ::"r"(smem_dst),
+        "l"(gsrc), "r"(int(pred))
+        : "memory");
+}
+__device__ __forceinline__ void cp_async16_plain(uint32_t smem_dst, const void *gsrc, bool pred) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t"
+        "@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}\n" ::"r"(smem_dst),
+        "l"(gsrc), "r"(int(pred))
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p, bool pred) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %1, 0;\n\t"
+        "@p prefetch.global.L2 [%0];\n\t}\n" ::"l"(p), "r"(int(pred))
+        : "memory");
+}
+#endif
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -230,6 +273,8 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 inline void cp_async16(uint32_t smem_dst, const void *gsrc, bool pred) {
     if (pred) memcpy(simt::shared_ptr(smem_dst), gsrc, 16);
 }
+inline void cp_async16_pol(uint32_t smem_dst, const void *gsrc, bool pred, uint64_t) { cp_async16(smem_dst, gsrc, pred); }
+inline uint64_t policy_evict_first() { return 0; }
 inline void cp_async_commit() {}
 template <int N>
 inline void cp_async_wait() {}
@@ -429,6 +474,11 @@ __device__ __forceinline__ void k1_scan_body(const Step st, const Quad qd, const
             rec.len = 0;
             rec.idx = 0xffffffffu;
             if (first + uint32_t(s) * 32u + lane < tile_end) rec = recs[first + uint32_t(s) * 32u + lane];
+            if (rec.len == K1_LEN_OVERFLOW) {  // reported by the tile sort; bit 0
+                out[rec.idx] = 0;
+                rec.len = 0;
+                rec.idx = 0xffffffffu;
+            }
             idx[s] = rec.idx;
             q[s] = start_state;
             const uint8_t *p = chars + rec.start;
@@ -589,13 +639,25 @@ __device__ __forceinline__ void k1_rows_body(const Step st, const Quad qd, const
     const uint32_t row0 = ring_base + (lane >> 3) * RING;  // row of the string instruction 0 serves for this lane
     const uint32_t my_row = ring_base + lane * RING;
     const uint32_t ntiles = uint32_t((n + K1_TILE_STRINGS - 1) / K1_TILE_STRINGS);
+    const uint64_t pol_first = policy_evict_first();
+#if defined(RXM_TUNING) && defined(RXM_K1_HINT) && RXM_K1_HINT == 4
+    const uint64_t pol_last = policy_evict_last();
+#endif
 
     for (;;) {
         uint32_t task = 0;
         if (lane == 0) task = atomicAdd(task_counter, 1u);
         task = __shfl_sync(0xffffffffu, task, 0);
-        const uint32_t grp = task / ntiles, tile = task - grp * ntiles;  // group g of every tile before group g+1 of any
+        // Tile-major: the 128 groups of a tile are handed out together, so the 256-byte blocks that neighbouring
+        // strings share are fetched while their first reader's copy is still in L2 (-3.5 % per step against
+        // "group g of every tile first"); within a tile the long groups come first.
+#if defined(RXM_TUNING) && defined(RXM_K1_ORDER) && RXM_K1_ORDER == 0
+        const uint32_t grp = task / ntiles, tile = task - grp * ntiles;
         if (grp >= K1_TILE_STRINGS / 32u) break;
+#else
+        const uint32_t tile = task / (K1_TILE_STRINGS / 32u), grp = task % (K1_TILE_STRINGS / 32u);
+        if (tile >= ntiles) break;
+#endif
         const uint64_t first = uint64_t(tile) * K1_TILE_STRINGS + grp * 32u;
         const uint64_t tile_end = min(n, uint64_t(tile + 1u) * K1_TILE_STRINGS);
         if (first >= tile_end) continue;
@@ -605,6 +667,11 @@ __device__ __forceinline__ void k1_rows_body(const Step st, const Quad qd, const
         rec.len = 0;
         rec.idx = 0xffffffffu;
         if (first + lane < tile_end) rec = recs[first + lane];
+        if (rec.len == K1_LEN_OVERFLOW) {  // reported by the tile sort; bit 0
+            out[rec.idx] = 0;
+            rec.len = 0;
+            rec.idx = 0xffffffffu;
+        }
         uint32_t q = start_state;
         // The lane's stream: 16-byte vectors in reading order, vector 0 the aligned one that holds the first
         // byte read (hb pad bytes in front of it); `lead` vectors of line 0 come before vector 0.
@@ -655,7 +722,24 @@ __device__ __forceinline__ void k1_rows_body(const Step st, const Quad qd, const
 #pragma unroll
             for (int g = 0; g < 8; g++) {
                 const bool want = m < hi[g] && (!first_line || m >= lo_first[g]);
+#if defined(RXM_TUNING) && defined(RXM_K1_HINT)
+#if RXM_K1_HINT == 0
+                cp_async16_plain(row0 + uint32_t(g) * (4u * RING) + pos[g] * 16u, src[g], want);
+#elif RXM_K1_HINT == 128
+                cp_async16_128(row0 + uint32_t(g) * (4u * RING) + pos[g] * 16u, src[g], want);
+#elif RXM_K1_HINT == 4  // the 256-byte blocks a string shares with its neighbours stay in L2, the others leave first
+                const bool inner = m >= lo_first[g] + 16u && m + 16u < hi[g];
+                cp_async16_pol(row0 + uint32_t(g) * (4u * RING) + pos[g] * 16u, src[g], want, inner ? pol_first : pol_last);
+#elif RXM_K1_HINT == 6  // no eviction policy
                 cp_async16(row0 + uint32_t(g) * (4u * RING) + pos[g] * 16u, src[g], want);
+#else  // 256-byte granule only where the whole 256-byte block lies inside the string
+                const bool inner = m >= lo_first[g] + 16u && m + 16u < hi[g];
+                cp_async16(row0 + uint32_t(g) * (4u * RING) + pos[g] * 16u, src[g], want && inner);
+                cp_async16_plain(row0 + uint32_t(g) * (4u * RING) + pos[g] * 16u, src[g], want && !inner);
+#endif
+#else
+                cp_async16_pol(row0 + uint32_t(g) * (4u * RING) + pos[g] * 16u, src[g], want, pol_first);
+#endif
                 src[g] = !REV ? src[g] + 128 : src[g] - 128;
                 pos[g] = pos[g] + 8u >= R16 ? pos[g] + 8u - R16 : pos[g] + 8u;
             }
@@ -670,6 +754,13 @@ __device__ __forceinline__ void k1_rows_body(const Step st, const Quad qd, const
         uint32_t pr = rot + lead;  // ring vector of the round's first vector
         for (uint32_t r = 0; r < nrounds; r++) {
             issue_line(false);  // line r + AHEAD (predicated off beyond each string's end; always commits)
+#if defined(RXM_TUNING) && defined(RXM_K1_PF)
+            {   // the lane's own string: line (r + AHEAD + PF) into L2
+                const uint32_t kk = r + uint32_t(AHEAD) + uint32_t(RXM_K1_PF);
+                const uint64_t pa = !REV ? org + uint64_t(kk) * 128u : org - uint64_t(kk + 1u) * 128u;
+                prefetch_l2(reinterpret_cast<const void *>(uintptr_t(pa)), kk * 8u < lead + nvec && nvec != 0u);
+            }
+#endif
             cp_async_wait<AHEAD - 1>();  // lines <= r + 1 have landed
             __syncwarp();
             const uint32_t v0 = r * 8u;
@@ -824,7 +915,7 @@ k1_dfa_classed_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict
 // The dynamic shared-memory limit is a per-FUNCTION attribute: it is always set to the same value, so that
 // handles sharing a kernel instantiation may launch from several host threads (the size a launch needs is
 // checked against it).
-constexpr int K1_MAX_DYN_SMEM = 200 * 1024;
+constexpr int K1_MAX_DYN_SMEM = 216 * 1024;
 struct V0 { static constexpr int CH = 64, STAGES = 2, NS = 1; };
 #ifdef RXM_TUNING
 inline int k1_variant() {
@@ -892,6 +983,7 @@ int launch_rows(const K1Tables &kt, const K1Launch &a) {
         case 4: return launch_rows_g<REV, L, MODE, 3, 8>(kt, a);
         case 5: return launch_rows_g<REV, L, MODE, 5, 9>(kt, a);
         case 6: return launch_rows_g<REV, L, MODE, 6, 8>(kt, a);
+        case 7: return launch_rows_g<REV, L, MODE, 3, 18>(kt, a);
         case 8:  // the chunk-staged ring of round 1 with this table's stride
             if constexpr (MODE == 2) return launch_chunks_w<REV, L, 64, 2, 8, OctStep>(kt, a);
             else if constexpr (MODE == 1) return launch_chunks_w<REV, L, 64, 2, 8, QuadStep>(kt, a);

@@ -51,7 +51,7 @@ extern "C" int rxm_tables_validate(const rxm_tables *t) {
     return RXM_OK;
 }
 
-extern "C" int rxm_tables_format(const rxm_tables *t, char *buf, size_t buf_size, size_t *needed) {
+static int tables_format_impl(const rxm_tables *t, char *buf, size_t buf_size, size_t *needed) {
     int st = rxm_tables_validate(t);
     if (st != RXM_OK) return st;
     std::ostringstream os;
@@ -97,7 +97,7 @@ struct Block {  // one allocation: header + arrays
 };
 }  // namespace
 
-extern "C" int rxm_tables_parse(const char *text, size_t len, rxm_tables **out) {
+static int tables_parse_impl(const char *text, size_t len, rxm_tables **out) {
     if (!text || !out) return RXM_ERR_INVALID;
     *out = nullptr;
     std::istringstream is(std::string(text, len));
@@ -138,7 +138,7 @@ extern "C" int rxm_tables_parse(const char *text, size_t len, rxm_tables **out) 
         uint32_t from, to;
         std::string kind, sym, act;
         if (!(ls >> from >> kind >> sym >> to) || kind.size() != 1) return RXM_ERR_PARSE;
-        if (from >= states || from < cur_from) return RXM_ERR_PARSE;
+        if (from >= states || to >= states || from < cur_from) return RXM_ERR_PARSE;  // (before `to` is narrowed)
         while (cur_from < from) h.edge_begin[++cur_from] = seen;
         uint8_t k;
         switch (kind[0]) {
@@ -216,6 +216,28 @@ extern "C" int rxm_tables_parse(const char *text, size_t len, rxm_tables **out) 
     }
     *out = t;
     return RXM_OK;
+}
+
+// The C entry points never throw: an allocation failure inside the C++ containers is RXM_ERR_NOMEM.
+extern "C" int rxm_tables_format(const rxm_tables *t, char *buf, size_t buf_size, size_t *needed) {
+    try {
+        return tables_format_impl(t, buf, buf_size, needed);
+    } catch (const std::bad_alloc &) {
+        return RXM_ERR_NOMEM;
+    } catch (...) {
+        return RXM_ERR_INVALID;
+    }
+}
+extern "C" int rxm_tables_parse(const char *text, size_t len, rxm_tables **out) {
+    try {
+        return tables_parse_impl(text, len, out);
+    } catch (const std::bad_alloc &) {
+        if (out) *out = nullptr;
+        return RXM_ERR_NOMEM;
+    } catch (...) {
+        if (out) *out = nullptr;
+        return RXM_ERR_PARSE;
+    }
 }
 
 extern "C" void rxm_tables_release(rxm_tables *t) { std::free(t); }

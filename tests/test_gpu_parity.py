@@ -193,11 +193,11 @@ def test_k1_every_length_and_alignment(name):
     m.close()
 
 
-@pytest.mark.parametrize("name", ["nfa_config2", "nfa_quirk", "nfa_abb", "nfa_dots", "nfa_third"])
+@pytest.mark.parametrize("name", ["nfa_config2", "nfa_quirk", "nfa_abb", "nfa_dots", "nfa_third", "nfa_alt"])
 def test_k1_quad_stride_and_bytes_outside_the_window(name):
-    """The four-bytes-per-lookup interior (dfa_stride 4) against the oracle and against the
-    one-byte scan (RXM_OPT_K1_NO_QUAD), on long strings that stay alive and carry bytes outside
-    the 4-letter window -- singly, in every position of a 16-byte vector, and in runs."""
+    """The eight- and four-bytes-per-lookup interiors (dfa_stride 8 / 4) against the oracle and against
+    the one-byte scan (RXM_OPT_K1_NO_QUAD), on long strings that stay alive and carry bytes outside
+    the stride's letter window -- singly, in every position of a 16-byte vector, and in runs."""
     t, _, _ = load_case(name)
     rng = np.random.default_rng(5)
     ab = np.frombuffer(b"ab", dtype=np.uint8)
@@ -226,14 +226,20 @@ def test_k1_quad_stride_and_bytes_outside_the_window(name):
     stride = m.plan().dfa_stride
     got = m.match_host(chars, off)
     m.close()
+    m4 = rxm.Matcher(t, 0, flags=rxm.OPT_K1_NO_OCT)
+    stride4 = m4.plan().dfa_stride
+    got4 = m4.match_host(chars, off)
+    m4.close()
     m1 = rxm.Matcher(t, 0, flags=rxm.OPT_K1_NO_QUAD)
     assert m1.plan().dfa_stride == 1
     got1 = m1.match_host(chars, off)
     m1.close()
     assert np.array_equal(got1, want)
+    assert np.array_equal(got4, want), (stride4, int((got4 != want).sum()))
     assert np.array_equal(got, want), (stride, int((got != want).sum()))
-    if name == "nfa_config2":
-        assert stride == 4
+    assert stride4 in (1, 4) and stride in (stride4, 8)
+    if name in ("nfa_config2", "nfa_abb"):  # literals a, b only: eight bytes per lookup, four on request
+        assert stride == 8 and stride4 == 4
 
 
 @pytest.mark.parametrize("mode", ["masks", "walk"])
