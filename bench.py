@@ -710,6 +710,7 @@ def main():
         step_device()
         torch.cuda.synchronize()
     launches0 = R.launch_count()
+    torch.cuda.cudart().cudaProfilerStart()  # `ncu --profile-from-start off`: exactly the timed steps' launches
     if strong:
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -726,6 +727,7 @@ def main():
         step_ms, local_total, flush = R.time_steps(args.steps, total_bytes, dev)
         barrier()
         total_ms = max_over_ranks(local_total)
+    torch.cuda.cudart().cudaProfilerStop()
     launches = R.launch_count() - launches0
     while time.perf_counter() - t_pad < 1.2:
         step_device()

@@ -146,7 +146,7 @@ k1_tilesort_kernel(const Spans sp, uint64_t n, K1Rec *__restrict__ recs,
         __syncthreads();
         const uint64_t lo = tile * K1_TILE;
         uint64_t beg[K1_SORT_PER_THREAD];
-        uint32_t len[K1_SORT_PER_THREAD], bkt[K1_SORT_PER_THREAD];
+        uint32_t len[K1_SORT_PER_THREAD], bkt[K1_SORT_PER_THREAD], rank[K1_SORT_PER_THREAD];
 #pragma unroll
         for (int k = 0; k < K1_SORT_PER_THREAD; k++) {
             const uint64_t i = lo + uint32_t(k) * K1_SORT_THREADS + t;
@@ -157,7 +157,7 @@ k1_tilesort_kernel(const Spans sp, uint64_t n, K1Rec *__restrict__ recs,
                 if (l >= 0x7fffffffull && overflow) atomicAdd(overflow, 1ull);
                 len[k] = clamp_len(l);
                 bkt[k] = len_bucket(len[k]);
-                atomicAdd(&cnt[bkt[k]], 1u);
+                rank[k] = atomicAdd(&cnt[bkt[k]], 1u);  // its place among the strings of the bucket
             }
         }
         __syncthreads();
@@ -189,7 +189,7 @@ k1_tilesort_kernel(const Spans sp, uint64_t n, K1Rec *__restrict__ recs,
 #pragma unroll
         for (int k = 0; k < K1_SORT_PER_THREAD; k++) {
             if (bkt[k] == 0xffffffffu) continue;
-            const uint32_t slot = atomicAdd(&cnt[bkt[k]], 1u);
+            const uint32_t slot = cnt[bkt[k]] + rank[k];
             K1Rec r;
             r.start = beg[k];
             r.len = len[k];

@@ -92,6 +92,26 @@ extern "C" int hostsim_k3_batch(const rxm_tables *t, const uint8_t *chars, const
     return run.finish(st, msg_out, msg_cap);
 }
 
+// rxm_k4.cu: k4_coop_verify (phase A's verification by the whole warp) on its own: case k asks for the first
+// j in [vp[k], vcap[k]) with s[j] != s[j - delta[k]] in the string s = chars[beg[k], beg[k] + len[k]).
+namespace {
+__global__ void coop_verify_kernel(const uint8_t *chars, const uint64_t *beg, const uint32_t *len, const uint32_t *delta,
+                                   const uint32_t *vp, const uint32_t *vcap, uint32_t cases, uint32_t *result) {
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t k = 0; k < cases; k++) {
+        const uint32_t r = rxm::k4_coop_verify(chars + beg[k], len[k], delta[k], vp[k], vcap[k], lane);
+        if (lane == (k & 31u)) result[k] = r;
+    }
+}
+}  // namespace
+extern "C" int hostsim_coop_verify(const uint8_t *chars, const uint64_t *beg, const uint32_t *len, const uint32_t *delta,
+                                   const uint32_t *vp, const uint32_t *vcap, uint32_t cases, uint32_t *result,
+                                   char *msg_out, uint32_t msg_cap, uint64_t seed) {
+    Run run(2000000000ull, seed);
+    RXM_LAUNCH(coop_verify_kernel, 1, 32, 0, nullptr, chars, beg, len, delta, vp, vcap, cases, result);
+    return run.finish(0, msg_out, msg_cap);
+}
+
 // K4 through rxm::k4_launch (128-thread blocks, per-thread sets of `maxl` slots in emulated shared
 // memory), then -- as rxm_api.cu does -- K3 over the strings K4 handed on (the redo list) when the
 // automaton has more nodes than a thread has slots.  redo_out (may be null) <- strings handed on.

@@ -267,3 +267,49 @@ def test_k4_emulated_on_config3_strings():
     assert rc == 0 and ovf == 0 and redo == 0, msg
     assert np.array_equal(got, want)
     assert 0 < int(want.sum()) < len(strings)
+
+
+def test_warp_cooperative_periodicity_check_every_alignment_and_distance():
+    """rxm_k4.cu: k4_coop_verify -- phase A's check `s[j] == s[j - delta] for j in [vp, vcap)` done by a whole
+    warp, 16-byte vectors, the stream delta bytes back picked with a loop-invariant word offset and funnel
+    shifts -- on the SIMT emulator against numpy: every start alignment mod 16, distances 1..70 and a few
+    thousand, differences planted before, at, and after the window's ends, windows shorter than a vector
+    and longer than a round."""
+    rng = np.random.default_rng(31)
+    chunks, beg, ln, dl, vps, vcs, want = [], [], [], [], [], [], []
+    pos = 0
+    lead = 16
+    for case in range(1500):
+        delta = int(rng.choice([1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 32, 33, 63, 64, 70, 1000, 4097])) if case % 3 else int(rng.integers(1, 71))
+        reps = int(rng.integers(1, 60)) if delta < 100 else int(rng.integers(1, 3))
+        n = delta * (reps + 1) + int(rng.integers(0, delta + 1))
+        unit = rng.integers(97, 100, size=delta).astype(np.uint8)
+        s = np.resize(unit, n).copy()
+        for _ in range(int(rng.integers(0, 3))):  # planted differences
+            s[int(rng.integers(0, n))] = 122
+        vp = int(rng.integers(delta, n + 1))
+        vcap = int(rng.integers(vp, n + 1))
+        j = np.arange(vp, vcap)
+        bad = j[s[j] != s[j - delta]]
+        want.append(int(bad[0]) if len(bad) else vcap)
+        shift = int(rng.integers(0, 16))  # every alignment of the string's first byte
+        chunks.append(np.full(shift, 35, dtype=np.uint8))
+        pos += shift
+        beg.append(pos)
+        chunks.append(s)
+        pos += n
+        ln.append(n); dl.append(delta); vps.append(vp); vcs.append(vcap)
+    chars = np.concatenate([np.full(lead, 36, dtype=np.uint8)] + chunks + [np.full(32, 37, dtype=np.uint8)])
+    beg = np.asarray(beg, dtype=np.uint64)
+    arrs = [np.asarray(a, dtype=np.uint32) for a in (ln, dl, vps, vcs)]
+    res = np.zeros(len(want), dtype=np.uint32)
+    L = hostsim()
+    L.hostsim_coop_verify.argtypes = [C.c_void_p] * 6 + [C.c_uint32, C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint64]
+    L.hostsim_coop_verify.restype = C.c_int
+    for seed in (0, 9):
+        msg = C.create_string_buffer(600)
+        rc = L.hostsim_coop_verify(chars.ctypes.data + lead, beg.ctypes.data, arrs[0].ctypes.data, arrs[1].ctypes.data,
+                                   arrs[2].ctypes.data, arrs[3].ctypes.data, len(want), res.ctypes.data, msg, 600, seed)
+        assert rc == 0, msg.value.decode()
+        diff = np.nonzero(res != np.asarray(want, dtype=np.uint32))[0]
+        assert len(diff) == 0, [(int(k), int(res[k]), want[k], dl[k], vps[k], vcs[k], ln[k]) for k in diff[:5]]
