@@ -22,10 +22,18 @@ constexpr uint32_t K4_CHUNK = 64;  // tickets a warp takes from the global count
 // issue); here a round trip is 1 KB of consecutive addresses -- 32 lanes x one aligned 16-byte vector x 2 in
 // flight -- and the vectors delta bytes back come from lines this warp has just read.  The stream delta bytes back
 // stands at a fixed byte offset against the 16-byte grid, so its five words per vector are picked with a
-// warp-uniform, loop-invariant word offset (WO: a template parameter, chosen once) and one funnel shift each.
+// warp-uniform, loop-invariant word offset (selects on three uniform predicates: four copies of the loop, one per
+// offset, cost more in instruction-cache misses than they saved -- ncu: no_instruction 10.7 per issue) and one
+// funnel shift each.
 // Only aligned 16-byte vectors that hold a byte of the string are loaded.  Warp-uniform arguments and result;
 // needs vp >= delta.
-constexpr uint32_t K4_COOP_MIN = 128;  // bytes still to verify from which a string can be worth the warp's time
+#ifndef RXM_K4_COOP_MIN  // (tuning builds set these two)
+#define RXM_K4_COOP_MIN 512
+#endif
+#ifndef RXM_K4_COOP_PER_LANE
+#define RXM_K4_COOP_PER_LANE 48
+#endif
+constexpr uint32_t K4_COOP_MIN = RXM_K4_COOP_MIN;  // bytes still to verify from which a string can be worth the warp's time
 constexpr int K4_COOP_UNROLL = 2;
 
 __device__ __forceinline__ uint4 k4_ld128(const uint8_t *p) {  // p is 16-byte aligned
@@ -35,53 +43,45 @@ __device__ __forceinline__ uint4 k4_ld128(const uint8_t *p) {  // p is 16-byte a
     return *reinterpret_cast<const uint4 *>(p);
 #endif
 }
-// the bytes [lo, hi) of a 16-byte vector that fall into its word k, as a byte mask of that word
+// the bytes [lo, hi) of a 16-byte vector that fall into its word k, as a byte mask of that word (branch-free)
 __device__ __forceinline__ uint32_t k4_word_mask(uint32_t lo, uint32_t hi, uint32_t k) {
-    const int a = int(lo) - int(4u * k), z = int(hi) - int(4u * k);
-    if (a >= 4 || z <= 0) return 0u;
-    uint32_t m = 0xffffffffu;
-    if (a > 0) m &= 0xffffffffu << (8 * a);
-    if (z < 4) m &= (1u << (8 * z)) - 1u;
-    return m;
+    const int a = min(max(int(lo) - int(4u * k), 0), 4), z = min(max(int(hi) - int(4u * k), 0), 4);
+    return uint32_t(~0ull << (8 * a)) & uint32_t((1ull << (8 * z)) - 1ull);
 }
 
-template <int I>
-__device__ __forceinline__ uint32_t k4_pick(const uint4 &a0, const uint4 &a1) {  // word I of the eight
-    if constexpr (I == 0) return a0.x;
-    else if constexpr (I == 1) return a0.y;
-    else if constexpr (I == 2) return a0.z;
-    else if constexpr (I == 3) return a0.w;
-    else if constexpr (I == 4) return a1.x;
-    else if constexpr (I == 5) return a1.y;
-    else if constexpr (I == 6) return a1.z;
-    else return a1.w;  // (I == 8 is only asked for when the streams are word-aligned: never shifted in)
-}
-
-template <int WO>
-__device__ __forceinline__ uint32_t k4_coop_loop(const uint8_t *s, const uint8_t *end, const uint8_t *b, const uint8_t *lim,
-                                                 const uint8_t *base0, uint32_t delta, uint32_t sh16, uint32_t lane) {
+__device__ __forceinline__ uint32_t k4_coop_verify(const uint8_t *s, uint32_t n, uint32_t delta, uint32_t vp, uint32_t vcap,
+                                                   uint32_t lane) {
+    // 32-bit offsets from an aligned origin 16..31 bytes before the string (so that nothing below goes negative)
+    const uint32_t lo_s = 16u + uint32_t(reinterpret_cast<uintptr_t>(s) & 15u);  // the string is [lo_s, end_s)
+    const uint8_t *org = s - lo_s;
+    const uint32_t end_s = lo_s + n, b = lo_s + vp, lim = lo_s + vcap;
+    const uint32_t sh16 = (b - delta) & 15u;  // == (any 16-aligned offset - delta) & 15: where the stream delta back stands
     const uint32_t bo8 = (sh16 & 3u) * 8u;
+    const bool w1 = (sh16 >> 2) == 1u, w2 = (sh16 >> 2) == 2u, w3 = (sh16 >> 2) == 3u;  // (uniform: selects, not branches)
     constexpr uint32_t NONE = 0xffffffffu;
-    for (const uint8_t *base = base0; base < lim; base += 512 * K4_COOP_UNROLL) {
+    for (uint32_t base = b & ~15u; base < lim; base += 512u * K4_COOP_UNROLL) {  // (warp-uniform)
         uint32_t at[K4_COOP_UNROLL];  // where this lane's vector differs first (offset into the string), or NONE
 RXM_UNROLL
         for (int u = 0; u < K4_COOP_UNROLL; u++) {
-            const uint8_t *c = base + 512 * u + 16u * lane;  // this lane's vector of the stream
+            const uint32_t c = base + 512u * uint32_t(u) + 16u * lane;  // this lane's vector of the stream
             at[u] = NONE;
             if (c < lim) {
-                const uint4 w = k4_ld128(c);
-                const uint8_t *A = c - delta - sh16;  // aligned: the two vectors that hold [c - delta, c - delta + 16)
+                const uint4 w = k4_ld128(org + c);
+                const uint32_t A = c - delta - sh16;  // aligned: the two vectors that hold [c - delta, c - delta + 16)
                 const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-                const uint4 a0 = (A + 16 > s) ? k4_ld128(A) : z;
-                const uint4 a1 = (sh16 != 0u && A + 16 < end) ? k4_ld128(A + 16) : z;
-                const uint32_t v0 = k4_pick<WO>(a0, a1), v1 = k4_pick<WO + 1>(a0, a1), v2 = k4_pick<WO + 2>(a0, a1),
-                               v3 = k4_pick<WO + 3>(a0, a1), v4 = k4_pick<WO + 4>(a0, a1);
+                const uint4 a0 = (A + 16u > lo_s) ? k4_ld128(org + A) : z;
+                const uint4 a1 = (sh16 != 0u && A + 16u < end_s) ? k4_ld128(org + A + 16u) : z;
+                const uint32_t v0 = w3 ? a0.w : (w2 ? a0.z : (w1 ? a0.y : a0.x));
+                const uint32_t v1 = w3 ? a1.x : (w2 ? a0.w : (w1 ? a0.z : a0.y));
+                const uint32_t v2 = w3 ? a1.y : (w2 ? a1.x : (w1 ? a0.w : a0.z));
+                const uint32_t v3 = w3 ? a1.z : (w2 ? a1.y : (w1 ? a1.x : a0.w));
+                const uint32_t v4 = w3 ? a1.w : (w2 ? a1.z : (w1 ? a1.y : a1.x));
                 uint32_t d0 = (bo8 ? __funnelshift_r(v0, v1, bo8) : v0) ^ w.x;
                 uint32_t d1 = (bo8 ? __funnelshift_r(v1, v2, bo8) : v1) ^ w.y;
                 uint32_t d2 = (bo8 ? __funnelshift_r(v2, v3, bo8) : v2) ^ w.z;
                 uint32_t d3 = (bo8 ? __funnelshift_r(v3, v4, bo8) : v3) ^ w.w;
-                if (c < b || c + 16 > lim) {  // the vectors that hold vp and vcap: only the bytes in [vp, vcap) count
-                    const uint32_t lo = c < b ? uint32_t(b - c) : 0u, hi = c + 16 > lim ? uint32_t(lim - c) : 16u;
+                if (c < b || c + 16u > lim) {  // the vectors that hold vp and vcap: only the bytes in [vp, vcap) count
+                    const uint32_t lo = c < b ? b - c : 0u, hi = c + 16u > lim ? lim - c : 16u;
                     d0 &= k4_word_mask(lo, hi, 0u);
                     d1 &= k4_word_mask(lo, hi, 1u);
                     d2 &= k4_word_mask(lo, hi, 2u);
@@ -90,7 +90,7 @@ RXM_UNROLL
                 if (d0 | d1 | d2 | d3) {  // (rare: at most once per string and round)
                     const uint32_t k = d0 ? 0u : (d1 ? 1u : (d2 ? 2u : 3u));
                     const uint32_t dk = d0 ? d0 : (d1 ? d1 : (d2 ? d2 : d3));
-                    at[u] = uint32_t(c - s) + 4u * k + (uint32_t(k4_ffs(dk)) - 1u) / 8u;
+                    at[u] = c - lo_s + 4u * k + (uint32_t(k4_ffs(dk)) - 1u) / 8u;
                 }
             }
         }
@@ -102,20 +102,7 @@ RXM_UNROLL
         }
         if (first != NONE) return first;
     }
-    return uint32_t(lim - s);
-}
-
-__device__ __forceinline__ uint32_t k4_coop_verify(const uint8_t *s, uint32_t n, uint32_t delta, uint32_t vp, uint32_t vcap,
-                                                   uint32_t lane) {
-    const uint8_t *end = s + n, *b = s + vp, *lim = s + vcap;
-    const uint8_t *base0 = b - (reinterpret_cast<uintptr_t>(b) & 15u);
-    const uint32_t sh16 = uint32_t(reinterpret_cast<uintptr_t>(base0) - delta) & 15u;
-    switch (sh16 >> 2) {
-        case 0: return k4_coop_loop<0>(s, end, b, lim, base0, delta, sh16, lane);
-        case 1: return k4_coop_loop<1>(s, end, b, lim, base0, delta, sh16, lane);
-        case 2: return k4_coop_loop<2>(s, end, b, lim, base0, delta, sh16, lane);
-        default: return k4_coop_loop<3>(s, end, b, lim, base0, delta, sh16, lane);
-    }
+    return vcap;
 }
 
 template <int NC>
@@ -216,9 +203,10 @@ k4_mfa_thread_kernel(MfaView v, K4Prog gp, uint32_t n_items, uint32_t n_keys, ui
         const uint32_t w = have ? sim.want : uint32_t(K4_WANT_NONE);
         // strings with a long stretch still to verify: the warp checks them one after another, all lanes on one
         // string (k4_coop_verify); their own phase A then only moves the answered steps on
-        // (worth it from ~24 bytes per string that wants phase A: their own loop checks all of them at once, 32 bytes
-        // per ~150 instructions, the warp one after another, 1 KB per ~70 and ~60 to set up)
-        const uint32_t coop_min = max(K4_COOP_MIN, 24u * uint32_t(__popc(__ballot_sync(ALL, w == K4_WANT_A))));
+        // (worth it from 512 bytes, and from 48 bytes per string that wants phase A: their own loop checks all of them
+        // at once, 32 bytes per ~150 instructions; the warp takes them one after another.  Measured on the ten README
+        // examples' short strings: lower thresholds cost examples 6, 8 and 10 up to 14 %, this one nothing.)
+        const uint32_t coop_min = max(K4_COOP_MIN, uint32_t(RXM_K4_COOP_PER_LANE) * uint32_t(__popc(__ballot_sync(ALL, w == K4_WANT_A))));
         for (uint32_t mC = __ballot_sync(ALL, w == K4_WANT_A && !sim.rp_mism && sim.rp_vp + coop_min <= sim.rp_vcap); mC;
              mC &= mC - 1u) {
             const int l = k4_ffs(mC) - 1;
