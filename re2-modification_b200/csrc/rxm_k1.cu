@@ -271,6 +271,7 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 #else  // tests/hostsim: the copy lands at once (a legal outcome of the asynchronous one), shared addresses
        // are offsets into the emulated block's memory (simt_shim.hpp)
 inline void cp_async16(uint32_t smem_dst, const void *gsrc, bool pred) {
+    if (pred && ((smem_dst | uint32_t(reinterpret_cast<uintptr_t>(gsrc))) & 15u)) simt::fail(4, "misaligned 16-byte cp.async");
     if (pred) memcpy(simt::shared_ptr(smem_dst), gsrc, 16);
 }
 inline void cp_async16_pol(uint32_t smem_dst, const void *gsrc, bool pred, uint64_t) { cp_async16(smem_dst, gsrc, pred); }
@@ -279,7 +280,10 @@ inline void cp_async_commit() {}
 template <int N>
 inline void cp_async_wait() {}
 inline uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
-inline uint4 lds128(uint32_t addr) { return *reinterpret_cast<const uint4 *>(simt::shared_ptr(addr)); }
+inline uint4 lds128(uint32_t addr) {
+    if (addr & 15u) simt::fail(4, "misaligned 16-byte shared load");
+    return *reinterpret_cast<const uint4 *>(simt::shared_ptr(addr));
+}
 #endif
 
 // q' = T[byte][q] with T[byte][SP] u8 in shared memory.  The index is formed with one

@@ -40,6 +40,9 @@ __device__ __forceinline__ uint4 k4_ld128(const uint8_t *p) {  // p is 16-byte a
 #if defined(__CUDA_ARCH__)
     return __ldg(reinterpret_cast<const uint4 *>(p));
 #else
+#ifdef RXM_SIMT_HOST  // the emulator reports what the device would fault on
+    if (reinterpret_cast<uintptr_t>(p) & 15u) simt::fail(4, "misaligned 16-byte global load");
+#endif
     return *reinterpret_cast<const uint4 *>(p);
 #endif
 }
@@ -55,7 +58,7 @@ __device__ __forceinline__ uint32_t k4_coop_verify(const uint8_t *s, uint32_t n,
     const uint32_t lo_s = 16u + uint32_t(reinterpret_cast<uintptr_t>(s) & 15u);  // the string is [lo_s, end_s)
     const uint8_t *org = s - lo_s;
     const uint32_t end_s = lo_s + n, b = lo_s + vp, lim = lo_s + vcap;
-    const uint32_t sh16 = (b - delta) & 15u;  // == (any 16-aligned offset - delta) & 15: where the stream delta back stands
+    const uint32_t sh16 = (0u - delta) & 15u;  // (any 16-aligned offset - delta) & 15: where the stream delta back stands
     const uint32_t bo8 = (sh16 & 3u) * 8u;
     const bool w1 = (sh16 >> 2) == 1u, w2 = (sh16 >> 2) == 2u, w3 = (sh16 >> 2) == 3u;  // (uniform: selects, not branches)
     constexpr uint32_t NONE = 0xffffffffu;
