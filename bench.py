@@ -574,6 +574,33 @@ def extra_workload(W, rxm, H, wl, strings, steps, dev, local_rank, seed):
         "gpu_launches": int(launches), "l2_flushed_between_steps": flushed, "parity_checked": checked,
         "match_fraction": float(sum(float(j["out"].float().sum().item()) for j in jobs) / max(1, n)),
     }
+    # the same call end to end: pinned HOST buffers, H2D of the strings + offsets and D2H of the bits inside the step
+    stream = torch.cuda.current_stream().cuda_stream
+    for j in jobs:
+        j["h_chars"] = torch.empty(j["bytes"], dtype=torch.uint8, pin_memory=True)
+        j["h_chars"].copy_(j["chars"][:j["bytes"]])
+        j["h_off"] = torch.empty(j["n"] + 1, dtype=torch.int64, pin_memory=True)
+        j["h_off"].copy_(j["offsets"])
+        j["h_out"] = torch.empty(j["n"], dtype=torch.uint8, pin_memory=True)
+    torch.cuda.synchronize()
+
+    def step_host():
+        for j in jobs:
+            j["matcher"].match_ptrs(j["h_chars"].data_ptr(), j["h_off"].data_ptr(), j["n"], j["h_out"].data_ptr(), stream)
+
+    step_host()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step_host()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / steps
+    same = all(bool(torch.equal(j["h_out"], j["out"].cpu())) for j in jobs)
+    if not same:
+        raise SystemExit(f"bench.py: {wl}: host route and device route disagree")
+    res["e2e"] = {"ms_per_step": e2e_ms, "value": n / (e2e_ms / 1e3), "unit": "strings/s",
+                  "h2d_bytes_per_step": int(total_bytes + 8 * (n + len(jobs))), "d2h_bytes_per_step": int(n),
+                  "note": "rxm_match_batch with pinned host buffers: copy in, kernels, copy out, one job after another"}
     eff = os.path.join(ROOT, "profiles", "mfa_kernel_efficiency.json")  # from the committed ncu captures
     if os.path.exists(eff):
         res["ncu"] = json.load(open(eff)).get(wl)
