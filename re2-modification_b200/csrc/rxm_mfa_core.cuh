@@ -481,7 +481,7 @@ struct ProgSim {
     uint32_t nb;
     uint32_t steps_run, steps_skipped;
     bool overflow;
-    // REPEATED STEPS (host study for the next K3 step; off unless `replay` is set): a
+    // REPEATED STEPS (host study of round 1 that K4's phase A grew out of, DESIGN.md 6 "K4"; off unless `replay` is set): a
     // step that starts from the set the previous step started from, moved on by the distance delta
     // between the two, with the same letter and the same outcomes of the same block compares, ends
     // in the previous result moved on by delta -- so only the compares are evaluated.
