@@ -15,6 +15,10 @@ namespace {
 
 constexpr int K4_THREADS = 128;
 constexpr uint32_t K4_CHUNK = 64;  // tickets a warp takes from the global counter at a time
+#ifndef RXM_K4_WAIT_MAX  // (tuning builds set it)
+#define RXM_K4_WAIT_MAX 3
+#endif
+constexpr uint32_t K4_WAIT_MAX = RXM_K4_WAIT_MAX;  // rounds a string may wait for its phase
 
 // Phase A's verification (rxm_k4_core.cuh) done by the WHOLE WARP for one string: the first j in [vp, vcap) with
 // s[j] != s[j - delta], or vcap.  A thread that checks its own string reads 32 bytes per round trip from a
@@ -156,6 +160,10 @@ k4_mfa_thread_kernel(MfaView v, K4Prog gp, uint32_t n_items, uint32_t n_keys, ui
     unsigned long long wnext = 0, wend = 0;  // this warp's tickets in hand (warp-uniform)
     bool have = false, exhausted = false;
     uint64_t si = 0;
+    uint32_t waited = 0;  // rounds this lane's string has waited for its phase
+#ifndef RXM_K4_HIST_MIN
+#define RXM_K4_HIST_MIN 24
+#endif
     for (;;) {
         const bool want = !have && !exhausted;
         const uint32_t wm = __ballot_sync(ALL, want);
@@ -224,11 +232,22 @@ k4_mfa_thread_kernel(MfaView v, K4Prog gp, uint32_t n_items, uint32_t n_keys, ui
             }
         }
         const uint32_t mA = __ballot_sync(ALL, w == K4_WANT_A), mB = __ballot_sync(ALL, w == K4_WANT_B);
-        if (mA != 0u && __popc(mA) >= __popc(mB)) {
+        // the phase most strings want -- but a string never waits more than K4_WAIT_MAX rounds for its phase: then the
+        // other phase runs once, whatever the count.  (The plain majority starves the strings of the rarer phase until
+        // enough of them have piled up: example 9 of the README runs mostly full steps, the few strings at the start of
+        // an a-run sat out ~a third of the warp's rounds -- 21.8 -> 15.5 ms; config 3 is unchanged, 2.60 ms.  Serving the
+        // rarer phase at once, or both phases every round, costs config 3 and example 10 12 - 40 %: `tools/k4_ab.sh`.)
+        bool run_a = mA != 0u && __popc(mA) >= __popc(mB);
+        if (mA != 0u && mB != 0u) {
+            const bool starving = have && waited >= K4_WAIT_MAX && (w == K4_WANT_A) != run_a;
+            if (__any_sync(ALL, starving)) run_a = !run_a;
+        }
+        if (run_a) {
             if (w == K4_WANT_A) sim.phase_a();
         } else if (mB != 0u) {
             if (w == K4_WANT_B) sim.phase_b(v, p);
         }
+        waited = (have && ((w == K4_WANT_A) != run_a)) ? waited + 1u : 0u;
         __syncwarp(ALL);
         if (have && sim.want == K4_DONE) {
             int r = sim.result;
