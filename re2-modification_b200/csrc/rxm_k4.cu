@@ -23,8 +23,8 @@ constexpr uint32_t K4_WAIT_MAX = RXM_K4_WAIT_MAX;  // rounds a string may wait f
 // Phase A's verification (rxm_k4_core.cuh) done by the WHOLE WARP for one string: the first j in [vp, vcap) with
 // s[j] != s[j - delta], or vcap.  A thread that checks its own string reads 32 bytes per round trip from a
 // line no other lane touches (ncu on config 3: 5.3 x the input over L2 -> SM, long-scoreboard stalls on every
-// issue); here a round trip is 1 KB of consecutive addresses -- 32 lanes x one aligned 16-byte vector x 2 in
-// flight -- and the vectors delta bytes back come from lines this warp has just read.  The stream delta bytes back
+// issue); here a round trip is 512 bytes of consecutive addresses -- 32 lanes x one aligned 16-byte vector --
+// and the vectors delta bytes back come from lines this warp has just read.  The stream delta bytes back
 // stands at a fixed byte offset against the 16-byte grid, so its five words per vector are picked with a
 // warp-uniform, loop-invariant word offset (selects on three uniform predicates: four copies of the loop, one per
 // offset, cost more in instruction-cache misses than they saved -- ncu: no_instruction 10.7 per issue) and one
@@ -38,7 +38,10 @@ constexpr uint32_t K4_WAIT_MAX = RXM_K4_WAIT_MAX;  // rounds a string may wait f
 #define RXM_K4_COOP_PER_LANE 48
 #endif
 constexpr uint32_t K4_COOP_MIN = RXM_K4_COOP_MIN;  // bytes still to verify from which a string can be worth the warp's time
-constexpr int K4_COOP_UNROLL = 2;
+#ifndef RXM_K4_COOP_UNROLL  // (tuning builds set it)
+#define RXM_K4_COOP_UNROLL 1  // measured on config 3: 1 -> 2.55 ms, 2 -> 2.74, 4 -> 3.26 (vectors past the stretch's end cost more than a round trip saves)
+#endif
+constexpr int K4_COOP_UNROLL = RXM_K4_COOP_UNROLL;
 
 __device__ __forceinline__ uint4 k4_ld128(const uint8_t *p) {  // p is 16-byte aligned
 #if defined(__CUDA_ARCH__)
