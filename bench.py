@@ -545,6 +545,15 @@ def hbm_peak():
     return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
 
 
+def engine_of(rxm, j):
+    """The kernel family that runs job j: the planner's choice for the automaton -- except that batches of long
+    strings (mean length above 4096) of a K4 automaton are K3's, 32 lanes per string (picked per batch, rxm_api.cu)."""
+    name = rxm.ENGINE_NAMES.get(j["matcher"].plan().engine, "?")
+    if name == "K4_THREAD" and j["n"] and j["bytes"] / j["n"] > 4096:
+        return "K3_WARP(32 lanes; long strings)"
+    return name
+
+
 def extra_workload(W, rxm, H, wl, strings, steps, dev, local_rank, seed):
     """A short measurement of another BASELINE config inside the default run: the same
     timing rules as the headline (warm-up, CUDA events, L2 flush for small inputs, parity spot check)."""
@@ -570,7 +579,7 @@ def extra_workload(W, rxm, H, wl, strings, steps, dev, local_rank, seed):
         "workload": WORKLOADS[wl][3], "strings": n, "bytes": total_bytes, "jobs_per_step": len(jobs), "steps": steps,
         "ms_per_step": k_ms, "strings_per_sec": n / (k_ms / 1e3), "input_gb_s": total_bytes / (k_ms / 1e3) / 1e9,
         "roofline_frac": algo / (k_ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_step": algo,
-        "engine": "+".join(sorted({rxm.ENGINE_NAMES.get(j["matcher"].plan().engine, "?") for j in jobs})),
+        "engine": "+".join(sorted({engine_of(rxm, j) for j in jobs})),
         "gpu_launches": int(launches), "l2_flushed_between_steps": flushed, "parity_checked": checked,
         "match_fraction": float(sum(float(j["out"].float().sum().item()) for j in jobs) / max(1, n)),
     }
@@ -935,7 +944,7 @@ def main():
         }
         del text, h_text
 
-    engines = "+".join(sorted({rxm.ENGINE_NAMES.get(j["matcher"].plan().engine, "?") for j in jobs}))
+    engines = "+".join(sorted({engine_of(rxm, j) for j in jobs}))
     dfa_stride = int(jobs[0]["matcher"].plan().dfa_stride)
     n_jobs, n_streams = len(jobs), max(1, len(R.job_streams))
 

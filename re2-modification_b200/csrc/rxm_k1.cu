@@ -147,13 +147,22 @@ k1_tilesort_kernel(const Spans sp, uint64_t n, K1Rec *__restrict__ recs,
         const uint64_t lo = tile * K1_TILE;
         uint64_t beg[K1_SORT_PER_THREAD];
         uint32_t len[K1_SORT_PER_THREAD], bkt[K1_SORT_PER_THREAD], rank[K1_SORT_PER_THREAD];
+        uint64_t fin[K1_SORT_PER_THREAD];
+#pragma unroll
+        for (int k = 0; k < K1_SORT_PER_THREAD; k++) {  // all loads first: one memory round trip, not one per string
+            const uint64_t i = lo + uint32_t(k) * K1_SORT_THREADS + t;
+            beg[k] = fin[k] = 0;
+            if (i < n) {
+                beg[k] = sp.begin[i];
+                fin[k] = sp.end[i];
+            }
+        }
 #pragma unroll
         for (int k = 0; k < K1_SORT_PER_THREAD; k++) {
             const uint64_t i = lo + uint32_t(k) * K1_SORT_THREADS + t;
             bkt[k] = 0xffffffffu;
             if (i < n) {
-                beg[k] = sp.begin[i];
-                const uint64_t l = sp.end[i] - beg[k];
+                const uint64_t l = fin[k] - beg[k];
                 if (l >= 0x7fffffffull && overflow) atomicAdd(overflow, 1ull);
                 len[k] = clamp_len(l);
                 bkt[k] = len_bucket(len[k]);
