@@ -147,6 +147,27 @@ def test_plan_reports_engine():
     m.close()
 
 
+def test_host_offsets_that_run_backwards_are_rejected_and_the_handle_stays_usable():
+    """rxm_match_batch with host buffers checks the offsets (while the copy of the strings runs): a string that starts
+    behind its end is RXM_ERR_INVALID, no kernel sees it, and the next call on the handle is answered as usual."""
+    t, strings, bits = load_case("nfa_abb")
+    chars, off = H.make_batch(strings)
+    bad = off.copy()
+    k = len(bad) // 2
+    bad[k] = bad[k + 1] + 5
+    m = rxm.Matcher(t, 0)
+    with pytest.raises(rxm.RxmError) as e:
+        m.match_host(chars, bad)
+    assert e.value.status == rxm.RXM_ERR_INVALID
+    bad = off.copy()
+    bad[0] = off[-1] + 1
+    with pytest.raises(rxm.RxmError) as e:
+        m.match_host(chars, bad)
+    assert e.value.status == rxm.RXM_ERR_INVALID
+    assert np.array_equal(m.match_host(chars, off), bits)
+    m.close()
+
+
 def test_mixed_host_device_pointers_are_rejected():
     import torch
     t, strings, _ = load_case("nfa_abb")
