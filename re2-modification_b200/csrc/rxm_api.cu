@@ -71,7 +71,7 @@ struct rxm_matcher {
     uint32_t k3_tile = 32;  // lanes per string
     bool k3_tile_forced = false;
     // K4: the programs' item lists; strings that outgrow a thread's sets go to K3 through the redo list
-    uint32_t *d_prog_lbeg = nullptr, *d_prog_lcnt = nullptr;
+    uint32_t *d_prog_lists = nullptr;  // K4's tables packed (rxm::k4_pack_lists)
     uint16_t *d_prog_sel = nullptr;
     uint32_t k4_maxl = 0;
     uint32_t *d_redo_list = nullptr;
@@ -257,9 +257,11 @@ static int upload_impl(const rxm_tables *host_tables, int device, const rxm_uplo
             if ((st = upload_vec(m->prog.items, &m->d_items)) != RXM_OK) return fail(st);
             if ((st = upload_vec(m->prog.begin, &m->d_prog_begin)) != RXM_OK) return fail(st);
             if ((st = upload_vec(m->prog.count, &m->d_prog_count)) != RXM_OK) return fail(st);
-            if ((st = upload_vec(m->prog.lbeg, &m->d_prog_lbeg)) != RXM_OK) return fail(st);
-            if ((st = upload_vec(m->prog.lcnt, &m->d_prog_lcnt)) != RXM_OK) return fail(st);
             if ((st = upload_vec(m->prog.sel, &m->d_prog_sel)) != RXM_OK) return fail(st);
+            {
+                const std::vector<uint32_t> lists = rxm::k4_pack_lists(m->prog);  // K4's tables as one array
+                if ((st = upload_vec(lists, &m->d_prog_lists)) != RXM_OK) return fail(st);
+            }
             m->k4_maxl = rxm::k4_pool_for(t.n_states);  // slots per thread: the current set and the one being built share them
             // K4 (one thread per string) unless the automaton is large: its sets outgrow a thread's slots, K3 (one
             // warp per string, one slot per node) runs the whole batch
@@ -306,9 +308,8 @@ extern "C" int rxm_free(rxm_handle h) {
     cudaFree(h->d_items);
     cudaFree(h->d_prog_begin);
     cudaFree(h->d_prog_count);
-    cudaFree(h->d_prog_lbeg);
-    cudaFree(h->d_prog_lcnt);
     cudaFree(h->d_prog_sel);
+    cudaFree(h->d_prog_lists);
     cudaFree(h->d_redo_list);
     cudaFree(h->d_redo_n);
     cudaFree(h->d_pick);
@@ -411,8 +412,8 @@ static int launch_on_device(rxm_matcher *m, const uint8_t *d_chars, rxm::Spans s
     } else if (m->info.engine == RXM_ENGINE_K4_THREAD) {
         rxm::MfaView v{m->d_edge_begin, m->d_edges, m->tables.n_states(), m->tables.start,
                        m->tables.finish, m->tables.reversed};
-        rxm::K4Prog kp{m->d_items, m->d_prog_begin, m->d_prog_count, m->d_prog_lbeg, m->d_prog_lcnt, m->d_prog_sel,
-                       m->prog.n_cells};
+        rxm::K4Prog kp{m->d_items, m->d_prog_lists, m->d_prog_sel, m->prog.n_cells, m->prog.n_classes,
+                       uint32_t(m->prog.begin.size())};
         rxm::ProgView gp{m->d_items, m->d_prog_begin, m->d_prog_count, m->prog.n_cells};
         // Batches of long strings (mean length above 4096: few strings, each bounded by its own length) are
         // K3's, 32 lanes per string; everything else is K4's.  With host buffers the lengths are known here;

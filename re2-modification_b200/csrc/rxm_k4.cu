@@ -14,6 +14,10 @@ namespace rxm {
 namespace {
 
 constexpr int K4_THREADS = 128;
+// shared-memory bytes of the block-shared program tables: the packed lists (K4Prog::lists), sel [n_sel]; rounded up to 16
+RXM_HD size_t k4_table_bytes(uint32_t n_keys, uint32_t n_sel, uint32_t n_classes) {
+    return (size_t(k4_list_words(n_keys, n_classes)) * 4 + size_t(n_sel) * 2 + 15) & ~size_t(15);
+}
 constexpr uint32_t K4_CHUNK = 64;  // tickets a warp takes from the global counter at a time
 #ifndef RXM_K4_WAIT_MAX  // (tuning builds set it)
 #define RXM_K4_WAIT_MAX 3
@@ -116,7 +120,7 @@ RXM_UNROLL
 }
 
 template <int NC>
-__global__ void __launch_bounds__(K4_THREADS)
+__global__ void __launch_bounds__(K4_THREADS, 6)
 k4_mfa_thread_kernel(MfaView v, K4Prog gp, uint32_t n_items, uint32_t n_keys, uint32_t n_sel, uint32_t items_in_smem,
                      uint32_t maxl, const uint8_t *__restrict__ chars, const Spans sp, const K1Rec *__restrict__ recs,
                      uint64_t n, uint8_t *__restrict__ out, unsigned long long *__restrict__ overflow,
@@ -126,21 +130,14 @@ k4_mfa_thread_kernel(MfaView v, K4Prog gp, uint32_t n_items, uint32_t n_keys, ui
     if (gate && *gate != 0u) return;  // a batch of long strings: K3 runs it (mfa_pick_kernel decided on the device)
     constexpr uint32_t ALL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u;
-    // ---- block-shared program tables ----
-    uint32_t *s_begin = reinterpret_cast<uint32_t *>(smem);
-    uint32_t *s_count = s_begin + n_keys;
-    uint32_t *s_lbeg = s_count + n_keys;
-    uint32_t *s_lcnt = s_lbeg + n_keys;
-    uint16_t *s_sel = reinterpret_cast<uint16_t *>(s_lcnt + n_keys);
-    size_t o = (size_t(n_keys) * 16 + size_t(n_sel) * 2 + 15) & ~size_t(15);
+    // ---- block-shared program tables: the packed lists, the item selections, the items if they fit ----
+    const uint32_t n_lw = k4_list_words(n_keys, gp.n_classes);
+    uint32_t *s_lists = reinterpret_cast<uint32_t *>(smem);
+    uint16_t *s_sel = reinterpret_cast<uint16_t *>(s_lists + n_lw);
+    size_t o = k4_table_bytes(n_keys, n_sel, gp.n_classes);
     ProgItem *s_items = reinterpret_cast<ProgItem *>(smem + o);
     if (items_in_smem) o += size_t(n_items) * sizeof(ProgItem);
-    for (uint32_t k = threadIdx.x; k < n_keys; k += blockDim.x) {
-        s_begin[k] = gp.begin[k];
-        s_count[k] = gp.count[k];
-        s_lbeg[k] = gp.lbeg[k];
-        s_lcnt[k] = gp.lcnt[k];
-    }
+    for (uint32_t k = threadIdx.x; k < n_lw; k += blockDim.x) s_lists[k] = gp.lists[k];
     for (uint32_t k = threadIdx.x; k < n_sel; k += blockDim.x) s_sel[k] = gp.sel[k];
     if (items_in_smem) {
         const uint4 *src = reinterpret_cast<const uint4 *>(gp.items);
@@ -148,7 +145,7 @@ k4_mfa_thread_kernel(MfaView v, K4Prog gp, uint32_t n_items, uint32_t n_keys, ui
         for (uint32_t k = threadIdx.x; k < n_items; k += blockDim.x) dst[k] = src[k];
     }
     __syncthreads();
-    const K4Prog p{items_in_smem ? s_items : gp.items, s_begin, s_count, s_lbeg, s_lcnt, s_sel, gp.n_cells};
+    const K4Prog p{items_in_smem ? s_items : gp.items, s_lists, s_sel, gp.n_cells, gp.n_classes, n_keys};
 
     K4Sim<NC, K4_THREADS> sim;
     sim.base = reinterpret_cast<uint32_t *>(smem + o) + threadIdx.x;
@@ -270,7 +267,7 @@ int launch_k4(const MfaView &v, const K4Prog &gp, uint32_t n_items, uint32_t n_k
               const uint8_t *d_chars, Spans spans, const K1Rec *d_recs, uint64_t n, uint8_t *d_out,
               unsigned long long *d_overflow, unsigned long long *d_next, uint32_t *d_redo_list,
               unsigned long long *d_redo_n, int sm_count, uint32_t sharing, cudaStream_t stream, const uint32_t *d_gate) {
-    const size_t tab = (size_t(n_keys) * 16 + size_t(n_sel) * 2 + 15) & ~size_t(15);
+    const size_t tab = k4_table_bytes(n_keys, n_sel, gp.n_classes);
     const bool in_smem = size_t(n_items) * sizeof(ProgItem) <= 24 * 1024;
     const size_t smem = tab + (in_smem ? size_t(n_items) * sizeof(ProgItem) : 0) +
                         size_t(K4_THREADS) * k4_words(NC, maxl) * 4;

@@ -36,15 +36,31 @@
 
 namespace rxm {
 
-struct K4Prog {  // the edge programs and the per-key item lists (MfaProgram)
+struct K4Prog {  // the edge programs and the per-key item lists (MfaProgram), the lists packed into ONE array
     const ProgItem *items;
-    const uint32_t *begin;  // [key] first item, 0xffffffff: a (node, cells) pair the host analysis did not reach
-    const uint32_t *count;  // [key] items | kProgStable
-    const uint32_t *lbeg;   // [key] first entry of the key's lists in sel
-    const uint32_t *lcnt;   // [key] leaves | enters << 16
+    // [begin | count | lbeg | lcnt] (n_keys words each), [cbeg | ccnt] (n_keys * n_classes words each), then the
+    // byte -> class table (256 bytes): one base pointer instead of seven -- the kernel runs at its register limit
+    //   begin[key]  first item, 0xffffffff: a (node, cells) pair the host analysis did not reach
+    //   count[key]  items | kProgStable
+    //   lbeg[key]   first entry of the key's lists in sel;  lcnt[key]  leaves | enters << 16
+    //   cbeg / ccnt[key * n_classes + class]  the leaves that can act on a letter of that class (n_classes >= 1)
+    const uint32_t *lists;
     const uint16_t *sel;    // item indices relative to begin[key]
-    uint32_t n_cells;
+    uint32_t n_cells, n_classes, n_keys;
+    RXM_HD uint32_t word(uint32_t idx) const { return lists[idx]; }
+    RXM_HD uint32_t sel_at(uint32_t idx) const { return sel[idx]; }
+    RXM_HD uint32_t cls(uint32_t byte) const {
+        return reinterpret_cast<const uint8_t *>(lists + (4u + 2u * n_classes) * n_keys)[byte];
+    }
+    RXM_HD uint32_t begin(uint32_t key) const { return word(key); }
+    RXM_HD uint32_t count(uint32_t key) const { return word(n_keys + key); }
+    RXM_HD uint32_t lbeg(uint32_t key) const { return word(2u * n_keys + key); }
+    RXM_HD uint32_t lcnt(uint32_t key) const { return word(3u * n_keys + key); }
+    RXM_HD uint32_t cbeg(uint32_t key, uint32_t c) const { return word(4u * n_keys + key * n_classes + c); }
+    RXM_HD uint32_t ccnt(uint32_t key, uint32_t c) const { return word((4u + n_classes) * n_keys + key * n_classes + c); }
 };
+// words of K4Prog::lists
+RXM_HD constexpr uint32_t k4_list_words(uint32_t n_keys, uint32_t n_classes) { return (4u + 2u * n_classes) * n_keys + 64u; }
 
 constexpr uint32_t K4_LOGN = 4;      // distinct block compares remembered per step
 constexpr uint32_t K4_BURST = 64;    // iterations of the repeated-step loop per round
@@ -532,6 +548,7 @@ RXM_UNROLL
         {
             const uint32_t ch = (i < n) ? at(i) : 0u;
             const uint32_t digit_bit = (ch >= '1' && ch <= '9') ? (1u << (ch - '1')) : 0u;
+            const uint32_t cc = p.cls(ch);  // an active configuration walks the leaves of this letter's class
             uint32_t todo = cur, js = 0, q = 0, nq = 0, lbase = 0, pb = 0;
             bool active = false, waiting = false, fin = false;
             cfg_t root;
@@ -549,17 +566,22 @@ RXM_UNROLL
                     if (!(active || waiting || fin)) continue;  // behind the step: no branch of mfa.cpp:161-197 fires
                     if (!(root.node == t.finish && fin) && t.reversed && need_of(root.flags, root.len) > n - i) continue;  // :141
                     const uint32_t key = (root.node << p.n_cells) | k4_exists_mask<NC>(root.flags);
-                    pb = p.begin[key];
+                    pb = p.begin(key);
                     if (pb == 0xffffffffu) {  // a (node, cells) pair the host analysis did not reach
                         overflow = true;
                         continue;
                     }
-                    const uint32_t lc = p.lcnt[key];
-                    lbase = p.lbeg[key] + (active ? 0u : (lc & 0xffffu));  // LEAF items act for an active configuration,
-                    nq = active ? (lc & 0xffffu) : (lc >> 16);             // ENTER items for a waiting / final one
+                    if (active) {  // LEAF items act for an active configuration: those of the letter's class
+                        lbase = p.cbeg(key, cc);
+                        nq = p.ccnt(key, cc);
+                    } else {       // ENTER items for a waiting / final one
+                        const uint32_t lc = p.lcnt(key);
+                        lbase = p.lbeg(key) + (lc & 0xffffu);
+                        nq = lc >> 16;
+                    }
                     continue;
                 }
-                const uint32_t x = p.sel[lbase + q];
+                const uint32_t x = p.sel_at(lbase + q);
                 q++;
                 K4_STAT(g_items++);
                 const ProgItem it = p.items[pb + x];
@@ -647,7 +669,7 @@ RXM_UNROLL
                 const uint32_t f = sp[0], nf = sp[STRIDE];
                 if (f < i + 2 || f == n) stable = false;
                 const uint32_t key = ((nf & 0xffffu) << p.n_cells) | k4_exists_mask<NC>(nf >> 16);
-                if (p.begin[key] == 0xffffffffu || !(p.count[key] & kProgStable)) stable = false;
+                if (p.begin(key) == 0xffffffffu || !(p.count(key) & kProgStable)) stable = false;
                 if (f < ev) ev = f;
                 if (t.reversed) {
                     cfg_t c;

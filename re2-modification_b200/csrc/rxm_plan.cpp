@@ -1,6 +1,7 @@
 // Host-side planner (see rxm_plan.hpp).
 #include "rxm_plan.hpp"
 
+#include <cstdlib>
 #include <algorithm>
 #include <functional>
 #include <map>
@@ -295,6 +296,38 @@ int compile_programs(const rxm_tables &t, MfaProgram &out, std::string *err) {
         for (const auto &f : g.found) {
             const size_t k2 = (size_t(f.first) << t.n_cells) | (f.second & (nm - 1));
             if (out.begin[k2] == 0xffffffffu) work.push_back(f);
+        }
+    }
+    {   // K4's leaf lists by letter class: class 0 = every byte without a class of its own (a byte no literal edge
+        // carries -- or, past kProgMaxClasses - 1 distinct literals, the literals that came too late: their edges
+        // stay in class 0's list and are told apart by the kernel's own test of the letter)
+        uint32_t nc = 1;
+        for (const ProgItem &it : out.items)
+            if ((it.a & 1u) && ((it.a >> 4) & 3u) == RXM_EDGE_LIT) {
+                const uint32_t sym = (it.a >> 6) & 0xffu;
+                if (!out.byte_class[sym] && nc < kProgMaxClasses) out.byte_class[sym] = uint8_t(nc++);
+            }
+        out.n_classes = nc;
+        out.cbeg.assign(out.begin.size() * nc, 0);
+        out.ccnt.assign(out.begin.size() * nc, 0);
+        for (size_t key = 0; key < out.begin.size(); key++) {
+            if (out.begin[key] == 0xffffffffu) continue;
+            const uint32_t first = out.lbeg[key], leaves = out.lcnt[key] & 0xffffu;
+            for (uint32_t c = 0; c < nc; c++) {
+                out.cbeg[key * nc + c] = uint32_t(out.sel.size());
+                uint32_t cnt = 0;
+                for (uint32_t q = 0; q < leaves; q++) {
+                    const uint16_t x = out.sel[first + q];
+                    const ProgItem &it = out.items[out.begin[key] + x];
+                    const uint32_t kind = (it.a >> 4) & 3u, sym = (it.a >> 6) & 0xffu;
+                    const bool reads = ((it.c >> 18) & 0xfu) != 0;
+                    if (kind == RXM_EDGE_ANY || reads || (kind == RXM_EDGE_LIT && out.byte_class[sym] == c)) {
+                        out.sel.push_back(x);
+                        cnt++;
+                    }
+                }
+                out.ccnt[key * nc + c] = cnt;
+            }
         }
     }
     return RXM_OK;

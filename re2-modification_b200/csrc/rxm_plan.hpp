@@ -1,3 +1,9 @@
+    // The same leaves split by the input letter's CLASS (class 0: the bytes without a class of their own; classes
+    // 1 .. n_classes-1: distinct literal bytes, at most kProgMaxClasses - 1 of them): cbeg / ccnt[key * n_classes + c]
+    // delimit, in `sel`, the leaves that can act on a letter of class c -- `.` edges, literal edges of that class,
+    // reads of a present cell -- in program order (a subsequence of the list above, so ties are decided as
+    // before).  A literal edge of another byte never fires on that letter: about half of an active
+    // configuration's items are not looked at.  n_classes >= 1.
 // Host-side planner: decides which kernel family runs a table and builds the
 // derived device tables.  No CUDA in this header.
 #ifndef RXM_PLAN_HPP
@@ -64,7 +70,35 @@ struct MfaProgram {
     // indices relative to begin[key], in program order.  lcnt[key] = leaves | enters << 16.
     std::vector<uint32_t> lbeg, lcnt;
     std::vector<uint16_t> sel;
+    // The same leaves split by the input letter's CLASS (class 0: a byte no literal edge carries; classes
+    // 1 .. n_classes-1: the distinct literal bytes): cbeg / ccnt[key * n_classes + c] delimit, in `sel`, the
+    // leaves that can act on a letter of class c -- `.` edges, literal edges of that byte, reads of a present
+    // cell -- in program order (a subsequence of the list above, so ties are decided as before).  A literal
+    // edge of another byte never fires on that letter: about half of an active configuration's items are not
+    // looked at.  n_classes == 0: too many distinct literals, K4 walks the undivided list.
+    uint32_t n_classes = 0;
+    std::vector<uint32_t> cbeg, ccnt;
+    uint8_t byte_class[256] = {0};
 };
+constexpr uint32_t kProgMaxClasses = 8;
+// K4Prog::lists (rxm_k4_core.cuh): begin | count | lbeg | lcnt | cbeg | ccnt | byte_class, one array
+inline std::vector<uint32_t> k4_pack_lists(const MfaProgram &p) {
+    const size_t nk = p.begin.size();
+    std::vector<uint32_t> v((4 + 2 * size_t(p.n_classes)) * nk + 64, 0);
+    for (size_t k = 0; k < nk; k++) {
+        v[k] = p.begin[k];
+        v[nk + k] = p.count[k];
+        v[2 * nk + k] = p.lbeg.empty() ? 0u : p.lbeg[k];
+        v[3 * nk + k] = p.lcnt.empty() ? 0u : p.lcnt[k];
+    }
+    for (size_t k = 0; k < p.cbeg.size(); k++) {
+        v[4 * nk + k] = p.cbeg[k];
+        v[(4 + p.n_classes) * nk + k] = p.ccnt[k];
+    }
+    uint8_t *cls = reinterpret_cast<uint8_t *>(v.data() + (4 + 2 * size_t(p.n_classes)) * nk);
+    for (int b = 0; b < 256; b++) cls[b] = p.byte_class[b];
+    return v;
+}
 
 // RXM_OK, or RXM_ERR_UNSUPPORTED (more than kProgMaxCells cells, program too large).
 int compile_programs(const rxm_tables &t, MfaProgram &out, std::string *err);

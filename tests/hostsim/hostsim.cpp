@@ -208,8 +208,9 @@ extern "C" int hostsim_k4core_batch(const rxm_tables *t, const uint8_t *chars, c
     for (uint32_t e = 0; e < t->n_edges; e++)
         er[e] = rxm::pack_edge(t->edge_kind[e], t->edge_sym[e], t->edge_to[e], t->edge_open[e], t->edge_close[e]);
     rxm::MfaView v{eb.data(), er.data(), t->n_states, t->start, t->finish, t->reversed};
-    rxm::K4Prog kp{prog.items.data(), prog.begin.data(), prog.count.data(), prog.lbeg.data(), prog.lcnt.data(),
-                   prog.sel.data(), prog.n_cells};
+    const std::vector<uint32_t> k4_lists = rxm::k4_pack_lists(prog);
+    rxm::K4Prog kp{prog.items.data(), k4_lists.data(), prog.sel.data(), prog.n_cells, prog.n_classes,
+                   uint32_t(prog.begin.size())};
     if (info3) info3[0] = info3[1] = info3[2] = 0;
     if (maxl == 0 || maxl > rxm::K4_POOL_MAX) maxl = rxm::k4_pool_for(t->n_states);  // the planner's choice
     if (t->n_cells <= 1) run_k4_batch<1>(v, kp, maxl, chars, off, n, out, info3);

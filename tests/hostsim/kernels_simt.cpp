@@ -125,8 +125,9 @@ extern "C" int hostsim_k4_batch(const rxm_tables *t, const uint8_t *chars, const
     if (st != RXM_OK) return st;
     DevTables dt;
     const rxm::MfaView v = dt.view(t);
-    rxm::K4Prog kp{prog.items.data(), prog.begin.data(), prog.count.data(), prog.lbeg.data(), prog.lcnt.data(),
-                   prog.sel.data(), prog.n_cells};
+    const std::vector<uint32_t> k4_lists = rxm::k4_pack_lists(prog);
+    rxm::K4Prog kp{prog.items.data(), k4_lists.data(), prog.sel.data(), prog.n_cells, prog.n_classes,
+                   uint32_t(prog.begin.size())};
     std::vector<rxm::K1Rec> recs = make_recs(order_idx, n);
     // the tile sort's layout: a short last tile is padded out by the kernel's own skip rule, so the
     // records of a permutation must be laid out tile by tile as k1_tilesort_kernel does

@@ -313,3 +313,29 @@ def test_warp_cooperative_periodicity_check_every_alignment_and_distance():
         assert rc == 0, msg.value.decode()
         diff = np.nonzero(res != np.asarray(want, dtype=np.uint32))[0]
         assert len(diff) == 0, [(int(k), int(res[k]), want[k], dl[k], vps[k], vcs[k], ln[k]) for k in diff[:5]]
+
+
+@pytest.mark.skipif(not os.path.exists(H.RXM_COMPILE), reason="bin/rxm_compile not built")
+@pytest.mark.parametrize("regex", ["{(a|b|c|d|e|f|g|h|i|j|k|l)*}:1m&1(n|&1)*", "({(ab|cd|ef|gh|ij)*}:1x|y&1)*z&1"])
+def test_k4_leaf_lists_by_letter_class_with_more_literals_than_classes(regex):
+    """rxm_plan.cpp: K4's leaf lists are split by the input letter's class, at most kProgMaxClasses - 1 literals get a
+    class of their own and the rest share class 0 with the bytes no edge carries -- an expression with 13 distinct
+    literals on the host core and on the emulated kernel against the C restatement; every list is a subsequence of
+    the key's undivided leaf list."""
+    t = H.rxm.Tables(H.compile_tables_text(regex))
+    rng = np.random.default_rng(3)
+    letters = sorted({c for c in regex.encode() if chr(c).isalpha()})
+    alpha = np.frombuffer(bytes(letters) + b"q1", dtype=np.uint8)
+    strings = [bytes(rng.choice(alpha, size=int(n))) for n in rng.integers(0, 40, size=1500)]
+    for _ in range(300):  # strings inside the language: a block, its separator, the block again
+        blk = bytes(rng.choice(alpha[:10], size=int(rng.integers(0, 12))))
+        strings.append(blk + bytes([letters[-2] if b"m" in regex.encode() else ord("x")]) + blk + blk * int(rng.integers(0, 3)))
+    chars, off = H.make_batch(strings)
+    off = off.astype(np.uint64)
+    want = H.oracle_bits(t, chars, off)
+    assert 0 < int(want.sum()) < len(want)
+    rc, got, info = k4_core(t, chars, off)
+    assert rc == 0 and np.array_equal(got, want), int((got != want).sum())
+    rc, got, ovf, redo, msg = k4_emulated(t, strings, seed=2)
+    assert rc == 0, msg
+    assert np.array_equal(np.where(got == 2, want, got), want) and ovf == 0
