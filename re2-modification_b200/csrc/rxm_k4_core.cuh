@@ -62,6 +62,10 @@ struct K4Prog {  // the edge programs and the per-key item lists (MfaProgram), t
 // words of K4Prog::lists
 RXM_HD constexpr uint32_t k4_list_words(uint32_t n_keys, uint32_t n_classes) { return (4u + 2u * n_classes) * n_keys + 64u; }
 
+#ifndef RXM_K4_A_WORDS  // (tuning builds set it)
+#define RXM_K4_A_WORDS 2  // 4: config 3 +2 %, the ten README examples +3 % (code size); 1: examples 1 and 4 +50 %
+#endif
+constexpr int K4_A_WORDS = RXM_K4_A_WORDS;  // aligned 8-byte words a thread checks per iteration of its own repeated-step loop
 constexpr uint32_t K4_LOGN = 4;      // distinct block compares remembered per step
 constexpr uint32_t K4_BURST = 64;    // iterations of the repeated-step loop per round
 constexpr uint32_t K4_POOL_MAX = 32;  // slots a thread can have at most (the set masks are 32 bits)
@@ -463,8 +467,8 @@ RXM_UNROLL
         for (uint32_t r = 0; r < K4_BURST; r++) {
             const bool can = !rp_mism && rp_vp < rp_vcap;
             if (can) {
-                // four aligned words of the input from the front on against the input delta bytes before them; the
-                // nine loads are issued together (one memory round trip per 32 bytes), and only words that hold a
+                // K4_A_WORDS aligned words of the input from the front on against the input delta bytes before them; their
+                // loads are issued together (one memory round trip per 8 * K4_A_WORDS bytes), and only words that hold a
                 // byte of the string are read
                 const uint8_t *b = s + rp_vp, *end = s + n;
                 const uint32_t ob = uint32_t(reinterpret_cast<uintptr_t>(b) & 7u);
@@ -473,17 +477,17 @@ RXM_UNROLL
                 const uint32_t oa = uint32_t(reinterpret_cast<uintptr_t>(ap) & 7u);
                 const uint8_t *a0 = ap - oa;
                 const uint32_t sh = oa * 8u;
-                uint64_t w[4], a[5];
+                uint64_t w[K4_A_WORDS], a[K4_A_WORDS + 1];
 RXM_UNROLL
-                for (int u = 0; u < 4; u++) w[u] = (b0 + 8 * u < end) ? k4_ld64(b0 + 8 * u) : 0ull;
+                for (int u = 0; u < K4_A_WORDS; u++) w[u] = (b0 + 8 * u < end) ? k4_ld64(b0 + 8 * u) : 0ull;
 RXM_UNROLL
-                for (int u = 0; u < 5; u++)  // word u of the past: read iff it holds a byte of [b - delta, end - delta)
+                for (int u = 0; u < K4_A_WORDS + 1; u++)  // word u of the past: read iff it holds a byte of [b - delta, end - delta)
                     a[u] = (a0 + 8 * u + 8 > b - delta && a0 + 8 * u < end - delta) ? k4_ld64(a0 + 8 * u) : 0ull;
                 k4_prefetch_l2(b0 + 512, end);
-                uint32_t nvp = uint32_t((b0 + 32 < end ? b0 + 32 : end) - s);
+                uint32_t nvp = uint32_t((b0 + 8 * K4_A_WORDS < end ? b0 + 8 * K4_A_WORDS : end) - s);
                 bool mism = false;
 RXM_UNROLL
-                for (int u = 3; u >= 0; u--) {  // the FIRST word that differs decides: walk backwards, keep the earliest
+                for (int u = K4_A_WORDS - 1; u >= 0; u--) {  // the FIRST word that differs decides: walk backwards, keep the earliest
                     uint64_t x = (sh ? ((a[u] >> sh) | (a[u + 1] << (64u - sh))) : a[u]) ^ w[u];
                     if (u == 0) x &= ~0ull << (8u * ob);
                     const uint8_t *ub = b0 + 8 * u;
