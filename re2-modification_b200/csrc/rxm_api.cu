@@ -561,7 +561,7 @@ extern "C" int rxm_match_batch(rxm_handle h, const uint8_t *chars, const uint64_
             return RXM_ERR_INVALID;
         }
     }
-    int st = launch_on_device(m, m->d_chars, rxm::csr_spans(m->d_offsets), n, m->d_bits, stream, total);
+    int st = launch_on_device(m, m->d_chars, rxm::csr_spans(m->d_offsets), n, m->d_bits, stream, total - offsets[0]);
     if (st != RXM_OK) return st;
     unsigned long long ovf = 0;
     if (n) CU(cudaMemcpyAsync(out_bits, m->d_bits, n, cudaMemcpyDeviceToHost, stream));
