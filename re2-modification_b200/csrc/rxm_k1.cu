@@ -929,6 +929,25 @@ k1_dfa_classed_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict
 // handles sharing a kernel instantiation may launch from several host threads (the size a launch needs is
 // checked against it).
 constexpr int K1_MAX_DYN_SMEM = 216 * 1024;
+// ... the same value for every launch of a function: all the dynamic shared memory its static tables leave of the
+// 227 KB a CTA may have (asking for more than that is an error at cudaFuncSetAttribute, which the automata with
+// 33 - 128 sets -- 16 / 32 KB of static tables -- ran into: found by tests/fuzz/fuzz_tables_gpu.py)
+template <class Kern>
+int k1_set_dyn_smem(Kern kern, size_t need) {
+#ifndef RXM_SIMT_HOST
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess) return RXM_ERR_CUDA;
+    const size_t room = size_t(227 * 1024) - fa.sharedSizeBytes;
+    const size_t limit = room < size_t(K1_MAX_DYN_SMEM) ? room : size_t(K1_MAX_DYN_SMEM);
+    if (need > limit) return RXM_ERR_UNSUPPORTED;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(limit)) != cudaSuccess)
+        return RXM_ERR_CUDA;
+#else
+    (void)kern;
+    (void)need;
+#endif
+    return RXM_OK;
+}
 struct V0 { static constexpr int CH = 64, STAGES = 2, NS = 1; };
 #ifdef RXM_TUNING
 inline int k1_variant() {
@@ -956,8 +975,7 @@ int launch_rows_g(const K1Tables &kt, const K1Launch &a) {
     const size_t smem = size_t(WARPS) * 32 * STAGES * 128;
     static_assert(size_t(WARPS) * 32 * STAGES * 128 <= size_t(K1_MAX_DYN_SMEM), "rows fit the per-function limit");
     auto kern = k1_rows_kernel<REV, L, STAGES, WARPS, MODE>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_MAX_DYN_SMEM) != cudaSuccess)
-        return RXM_ERR_CUDA;
+    if (const int st = k1_set_dyn_smem(kern, smem)) return st;
     const int nb = blocks_per_sm(kern, WARPS * 32, smem);
     if (nb <= 0) return RXM_ERR_CUDA;
     const uint64_t tasks = (a.n + 31) / 32;
@@ -973,8 +991,7 @@ template <bool REV, int L, int CH, int STAGES, int WARPS, class Multi>
 int launch_chunks_w(const K1Tables &kt, const K1Launch &a) {
     const size_t smem = size_t(WARPS) * STAGES * 32 * (CH + 16);
     auto kern = k1_dfa_quad_kernel<REV, L, CH, STAGES, WARPS, Multi>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_MAX_DYN_SMEM) != cudaSuccess)
-        return RXM_ERR_CUDA;
+    if (const int st = k1_set_dyn_smem(kern, smem)) return st;
     const int nb = blocks_per_sm(kern, WARPS * 32, smem);
     if (nb <= 0) return RXM_ERR_CUDA;
     const uint64_t tasks = (a.n + 31) / 32;
@@ -1041,8 +1058,7 @@ template <bool REV>
 int launch_classed(const K1Tables &kt, const K1Launch &a) {
     const size_t smem = size_t(kt.table_bytes) + kt.accept_bytes + 128 + size_t(K1_WARPS) * V0::STAGES * 32 * (V0::CH + 16);
     auto kern = k1_dfa_classed_kernel<REV, V0::CH, V0::STAGES>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_MAX_DYN_SMEM) != cudaSuccess)
-        return RXM_ERR_CUDA;
+    if (const int st = k1_set_dyn_smem(kern, smem)) return st;
     int nb = blocks_per_sm(kern, K1_WARPS * 32, smem);
     if (nb <= 0) return RXM_ERR_CUDA;
     const uint64_t tasks = (a.n + 31) / 32;

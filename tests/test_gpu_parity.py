@@ -3,6 +3,8 @@
 Bit-exact: this is byte/integer work."""
 import ctypes as C
 
+import os
+
 import numpy as np
 import pytest
 
@@ -145,6 +147,33 @@ def test_plan_reports_engine():
     p = m.plan()
     assert rxm.ENGINE_NAMES[p.engine] == "K1_DFA" and 128 < p.dfa_states <= 4096 and p.dfa_stride == 1
     m.close()
+
+
+@pytest.mark.skipif(not os.path.exists(H.RXM_COMPILE), reason="bin/rxm_compile not built")
+@pytest.mark.parametrize("regex,lo,hi", [("(a|b)*a(a|b)(a|b)(a|b)b(a|b)*", 33, 64), ("(a|b)*a(a|b)(a|b)(a|b)(a|b)b(a|b)*", 65, 128),
+                                         ("(a|b|c)*a(a|b|c)(a|b|c)b(a|b|c)*", 33, 64),
+                                         ("(a|b|c)*a(a|b|c)(a|b|c)(a|b|c)b(a|b|c)*", 65, 128)])
+def test_k1_tables_of_33_to_128_sets(regex, lo, hi):
+    """K1 with 16 / 32 KB of static tables next to its 192 KB of rows (SP = 64: T and a stride table; SP = 128: T
+    alone): the kernels' dynamic shared-memory limit must leave room for them (a fixed 216 KB was refused by
+    cudaFuncSetAttribute -- found by tests/fuzz/fuzz_tables_gpu.py); every stride of the automaton against the oracle."""
+    t = rxm.Tables(H.compile_tables_text(regex))
+    rng = np.random.default_rng(21)
+    alpha = np.frombuffer(b"abc" if "c" in regex else b"ab", dtype=np.uint8)
+    strings = [bytes(rng.choice(alpha, size=int(n))) for n in rng.integers(0, 700, size=3000)]
+    strings += [bytes(rng.choice(alpha, size=int(n))) for n in rng.integers(3000, 5000, size=64)]
+    chars, off = H.make_batch(strings)
+    want = H.oracle_bits(t, chars, off)
+    assert 0 < int(want.sum()) < len(want)
+    seen = set()
+    for flags in (0, rxm.OPT_K1_NO_OCT, rxm.OPT_K1_NO_QUAD):
+        m = rxm.Matcher(t, 0, flags=flags)
+        p = m.plan()
+        assert rxm.ENGINE_NAMES[p.engine] == "K1_DFA" and lo <= p.dfa_states <= hi, p.dfa_states
+        seen.add(p.dfa_stride)
+        assert np.array_equal(m.match_host(chars, off), want), (flags, p.dfa_stride)
+        m.close()
+    assert 1 in seen
 
 
 def test_host_offsets_that_run_backwards_are_rejected_and_the_handle_stays_usable():
