@@ -88,8 +88,8 @@ int k1_build_tables(const DfaPlan &p, K1Tables &kt, std::vector<uint8_t> &table,
         }
     } else {
         kt.mode = K1_CLASSED;
-        const size_t bytes = 256 + 2 * size_t(p.n_classes) * p.n_states;
-        if (bytes + kt.accept_bytes > 160 * 1024) {
+        const size_t bytes = k1_classed_table_bytes(p.n_classes, p.n_states);
+        if (!k1_classed_fits(p.n_classes, p.n_states)) {  // (plan_dfa stops there too)
             if (err) *err = "determinised automaton does not fit shared memory";
             return RXM_ERR_UNSUPPORTED;
         }
@@ -1056,7 +1056,9 @@ int launch_direct_l(const K1Tables &kt, const K1Launch &a) {
 
 template <bool REV>
 int launch_classed(const K1Tables &kt, const K1Launch &a) {
-    const size_t smem = size_t(kt.table_bytes) + kt.accept_bytes + 128 + size_t(K1_WARPS) * V0::STAGES * 32 * (V0::CH + 16);
+    constexpr size_t ring = size_t(K1_WARPS) * V0::STAGES * 32 * (V0::CH + 16);
+    static_assert(kK1ClassedBytes + 128 + ring <= size_t(K1_MAX_DYN_SMEM), "the planner's table limit is what this launch can hold");
+    const size_t smem = size_t(kt.table_bytes) + kt.accept_bytes + 128 + ring;
     auto kern = k1_dfa_classed_kernel<REV, V0::CH, V0::STAGES>;
     if (const int st = k1_set_dyn_smem(kern, smem)) return st;
     int nb = blocks_per_sm(kern, K1_WARPS * 32, smem);

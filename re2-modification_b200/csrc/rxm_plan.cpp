@@ -152,8 +152,8 @@ int plan_dfa(const rxm_tables &t, DfaPlan &out, std::string *err) {
             if (nx != nc) out.exact_step_differs++;
             auto it = ids.find(nx);
             if (it == ids.end()) {
-                if (sets.size() >= kMaxDfaStates) {
-                    if (err) *err = "determinised automaton exceeds " + std::to_string(kMaxDfaStates) + " states";
+                if (!k1_classed_fits(out.n_classes, uint32_t(sets.size()) + 1u)) {
+                    if (err) *err = "determinised automaton exceeds " + std::to_string(sets.size()) + " sets: its table does not fit shared memory";
                     return RXM_ERR_UNSUPPORTED;
                 }
                 it = ids.emplace(nx, uint32_t(sets.size())).first;

@@ -35,7 +35,21 @@ struct DfaPlan {
     std::vector<uint8_t> accept;  // [n_states]: finish in the set after the final epsilon pass (:201-209)
 };
 
-constexpr uint32_t kMaxDfaStates = 4096;
+// The determinisation goes on for as long as its table still fits K1's shared memory in the two-lookup form
+// (byte class u8 [256], then [class][set] u16, then one accept byte per set rounded up to 256): ~25 000 sets with
+// three byte classes.  (Round 1 stopped at 4096 sets; the 24 577 sets of `(a|b)*a(a|b)^12 b(a|b)*` went to the
+// bit-set engine at 38 GB/s although their table is 172 KB.)  Set ids are u16: 65 535 at most.
+constexpr uint32_t kMaxDfaStates = 65535;
+// table + accept bytes K1's two-lookup kernel can keep next to its ring: 216 KB of dynamic shared memory less the
+// ring (8 warps x 2 stages x 32 lanes x 80 bytes) and the ring's alignment (rxm_k1.cu: launch_classed asserts it)
+constexpr size_t kK1ClassedBytes = 216 * 1024 - 8 * 2 * 32 * 80 - 128;
+constexpr size_t k1_classed_table_bytes(uint32_t n_classes, uint32_t n_states) {
+    return 256 + 2 * size_t(n_classes) * n_states;
+}
+constexpr size_t k1_accept_bytes(uint32_t n_states) { return (size_t(n_states) + 255) & ~size_t(255); }
+constexpr bool k1_classed_fits(uint32_t n_classes, uint32_t n_states) {
+    return n_states <= kMaxDfaStates && k1_classed_table_bytes(n_classes, n_states) + k1_accept_bytes(n_states) <= kK1ClassedBytes;
+}
 constexpr int kMaxEpsDepth = 256;  // deeper == epsilon cycle: the reference overflows its stack
 
 // RXM_OK, or RXM_ERR_UNSUPPORTED (too many DFA states / epsilon cycle) with *err set.

@@ -47,10 +47,14 @@ NFA_EXPRESSIONS = [
     # an `a`, six letters, a `b`: 2^8 active sets -> more than 128, K1's two-lookup table form (K1_CLASSED)
     ("mid", "(a|b)*a" + "(a|b)" * 6 + "b(a|b)*",
      ["a" + "a" * 6 + "b", "b" * 30, "ab" * 20, "a" * 7 + "b", "a" * 6 + "b", "ba" + "b" * 6 + "ba"]),
-    # an `a`, twelve letters, a `b`: 2^14 active sets in either reading direction -> beyond the
-    # table engine's limit, runs on the bit-set engine (K1B); Thompson branch, 77 nodes
+    # an `a`, twelve letters, a `b`: 24 577 active sets -> the largest table K1 holds in shared memory (172 KB,
+    # two-lookup form); Thompson branch, 77 nodes.  (Round 1's planner stopped at 4096 sets: K1B ran it.)
     ("blowup", "(a|b)*a" + "(a|b)" * 12 + "b(a|b)*",
      ["a" + "a" * 12 + "b", "b" * 30, "ab" * 20, "a" * 13 + "b", "a" * 12 + "b", "ba" + "b" * 12 + "ba"]),
+    # fourteen letters in between: ~98 000 active sets -> no table fits, the planner hands it to the bit-set
+    # engine (K1B); Thompson branch, 89 nodes
+    ("huge", "(a|b)*a" + "(a|b)" * 14 + "b(a|b)*",
+     ["a" + "a" * 14 + "b", "b" * 30, "ab" * 20, "a" * 15 + "b", "a" * 14 + "b", "ba" + "b" * 14 + "ba"]),
 ]
 
 

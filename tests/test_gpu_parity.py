@@ -145,7 +145,7 @@ def test_plan_reports_engine():
     t, _, _ = load_case("nfa_mid")
     m = rxm.Matcher(t, 0)
     p = m.plan()
-    assert rxm.ENGINE_NAMES[p.engine] == "K1_DFA" and 128 < p.dfa_states <= 4096 and p.dfa_stride == 1
+    assert rxm.ENGINE_NAMES[p.engine] == "K1_DFA" and 128 < p.dfa_states <= 4096 and p.dfa_stride == 1  # (257 sets)
     m.close()
 
 
@@ -314,11 +314,13 @@ def test_bitset_engine_on_every_memory_free_fixture(name, mode):
 
 
 def test_planner_hands_large_determinisations_to_the_bitset_engine():
-    """nfa_blowup has 2^14 reachable active sets: no table, K1B instead of RXM_ERR_UNSUPPORTED;
+    """nfa_huge has ~98 000 reachable active sets: no table fits, K1B instead of RXM_ERR_UNSUPPORTED;
     long strings that stay alive, raw-text route included."""
-    t, strings, bits = load_case("nfa_blowup")
+    t, strings, bits = load_case("nfa_huge")
     m = rxm.Matcher(t, 0)
     assert rxm.ENGINE_NAMES[m.plan().engine] == "K1_BITSET"
+    chars, off = H.make_batch(strings)
+    assert np.array_equal(m.match_host(chars, off), bits)
     rng = np.random.default_rng(4)
     ab = np.frombuffer(b"ab", dtype=np.uint8)
     long_strings = [bytes(rng.choice(ab, size=int(L))) for L in rng.integers(1000, 6000, size=64)]
@@ -330,6 +332,38 @@ def test_planner_hands_large_determinisations_to_the_bitset_engine():
     chars, off = _random_batch(rng, 20000, 0, 200, b"ab")
     assert np.array_equal(m.match_host(chars, off), H.oracle_bits(t, chars, off))
     m.close()
+
+
+def test_k1_holds_the_largest_table_that_fits_shared_memory():
+    """nfa_blowup: 24 577 active sets, a 172 KB two-lookup table next to the ring (round 1's planner stopped at 4096
+    sets and K1B ran it at 38 GB/s): golden bits, long strings that stay alive, the raw-text route, a tile-sorted
+    batch -- and the bit-set engine on the same inputs."""
+    t, strings, bits = load_case("nfa_blowup")
+    m = rxm.Matcher(t, 0)
+    p = m.plan()
+    assert rxm.ENGINE_NAMES[p.engine] == "K1_DFA" and p.dfa_states == 24578 and p.dfa_classes == 3 and p.dfa_stride == 1
+    b = rxm.Matcher(t, 0, engine="bitset")
+    assert rxm.ENGINE_NAMES[b.plan().engine] == "K1_BITSET"
+    chars, off = H.make_batch(strings)
+    assert np.array_equal(m.match_host(chars, off), bits)
+    rng = np.random.default_rng(4)
+    ab = np.frombuffer(b"ab", dtype=np.uint8)
+    long_strings = [bytes(rng.choice(ab, size=int(L))) for L in rng.integers(1000, 6000, size=64)]
+    long_strings += [b"b" * 3000, b"a" * 3000, b"b" * 2000 + b"a" + b"b" * 12, b"b" * 2000 + b"a" + b"b" * 13, b"ab" * 7 + b"b" * 4000]
+    chars, off = H.make_batch(long_strings)
+    want = H.oracle_bits(t, chars, off)
+    assert 0 < int(want.sum()) < len(want)
+    assert np.array_equal(m.match_host(chars, off), want)
+    assert np.array_equal(b.match_host(chars, off), want)
+    assert np.array_equal(m.match_text_host(b"\n".join(long_strings)), want)
+    chars, off = _random_batch(rng, 20000, 0, 200, b"ab")
+    want = H.oracle_bits(t, chars, off)
+    assert np.array_equal(m.match_host(chars, off), want)
+    assert np.array_equal(b.match_host(chars, off), want)
+    chars, off = _random_batch(rng, 3000, 0, 60, b"abz.")  # bytes of class 0
+    assert np.array_equal(m.match_host(chars, off), H.oracle_bits(t, chars, off))
+    m.close()
+    b.close()
 
 
 def test_k1_large_batch_properties():
@@ -505,7 +539,7 @@ def test_mfa_large_batch_properties(engine):
     m.close()
 
 
-@pytest.mark.parametrize("name", ["nfa_config2", "ex05_fwd", "ex02_rev", "nfa_blowup"])
+@pytest.mark.parametrize("name", ["nfa_config2", "ex05_fwd", "ex02_rev", "nfa_blowup", "nfa_huge"])
 def test_sharded_1_2_4_8_ways_gives_the_identical_bit_vector(name):
     """the batch cut into 1, 2, 4 and 8 byte-balanced contiguous shards
     (re2-modification_b200/sharding.py -- what each rank of an N-GPU job owns), every shard matched
