@@ -97,6 +97,44 @@ int k1_build_tables(const DfaPlan &p, K1Tables &kt, std::vector<uint8_t> &table,
         for (uint32_t b = 0; b < 256; b++) table[b] = p.byte_class[b];
         uint16_t *tr = reinterpret_cast<uint16_t *>(table.data() + 256);
         for (size_t i = 0; i < p.trans.size(); i++) tr[i] = p.trans[i];
+        // Strides for the two-lookup form: with all literals in a TWO-letter window [lo, lo+1] a letter is one bit,
+        // and the interior of a string takes EIGHT bytes per lookup from O[set][256] u16 (512 bytes per set: up to
+        // ~300 sets) or FOUR from Q[set][16] u16 (32 bytes per set: up to ~4700 sets) -- whichever still fits next to
+        // the per-byte tables, which stay for the first / last vectors and for vectors with a byte outside the window.
+        // Bit i of the code = (byte i of the aligned group, memory order) - lo; composed in READING order.
+        int lit_lo = 256, lit_hi = -1;
+        for (int b = 0; b < 256; b++)
+            if (p.byte_class[b]) {
+                lit_lo = std::min(lit_lo, b);
+                lit_hi = std::max(lit_hi, b);
+            }
+        if (lit_hi >= 0 && lit_hi - lit_lo <= 1 && !no_quad) {
+            const uint32_t lo = uint32_t(std::min(lit_lo, 254));
+            const size_t room = kK1ClassedBytes - kt.accept_bytes;
+            const size_t base = table.size();
+            int letters = 0;
+            if (!no_oct && base + size_t(512) * p.n_states <= room) letters = 8;
+            else if (base + size_t(32) * p.n_states <= room) letters = 4;
+            if (letters) {
+                const uint32_t codes = 1u << letters;
+                kt.quad = letters == 8 ? 2 : 1;
+                kt.quad_lo = lo;
+                kt.multi_off = uint32_t(base);
+                table.resize(base + size_t(2) * codes * p.n_states, 0);
+                uint16_t *mt = reinterpret_cast<uint16_t *>(table.data() + base);
+                tr = reinterpret_cast<uint16_t *>(table.data() + 256);  // (the vector moved)
+                const uint32_t c0 = p.byte_class[lo], c1 = p.byte_class[lo + 1];
+                for (uint32_t q = 0; q < p.n_states; q++)
+                    for (uint32_t code = 0; code < codes; code++) {
+                        uint32_t r = q;
+                        for (int k = 0; k < letters; k++) {
+                            const uint32_t bit = (code >> (p.reversed ? letters - 1 - k : k)) & 1u;
+                            r = tr[size_t(bit ? c1 : c0) * p.n_states + r];
+                        }
+                        mt[size_t(q) * codes + code] = uint16_t(r);
+                    }
+            }
+        }
     }
     kt.table_bytes = uint32_t(table.size());
     return RXM_OK;
@@ -409,6 +447,60 @@ struct OctStep {
         bad = 0;
         return q ^ ((w[0] ^ w[1] ^ w[2] ^ w[3]) & 1u);
 #endif
+        if (!REV) {
+            q = pair(q, w[0], w[1], b);
+            q = pair(q, w[2], w[3], b);
+        } else {
+            q = pair(q, w[2], w[3], b);
+            q = pair(q, w[0], w[1], b);
+        }
+        bad = b & 0xfefefefeu;
+        return q;
+    }
+};
+
+// The same strides for the two-lookup tables (u16 entries, one bit per letter of a two-letter window):
+// four bytes per lookup from Q[set][16], eight from O[set][256].
+struct ClassedQuadStep {
+    static constexpr bool on = true;
+    const uint16_t *Q;
+    uint32_t neg_lo4;
+    __device__ __forceinline__ uint32_t word(uint32_t q, uint32_t w, uint32_t &bad) const {
+        const uint32_t x = w + neg_lo4;
+        bad |= x;
+        return Q[mad_lo(q, 16u, (x * 0x01020408u) >> 24)];  // bits 24..27 <- the four letters, 28..31 stay clear
+    }
+    template <bool REV>
+    __device__ __forceinline__ uint32_t vec(uint32_t q, const uint32_t (&w)[4], uint32_t &bad) const {
+        uint32_t b = 0;
+        if (!REV) {
+            q = word(q, w[0], b);
+            q = word(q, w[1], b);
+            q = word(q, w[2], b);
+            q = word(q, w[3], b);
+        } else {
+            q = word(q, w[3], b);
+            q = word(q, w[2], b);
+            q = word(q, w[1], b);
+            q = word(q, w[0], b);
+        }
+        bad = b & 0xfefefefeu;
+        return q;
+    }
+};
+struct ClassedOctStep {
+    static constexpr bool on = true;
+    const uint16_t *Q;
+    uint32_t neg_lo4;
+    __device__ __forceinline__ uint32_t pair(uint32_t q, uint32_t w0, uint32_t w1, uint32_t &bad) const {
+        const uint32_t x0 = w0 + neg_lo4, x1 = w1 + neg_lo4;
+        bad |= x0 | x1;
+        const uint32_t code = mad_lo(x1, 0x10204080u, x0 * 0x01020408u) >> 24;
+        return Q[mad_lo(q, 256u, code)];
+    }
+    template <bool REV>
+    __device__ __forceinline__ uint32_t vec(uint32_t q, const uint32_t (&w)[4], uint32_t &bad) const {
+        uint32_t b = 0;
         if (!REV) {
             q = pair(q, w[0], w[1], b);
             q = pair(q, w[2], w[3], b);
@@ -902,12 +994,13 @@ k1_dfa_quad_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict__ 
 }
 #endif
 
-template <bool REV, int CH, int STAGES>
+// MODE 0: one byte per (two-step) lookup, 1: four bytes (Q at multi_off), 2: eight bytes (O at multi_off)
+template <bool REV, int CH, int STAGES, int MODE>
 __global__ void __launch_bounds__(K1_WARPS * 32)
 k1_dfa_classed_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict__ recs, uint64_t n,
                       uint8_t *__restrict__ out, const uint8_t *__restrict__ g_table, uint32_t table_bytes,
                       const uint8_t *__restrict__ g_accept, uint32_t accept_bytes, uint32_t n_states,
-                      uint32_t start, uint32_t *__restrict__ task_counter) {
+                      uint32_t start, uint32_t multi_off, uint32_t quad_lo, uint32_t *__restrict__ task_counter) {
     RXM_DYN_SMEM_128(smem);
     const uint4 *s4 = reinterpret_cast<const uint4 *>(g_table);
     uint4 *d4 = reinterpret_cast<uint4 *>(smem);
@@ -917,8 +1010,19 @@ k1_dfa_classed_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict
     const uint32_t sbase = uint32_t(__cvta_generic_to_shared(smem));
     const uint32_t ring0 = (sbase + table_bytes + accept_bytes + 127u) & ~127u;
     const ClassedStep st{smem, reinterpret_cast<const uint16_t *>(smem + 256), n_states};
-    k1_scan_body<REV, ClassedStep, CH, STAGES, 1>(st, NoQuad(), chars, recs, n, out, smem + table_bytes, start, task_counter,
-                                                  ring0 + (threadIdx.x >> 5) * (STAGES * 32 * (CH + 16)));
+    const uint32_t my_ring = ring0 + (threadIdx.x >> 5) * (STAGES * 32 * (CH + 16));
+    if constexpr (MODE == 2) {
+        const ClassedOctStep qd{reinterpret_cast<const uint16_t *>(smem + multi_off), 0u - quad_lo * 0x01010101u};
+        k1_scan_body<REV, ClassedStep, CH, STAGES, 1, ClassedOctStep>(st, qd, chars, recs, n, out, smem + table_bytes, start,
+                                                                      task_counter, my_ring);
+    } else if constexpr (MODE == 1) {
+        const ClassedQuadStep qd{reinterpret_cast<const uint16_t *>(smem + multi_off), 0u - quad_lo * 0x01010101u};
+        k1_scan_body<REV, ClassedStep, CH, STAGES, 1, ClassedQuadStep>(st, qd, chars, recs, n, out, smem + table_bytes, start,
+                                                                       task_counter, my_ring);
+    } else {
+        k1_scan_body<REV, ClassedStep, CH, STAGES, 1>(st, NoQuad(), chars, recs, n, out, smem + table_bytes, start, task_counter,
+                                                      my_ring);
+    }
 }
 
 // Geometry.  The product library holds ONE geometry per kernel: rows of 3 lines, 16 warps per CTA (one CTA per SM:
@@ -1054,12 +1158,12 @@ int launch_direct_l(const K1Tables &kt, const K1Launch &a) {
     }
 }
 
-template <bool REV>
-int launch_classed(const K1Tables &kt, const K1Launch &a) {
+template <bool REV, int MODE>
+int launch_classed_m(const K1Tables &kt, const K1Launch &a) {
     constexpr size_t ring = size_t(K1_WARPS) * V0::STAGES * 32 * (V0::CH + 16);
     static_assert(kK1ClassedBytes + 128 + ring <= size_t(K1_MAX_DYN_SMEM), "the planner's table limit is what this launch can hold");
     const size_t smem = size_t(kt.table_bytes) + kt.accept_bytes + 128 + ring;
-    auto kern = k1_dfa_classed_kernel<REV, V0::CH, V0::STAGES>;
+    auto kern = k1_dfa_classed_kernel<REV, V0::CH, V0::STAGES, MODE>;
     if (const int st = k1_set_dyn_smem(kern, smem)) return st;
     int nb = blocks_per_sm(kern, K1_WARPS * 32, smem);
     if (nb <= 0) return RXM_ERR_CUDA;
@@ -1067,8 +1171,14 @@ int launch_classed(const K1Tables &kt, const K1Launch &a) {
     uint64_t blocks = uint64_t(a.sm_count) * nb;
     const uint64_t need = (tasks + K1_WARPS - 1) / K1_WARPS;
     if (blocks > need) blocks = need;
-    RXM_LAUNCH(kern, unsigned(blocks), K1_WARPS * 32, smem, a.stream, a.d_chars, a.d_recs, a.n, a.d_out, a.d_table, kt.table_bytes, a.d_accept, kt.accept_bytes, kt.n_states, kt.start, a.d_task_counter);
+    RXM_LAUNCH(kern, unsigned(blocks), K1_WARPS * 32, smem, a.stream, a.d_chars, a.d_recs, a.n, a.d_out, a.d_table, kt.table_bytes, a.d_accept, kt.accept_bytes, kt.n_states, kt.start, kt.multi_off, kt.quad_lo, a.d_task_counter);
     return RXM_OK;
+}
+template <bool REV>
+int launch_classed(const K1Tables &kt, const K1Launch &a) {
+    if (kt.quad == 2) return launch_classed_m<REV, 2>(kt, a);
+    if (kt.quad == 1) return launch_classed_m<REV, 1>(kt, a);
+    return launch_classed_m<REV, 0>(kt, a);
 }
 
 }  // namespace

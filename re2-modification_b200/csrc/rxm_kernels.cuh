@@ -47,8 +47,11 @@ struct K1Tables {
     uint32_t table_bytes;  // bytes of the device table blob (copied to shared memory)
     uint32_t accept_bytes;
     uint32_t quad;         // K1_DIRECT with SP <= 64: 1 = the quad table Q[SP][256] (four bytes per lookup, 4-letter
-                           // window) follows T in the blob, 2 = the oct table O[SP][256] (eight bytes, 2-letter window)
+                           // window) follows T in the blob, 2 = the oct table O[SP][256] (eight bytes, 2-letter window).
+                           // K1_CLASSED with a 2-letter window: 1 = Q[n_states][16] u16 (four bytes per lookup, one bit
+                           // per letter), 2 = O[n_states][256] u16 (eight bytes), at multi_off in the blob
     uint32_t quad_lo;      // lowest byte value of the window
+    uint32_t multi_off;    // K1_CLASSED: byte offset of the stride table in the blob (16-byte aligned)
 };
 
 int k1_build_tables(const DfaPlan &p, K1Tables &kt, std::vector<uint8_t> &table,

@@ -145,7 +145,7 @@ def test_plan_reports_engine():
     t, _, _ = load_case("nfa_mid")
     m = rxm.Matcher(t, 0)
     p = m.plan()
-    assert rxm.ENGINE_NAMES[p.engine] == "K1_DFA" and 128 < p.dfa_states <= 4096 and p.dfa_stride == 1  # (257 sets)
+    assert rxm.ENGINE_NAMES[p.engine] == "K1_DFA" and p.dfa_states == 386 and p.dfa_stride == 4  # Q[set][16]: four bytes per lookup
     m.close()
 
 
@@ -332,6 +332,37 @@ def test_planner_hands_large_determinisations_to_the_bitset_engine():
     chars, off = _random_batch(rng, 20000, 0, 200, b"ab")
     assert np.array_equal(m.match_host(chars, off), H.oracle_bits(t, chars, off))
     m.close()
+
+
+@pytest.mark.skipif(not os.path.exists(H.RXM_COMPILE), reason="bin/rxm_compile not built")
+@pytest.mark.parametrize("regex,sets,stride", [("(a|b)*a" + "(a|b)" * 5 + "b(a|b)*", 194, 8),
+                                               ("(b|a)*a" + "(a|b)" * 8 + "(a|b)*abb", 1218, 4)])
+@pytest.mark.parametrize("right_to_left", [0, 1])
+def test_k1_two_lookup_tables_with_strides(regex, sets, stride, right_to_left):
+    """K1's two-lookup form (more than 128 sets) with a stride table for two-letter windows (eight bytes per lookup
+    while 512 bytes per set fit shared memory, else four): every stride against the oracle, forward and with the
+    tables read right-to-left; bytes outside the window, long strings, a tile-sorted batch."""
+    text = H.compile_tables_text(regex)
+    if right_to_left:
+        text = text.replace("reversed 0", "reversed 1")
+    t = rxm.Tables(text)
+    rng = np.random.default_rng(6)
+    ab, abz = np.frombuffer(b"ab", dtype=np.uint8), np.frombuffer(b"abbaz", dtype=np.uint8)
+    strings = [bytes(rng.choice(ab, size=int(n))) for n in rng.integers(0, 300, size=18000)]
+    strings += [bytes(rng.choice(abz, size=int(n))) for n in rng.integers(0, 200, size=1500)]
+    strings += [bytes(rng.choice(ab, size=int(n))) for n in rng.integers(3000, 6000, size=64)]
+    chars, off = H.make_batch(strings)
+    want = H.oracle_bits(t, chars, off)
+    assert 0 < int(want.sum()) < len(want)
+    seen = []
+    for flags in (0, rxm.OPT_K1_NO_OCT, rxm.OPT_K1_NO_QUAD):
+        m = rxm.Matcher(t, 0, flags=flags)
+        p = m.plan()
+        assert rxm.ENGINE_NAMES[p.engine] == "K1_DFA" and p.dfa_states == sets
+        seen.append(p.dfa_stride)
+        assert np.array_equal(m.match_host(chars, off), want), (flags, p.dfa_stride)
+        m.close()
+    assert seen == [stride, 4, 1]
 
 
 def test_k1_holds_the_largest_table_that_fits_shared_memory():
