@@ -76,8 +76,23 @@ k1b_bitset_kernel(const uint16_t *__restrict__ g_eb, const uint32_t *__restrict_
     }
 }
 
+__device__ __forceinline__ uint4 k1b_ld128(const uint8_t *p) {  // p is 16-byte aligned
+#if defined(__CUDA_ARCH__)
+    return __ldg(reinterpret_cast<const uint4 *>(p));
+#else
+#ifdef RXM_SIMT_HOST  // the emulator reports what the device would fault on
+    if (reinterpret_cast<uintptr_t>(p) & 15u) simt::fail(4, "misaligned 16-byte global load");
+#endif
+    return *reinterpret_cast<const uint4 *>(p);
+#endif
+}
+__device__ __forceinline__ uint32_t k1b_vec_byte(const uint4 &v, uint32_t j) {  // byte j (memory order) of a vector
+    const uint32_t w = (j & 8u) ? ((j & 4u) ? v.w : v.z) : ((j & 4u) ? v.y : v.x);
+    return (w >> ((j & 3u) * 8u)) & 0xffu;
+}
+
 // Bit-parallel form (rxm_plan.hpp: BitsetMasks): per input byte one class lookup and, per root of
-// the active set, two 64-bit follow-mask words from shared memory -- no edge walk, no stack.
+// the active set, one 16-byte follow-mask row from shared memory -- no edge walk, no stack.
 __global__ void __launch_bounds__(K1B_THREADS)
 k1b_mask_kernel(const uint64_t *__restrict__ g_ls, const uint8_t *__restrict__ g_class, uint32_t n_states,
                 uint32_t n_classes, uint32_t start, uint64_t acc_lo, uint64_t acc_hi, uint32_t reversed,
@@ -117,9 +132,24 @@ k1b_mask_kernel(const uint64_t *__restrict__ g_ls, const uint8_t *__restrict__ g
         const uint32_t len = uint32_t(e - b);
         Bits128 S{0, 0};
         S.set(start);  // automata.cpp:178-179
-        for (uint32_t k = 0; k < len && !S.empty(); k++) {  // :181-200, break on the empty set (:186-188)
-            const uint32_t byte = reversed ? s[len - 1u - k] : s[k];
-            S = nfa_mask_step(ls + size_t(bc[byte]) * n_states * 2, S);
+        // :181-200, break on the empty set (:186-188).  The string is read in aligned 16-byte vectors (only those that
+        // hold a byte of it), forward from its first byte or downwards from its last.
+        for (uint32_t k = 0; k < len && !S.empty();) {
+            const uint8_t *at = reversed ? s + (len - 1u - k) : s + k;  // the next byte read
+            const uint32_t o = uint32_t(reinterpret_cast<uintptr_t>(at) & 15u);
+            const uint4 v = k1b_ld128(at - o);
+            const uint32_t left = len - k;
+            if (!reversed) {
+                const uint32_t hi = o + left < 16u ? o + left : 16u;
+                for (uint32_t j = o; j < hi && !S.empty(); j++)
+                    S = nfa_mask_step(ls + size_t(bc[k1b_vec_byte(v, j)]) * n_states * 2, S);
+                k += hi - o;
+            } else {
+                const uint32_t take = o + 1u < left ? o + 1u : left;  // bytes o, o-1, ... of the vector
+                for (uint32_t j = 0; j < take && !S.empty(); j++)
+                    S = nfa_mask_step(ls + size_t(bc[k1b_vec_byte(v, o - j)]) * n_states * 2, S);
+                k += take;
+            }
         }
         out[i] = ((S.lo & acc_lo) | (S.hi & acc_hi)) ? 1 : 0;  // :201-209
     }
