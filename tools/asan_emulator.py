@@ -60,7 +60,13 @@ def main():
         want = H.oracle_bits(t, *[np.ascontiguousarray(x) for x in H.make_batch(batch)])
         for shift in (0, 5, 17):
             if kind == "nfa":
-                if name == "nfa_huge":  # no table: K1B
+                # K1B, follow masks: the string in aligned 16-byte vectors, forward or downwards from its end
+                ovf = C.c_ulonglong(0)
+                rc, got, msg = run(L.hostsim_k1b_batch, t, batch, C.c_int(0), None, C.c_uint64(400_000_000), C.byref(ovf),
+                                   shift=shift)
+                assert rc == 0 and np.array_equal(got, want), (name, "k1b", rc, msg)
+                runs += 1
+                if name == "nfa_huge":  # no table fits: K1B only
                     continue
                 info = (C.c_uint32 * 3)()
                 ovf = C.c_ulonglong(0)

@@ -15,7 +15,10 @@ chars = (torch.randint(0, 2, (int(off[-1]),), device="cuda", generator=rng) + 97
 out = torch.empty(n, dtype=torch.uint8, device="cuda")
 s = torch.cuda.current_stream().cuda_stream
 ref = {}
+only = sys.argv[2].split(",") if len(sys.argv) > 2 else None  # e.g. nfa_mid (for an ncu capture of one kernel)
 for case, engine in (("nfa_blowup", None), ("nfa_blowup", "bitset"), ("nfa_huge", None), ("nfa_mid", None)):
+    if only and case not in only:
+        continue
     t = rxm.Tables.load(os.path.join(ROOT, "tests", "golden", "cases", case + ".rxt"))
     m = rxm.Matcher(t, 0, engine=engine)
     p = m.plan()
