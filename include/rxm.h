@@ -129,9 +129,9 @@ typedef struct rxm_plan_info {
     uint32_t sm_count;
     uint32_t dfa_stride;    /* K1_DFA: input bytes per table lookup in the scan's interior: 1; 4 when all
                                literals lie in one 4-letter window and there are <= 64 sets; 8 when the
-                               window has two letters.  More than 128 sets (two-lookup tables) with a
-                               two-letter window: 8 while the stride table fits shared memory (~300 sets),
-                               else 4 (~4700 sets), else 1                                             */
+                               window has two letters.  Two-lookup tables (more than 128 sets; more than
+                               64 with a two-letter window): 4 with a two-letter window while the stride
+                               table fits shared memory (~4700 sets), else 1                           */
     uint32_t reserved[6];
 } rxm_plan_info;
 

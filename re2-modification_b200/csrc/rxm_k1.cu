@@ -34,7 +34,17 @@ int k1_build_tables(const DfaPlan &p, K1Tables &kt, std::vector<uint8_t> &table,
     accept.assign(p.accept.begin(), p.accept.end());
     while (accept.size() % 256) accept.push_back(0);
     kt.accept_bytes = uint32_t(accept.size());
-    if (p.n_states <= 128) {  // direct table (static shared memory, <= 32 KB)
+    int lit_lo = 256, lit_hi = -1;  // the window of the literal bytes
+    for (int b = 0; b < 256; b++)
+        if (p.byte_class[b]) {
+            lit_lo = std::min(lit_lo, b);
+            lit_hi = std::max(lit_hi, b);
+        }
+    // 65 - 128 sets over a two-letter window: the direct table has no room for a stride table (T and O / Q [128][256]
+    // would be 64 KB of static shared memory next to 192 KB of rows), the two-lookup form has (Q[set][16] u16, 4 KB) --
+    // measured on a 98-set automaton, 200 k strings: 0.194 ms per byte on the rows, 0.13 ms with four bytes per lookup
+    const bool small_window_mid = p.n_states > 64 && lit_hi >= 0 && lit_hi - lit_lo <= 1 && !no_quad;
+    if (p.n_states <= 128 && !small_window_mid) {  // direct table (static shared memory, <= 32 KB)
         uint32_t l = 4;
         while ((1u << l) < p.n_states) l++;
         kt.mode = K1_DIRECT;
@@ -50,12 +60,6 @@ int k1_build_tables(const DfaPlan &p, K1Tables &kt, std::vector<uint8_t> &table,
         // composed in READING order (right-to-left automata read byte 3 first).  A byte outside
         // the window sends its 16-byte vector to the per-byte table, so every input gets the
         // same answer as with the per-byte scan.
-        int lit_lo = 256, lit_hi = -1;
-        for (int b = 0; b < 256; b++)
-            if (p.byte_class[b]) {
-                lit_lo = std::min(lit_lo, b);
-                lit_hi = std::max(lit_hi, b);
-            }
         if (lit_hi < 0) lit_lo = lit_hi = 'a';
         // Oct stride: with all literals in a TWO-letter window [lo, lo+1] a letter is one bit, and the
         // interior takes EIGHT input bytes per lookup: O[q][code], bit i of code = (byte i of the aligned
@@ -97,41 +101,32 @@ int k1_build_tables(const DfaPlan &p, K1Tables &kt, std::vector<uint8_t> &table,
         for (uint32_t b = 0; b < 256; b++) table[b] = p.byte_class[b];
         uint16_t *tr = reinterpret_cast<uint16_t *>(table.data() + 256);
         for (size_t i = 0; i < p.trans.size(); i++) tr[i] = p.trans[i];
-        // Strides for the two-lookup form: with all literals in a TWO-letter window [lo, lo+1] a letter is one bit,
-        // and the interior of a string takes EIGHT bytes per lookup from O[set][256] u16 (512 bytes per set: up to
-        // ~300 sets) or FOUR from Q[set][16] u16 (32 bytes per set: up to ~4700 sets) -- whichever still fits next to
-        // the per-byte tables, which stay for the first / last vectors and for vectors with a byte outside the window.
-        // Bit i of the code = (byte i of the aligned group, memory order) - lo; composed in READING order.
-        int lit_lo = 256, lit_hi = -1;
-        for (int b = 0; b < 256; b++)
-            if (p.byte_class[b]) {
-                lit_lo = std::min(lit_lo, b);
-                lit_hi = std::max(lit_hi, b);
-            }
+        // A stride for the two-lookup form: with all literals in a TWO-letter window [lo, lo+1] a letter is one bit,
+        // and the interior of a string takes FOUR bytes per lookup from Q[set][16] u16 (32 bytes per set: up to ~4700
+        // sets) if that still fits next to the per-byte tables, which stay for the first / last vectors and for vectors
+        // with a byte outside the window.  Bit i of the code = (byte i of the aligned word, memory order) - lo; composed
+        // in READING order.  (Eight bytes per lookup from O[set][256] u16 was built and measured: 512 bytes per set leave
+        // one CTA per SM where Q leaves four -- 194 sets: 0.179 ms against 0.130 ms per 200 k strings.  Not kept.)
         if (lit_hi >= 0 && lit_hi - lit_lo <= 1 && !no_quad) {
             const uint32_t lo = uint32_t(std::min(lit_lo, 254));
             const size_t room = kK1ClassedBytes - kt.accept_bytes;
             const size_t base = table.size();
-            int letters = 0;
-            if (!no_oct && base + size_t(512) * p.n_states <= room) letters = 8;
-            else if (base + size_t(32) * p.n_states <= room) letters = 4;
-            if (letters) {
-                const uint32_t codes = 1u << letters;
-                kt.quad = letters == 8 ? 2 : 1;
+            if (base + size_t(32) * p.n_states <= room) {
+                kt.quad = 1;
                 kt.quad_lo = lo;
                 kt.multi_off = uint32_t(base);
-                table.resize(base + size_t(2) * codes * p.n_states, 0);
+                table.resize(base + size_t(32) * p.n_states, 0);
                 uint16_t *mt = reinterpret_cast<uint16_t *>(table.data() + base);
                 tr = reinterpret_cast<uint16_t *>(table.data() + 256);  // (the vector moved)
                 const uint32_t c0 = p.byte_class[lo], c1 = p.byte_class[lo + 1];
                 for (uint32_t q = 0; q < p.n_states; q++)
-                    for (uint32_t code = 0; code < codes; code++) {
+                    for (uint32_t code = 0; code < 16; code++) {
                         uint32_t r = q;
-                        for (int k = 0; k < letters; k++) {
-                            const uint32_t bit = (code >> (p.reversed ? letters - 1 - k : k)) & 1u;
+                        for (int k = 0; k < 4; k++) {
+                            const uint32_t bit = (code >> (p.reversed ? 3 - k : k)) & 1u;
                             r = tr[size_t(bit ? c1 : c0) * p.n_states + r];
                         }
-                        mt[size_t(q) * codes + code] = uint16_t(r);
+                        mt[size_t(q) * 16 + code] = uint16_t(r);
                     }
             }
         }
@@ -459,8 +454,8 @@ struct OctStep {
     }
 };
 
-// The same strides for the two-lookup tables (u16 entries, one bit per letter of a two-letter window):
-// four bytes per lookup from Q[set][16], eight from O[set][256].
+// The quad stride for the two-lookup tables (u16 entries, one bit per letter of a two-letter window): four bytes per
+// lookup from Q[set][16].
 struct ClassedQuadStep {
     static constexpr bool on = true;
     const uint16_t *Q;
@@ -488,31 +483,6 @@ struct ClassedQuadStep {
         return q;
     }
 };
-struct ClassedOctStep {
-    static constexpr bool on = true;
-    const uint16_t *Q;
-    uint32_t neg_lo4;
-    __device__ __forceinline__ uint32_t pair(uint32_t q, uint32_t w0, uint32_t w1, uint32_t &bad) const {
-        const uint32_t x0 = w0 + neg_lo4, x1 = w1 + neg_lo4;
-        bad |= x0 | x1;
-        const uint32_t code = mad_lo(x1, 0x10204080u, x0 * 0x01020408u) >> 24;
-        return Q[mad_lo(q, 256u, code)];
-    }
-    template <bool REV>
-    __device__ __forceinline__ uint32_t vec(uint32_t q, const uint32_t (&w)[4], uint32_t &bad) const {
-        uint32_t b = 0;
-        if (!REV) {
-            q = pair(q, w[0], w[1], b);
-            q = pair(q, w[2], w[3], b);
-        } else {
-            q = pair(q, w[2], w[3], b);
-            q = pair(q, w[0], w[1], b);
-        }
-        bad = b & 0xfefefefeu;
-        return q;
-    }
-};
-
 template <bool REV>
 __device__ __forceinline__ uint32_t vec_byte(const uint32_t (&w)[4], int k) {  // k-th byte in READING order
     const int mb = REV ? 15 - k : k;
@@ -994,7 +964,7 @@ k1_dfa_quad_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict__ 
 }
 #endif
 
-// MODE 0: one byte per (two-step) lookup, 1: four bytes (Q at multi_off), 2: eight bytes (O at multi_off)
+// MODE 0: one byte per (two-step) lookup, 1: four bytes (Q at multi_off)
 template <bool REV, int CH, int STAGES, int MODE>
 __global__ void __launch_bounds__(K1_WARPS * 32)
 k1_dfa_classed_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict__ recs, uint64_t n,
@@ -1011,11 +981,7 @@ k1_dfa_classed_kernel(const uint8_t *__restrict__ chars, const K1Rec *__restrict
     const uint32_t ring0 = (sbase + table_bytes + accept_bytes + 127u) & ~127u;
     const ClassedStep st{smem, reinterpret_cast<const uint16_t *>(smem + 256), n_states};
     const uint32_t my_ring = ring0 + (threadIdx.x >> 5) * (STAGES * 32 * (CH + 16));
-    if constexpr (MODE == 2) {
-        const ClassedOctStep qd{reinterpret_cast<const uint16_t *>(smem + multi_off), 0u - quad_lo * 0x01010101u};
-        k1_scan_body<REV, ClassedStep, CH, STAGES, 1, ClassedOctStep>(st, qd, chars, recs, n, out, smem + table_bytes, start,
-                                                                      task_counter, my_ring);
-    } else if constexpr (MODE == 1) {
+    if constexpr (MODE == 1) {
         const ClassedQuadStep qd{reinterpret_cast<const uint16_t *>(smem + multi_off), 0u - quad_lo * 0x01010101u};
         k1_scan_body<REV, ClassedStep, CH, STAGES, 1, ClassedQuadStep>(st, qd, chars, recs, n, out, smem + table_bytes, start,
                                                                        task_counter, my_ring);
@@ -1176,7 +1142,6 @@ int launch_classed_m(const K1Tables &kt, const K1Launch &a) {
 }
 template <bool REV>
 int launch_classed(const K1Tables &kt, const K1Launch &a) {
-    if (kt.quad == 2) return launch_classed_m<REV, 2>(kt, a);
     if (kt.quad == 1) return launch_classed_m<REV, 1>(kt, a);
     return launch_classed_m<REV, 0>(kt, a);
 }

@@ -49,7 +49,7 @@ struct K1Tables {
     uint32_t quad;         // K1_DIRECT with SP <= 64: 1 = the quad table Q[SP][256] (four bytes per lookup, 4-letter
                            // window) follows T in the blob, 2 = the oct table O[SP][256] (eight bytes, 2-letter window).
                            // K1_CLASSED with a 2-letter window: 1 = Q[n_states][16] u16 (four bytes per lookup, one bit
-                           // per letter), 2 = O[n_states][256] u16 (eight bytes), at multi_off in the blob
+                           // per letter) at multi_off in the blob
     uint32_t quad_lo;      // lowest byte value of the window
     uint32_t multi_off;    // K1_CLASSED: byte offset of the stride table in the blob (16-byte aligned)
 };

@@ -335,13 +335,14 @@ def test_planner_hands_large_determinisations_to_the_bitset_engine():
 
 
 @pytest.mark.skipif(not os.path.exists(H.RXM_COMPILE), reason="bin/rxm_compile not built")
-@pytest.mark.parametrize("regex,sets,stride", [("(a|b)*a" + "(a|b)" * 5 + "b(a|b)*", 194, 8),
+@pytest.mark.parametrize("regex,sets,stride", [("(a|b)*a" + "(a|b)" * 4 + "b(a|b)*", 98, 4),
+                                               ("(a|b)*a" + "(a|b)" * 5 + "b(a|b)*", 194, 4),
                                                ("(b|a)*a" + "(a|b)" * 8 + "(a|b)*abb", 1218, 4)])
 @pytest.mark.parametrize("right_to_left", [0, 1])
 def test_k1_two_lookup_tables_with_strides(regex, sets, stride, right_to_left):
-    """K1's two-lookup form (more than 128 sets) with a stride table for two-letter windows (eight bytes per lookup
-    while 512 bytes per set fit shared memory, else four): every stride against the oracle, forward and with the
-    tables read right-to-left; bytes outside the window, long strings, a tile-sorted batch."""
+    """K1's two-lookup form (more than 64 sets over a two-letter window, more than 128 otherwise) with its stride
+    table (four bytes per lookup): both strides against the oracle, forward and with the tables read right-to-left;
+    bytes outside the window, long strings, a tile-sorted batch."""
     text = H.compile_tables_text(regex)
     if right_to_left:
         text = text.replace("reversed 0", "reversed 1")
@@ -362,7 +363,7 @@ def test_k1_two_lookup_tables_with_strides(regex, sets, stride, right_to_left):
         seen.append(p.dfa_stride)
         assert np.array_equal(m.match_host(chars, off), want), (flags, p.dfa_stride)
         m.close()
-    assert seen == [stride, 4, 1]
+    assert seen == [stride, stride, 1]
 
 
 def test_k1_holds_the_largest_table_that_fits_shared_memory():

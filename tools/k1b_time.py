@@ -16,11 +16,14 @@ out = torch.empty(n, dtype=torch.uint8, device="cuda")
 s = torch.cuda.current_stream().cuda_stream
 ref = {}
 only = sys.argv[2].split(",") if len(sys.argv) > 2 else None  # e.g. nfa_mid (for an ncu capture of one kernel)
-for case, engine in (("nfa_blowup", None), ("nfa_blowup", "bitset"), ("nfa_huge", None), ("nfa_mid", None)):
+cases = [("nfa_blowup", None), ("nfa_blowup", "bitset"), ("nfa_huge", None), ("nfa_mid", None)]
+if only and any(c.endswith(".rxt") for c in only):  # table files (tools/build/*.rxt) on the planner's engine
+    cases = [(c, None) for c in only]
+for case, engine in cases:
     if only and case not in only:
         continue
-    t = rxm.Tables.load(os.path.join(ROOT, "tests", "golden", "cases", case + ".rxt"))
-    m = rxm.Matcher(t, 0, engine=engine)
+    t = rxm.Tables.load(case if case.endswith(".rxt") else os.path.join(ROOT, "tests", "golden", "cases", case + ".rxt"))
+    m = rxm.Matcher(t, 0, engine=engine, flags=int(os.environ.get("RXM_K1_FLAGS", "0")))
     p = m.plan()
     for _ in range(2):
         m.match_ptrs(chars.data_ptr(), off.data_ptr(), n, out.data_ptr(), s)
