@@ -619,6 +619,51 @@ def extra_workload(W, rxm, H, wl, strings, steps, dev, local_rank, seed):
     return res
 
 
+def large_table_workloads(rxm, H, dev, steps=3, n=200_000):
+    """Memory-free automata with large determinisations, briefly, in the default run (not a BASELINE config; the
+    planner's regimes beyond config 2's 13 sets): 386 sets (two-lookup table with its four-byte stride), 24 577 sets
+    (the largest table K1 holds in shared memory), ~98 000 sets (no table: the bit-set engine K1B).  200 k random
+    {a, b} strings of 64-4096 letters, device-resident, CUDA events on the launching stream; parity spot check against
+    the C restatement outside the timed region."""
+    import torch
+    g = torch.Generator(device=dev).manual_seed(1)
+    lens = torch.randint(64, 4097, (n,), device=dev, generator=g)
+    off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    off[1:] = torch.cumsum(lens, 0)
+    total = int(off[-1])
+    chars = torch.empty(total + 64, dtype=torch.uint8, device=dev)
+    chars[:total] = (torch.randint(0, 2, (total,), device=dev, generator=g) + 97).to(torch.uint8)
+    out = torch.empty(n, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    peak, _ = hbm_peak()
+    res = []
+    for case in ("nfa_mid", "nfa_blowup", "nfa_huge"):
+        t = rxm.Tables.load(os.path.join(ROOT, "tests", "golden", "cases", case + ".rxt"))
+        m = rxm.Matcher(t, dev.index or 0)
+        p = m.plan()
+        for _ in range(2):
+            m.match_ptrs(chars.data_ptr(), off.data_ptr(), n, out.data_ptr(), stream)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            m.match_ptrs(chars.data_ptr(), off.data_ptr(), n, out.data_ptr(), stream)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        job = {"name": case, "n": n, "bytes": total, "offsets": off, "chars": chars, "out": out, "tables": t}
+        checked = parity_spot_check([job], H)
+        res.append({"automaton": case, "engine": rxm.ENGINE_NAMES.get(p.engine, "?"), "active_sets": int(p.dfa_states),
+                    "bytes_per_lookup": int(p.dfa_stride), "strings": n, "bytes": total, "steps": steps, "ms_per_step": ms,
+                    "strings_per_sec": n / (ms / 1e3), "input_gb_s": total / (ms / 1e3) / 1e9,
+                    "roofline_frac": (total + 9 * n) / (ms / 1e3) / 1e9 / peak, "parity_checked": checked,
+                    "match_fraction": float(out.float().mean().item())})
+        m.close()
+    del chars, off, out
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -1009,6 +1054,10 @@ def main():
             wk = {}
             for xwl, xs, xn in (("config3", 3, 1_000_000), ("config4", 2, 4096), ("config5", 3, 1_000_000)):
                 wk[xwl] = extra_workload(W, rxm, H, xwl, xn, xs, dev, local_rank, 1000)
+            try:  # (an extra: a failure here must not take the headline line with it; a parity difference still does)
+                wk["memory_free_large_tables"] = large_table_workloads(rxm, H, dev)
+            except Exception as e:  # noqa: BLE001
+                wk["memory_free_large_tables"] = {"error": repr(e)}
             line["workloads"] = wk
         print(json.dumps(line), file=RESULT_OUT, flush=True)
     if world > 1:
