@@ -1,5 +1,5 @@
-# one gpurun call: the GPU test tier, smoke, the default bench line and the reference arm, one ncu capture of the
-# two-lookup K1 kernel with its stride table (nfa_mid), the large-table timings
+# one gpurun call: the GPU test tier, smoke, the default bench line and the reference arm, the
+# large-table timings
 T=${1:-final4}
 set -x
 python -m pytest tests -m gpu -q > gpurun_out/r02_gputest_$T.log 2>&1; tail -3 gpurun_out/r02_gputest_$T.log
@@ -7,4 +7,3 @@ python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke_$T.log
 python bench.py > gpurun_out/r02_bench_$T.json 2> gpurun_out/r02_bench_$T.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02_bench_${T}_reference_arm.json 2> gpurun_out/r02_bench_${T}_reference_arm.err; echo "reference arm rc=$?"
 python tools/k1b_time.py > gpurun_out/r02_k1_large_tables_$T.log 2>&1; cat gpurun_out/r02_k1_large_tables_$T.log
-ncu --set full --clock-control none --import-source on -k regex:k1_dfa_classed -c 1 -s 2 -o gpurun_out/r02_k1_classed_$T python tools/k1b_time.py 200000 nfa_mid > gpurun_out/r02_k1_classed_${T}_ncu.log 2>&1; echo "ncu classed rc=$?"
